@@ -1,0 +1,137 @@
+/* liblafs_b200 -- C ABI of the B200-native LAFS hot path.
+ *
+ * The reference (szlbiubiubiu/LAFS_CVPR2024) is pure Python/PyTorch and has no FFI of its
+ * own; the drop-in boundary is its Python module surface.  The Python
+ * classes in lafs_cvpr2024_b200/ keep that surface and bind the entry points below with
+ * ctypes.  Each entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller owns every buffer; the library never allocates device memory and keeps
+ *     no mutable global state except a thread-local last-error string;
+ *   - work is enqueued on `stream` (a cudaStream_t) and the call returns immediately;
+ *   - return value: 0 on success, negative on failure (LAFS_ERR_*); the message is
+ *     available from lafs_last_error_string().  No exception crosses the boundary;
+ *   - dtype codes: 0 = fp32, 1 = bf16, 2 = fp16.
+ */
+#ifndef LAFS_B200_H_
+#define LAFS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* lafs_stream_t; /* cudaStream_t */
+
+#define LAFS_API __attribute__((visibility("default")))
+
+#define LAFS_OK 0
+#define LAFS_ERR_ARG (-1)
+#define LAFS_ERR_CUDA (-2)
+#define LAFS_ERR_WORKSPACE (-3)
+
+#define LAFS_F32 0
+#define LAFS_BF16 1
+#define LAFS_F16 2
+
+LAFS_API int lafs_version(void);
+LAFS_API const char* lafs_last_error_string(void);
+/* 1 when the running device is compute capability 10.x, 0 otherwise, negative on error. */
+LAFS_API int lafs_device_ok(void);
+
+/* ------------------------------------------------------------------------------------------
+ * (3) Teacher EMA  --  replaces the per-parameter loop  lafs_train.py:610-613
+ *       param_k.data.mul_(m).add_((1 - m) * param_q.detach().data)
+ * One launch for all tensors.  `table` is a device array of nchunks records
+ *   struct { float* k; const float* q; int64_t n; }   (24 bytes, n <= LAFS_EMA_CHUNK)
+ * each describing a contiguous run of one fp32 tensor pair.  Arithmetic is
+ *   k = fl(fl(k*m) + fl(q*one_minus_m))   -- three separately rounded fp32 operations,
+ * bit-identical to the reference (m and 1-m are rounded to fp32 by the caller from the
+ * float64 schedule value, as PyTorch does).
+ */
+#define LAFS_EMA_CHUNK 16384
+LAFS_API int lafs_ema_multi(const void* table, int nchunks, float m, float one_minus_m, lafs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (2) DINO loss  --  replaces DINOLoss.forward / update_center  lafs_train.py:643-679
+ *
+ * student [ncrops*B, K] (crop v occupies rows [v*B,(v+1)*B): Tensor.chunk(ncrops)),
+ * teacher [2*B, K], both of `dtype`; center [K] fp32 (the OLD centre: the update happens
+ * after the loss).  inv_student_temp = 1/student_temp, inv_teacher_temp =
+ * 1/teacher_temp_schedule[epoch].
+ *
+ * lafs_dino_fwd writes
+ *   loss_out   [1]  fp32   mean over the 2*ncrops-2 (teacher view, student crop) terms
+ *   row_stats  [(ncrops+2)*B] fp32: log2-domain log-sum-exp of every student row, followed
+ *              by the 2*B teacher rows (consumed by lafs_dino_bwd)
+ *   colsum_out [K]  fp32   sum over the 2*B teacher rows (the message of the reference's
+ *              dist.all_reduce, lafs_train.py:674-675)
+ * The result is deterministic (no floating-point atomics).
+ * K must be a multiple of 8 (16-bit dtypes) or 4 (fp32); 2 <= ncrops <= 12.
+ */
+LAFS_API size_t lafs_dino_workspace_bytes(int B, int K, int ncrops);
+LAFS_API int lafs_dino_fwd(const void* student, const void* teacher, const float* center, int B, int K,
+                  int ncrops, float inv_student_temp, float inv_teacher_temp, int dtype,
+                  float* loss_out, float* row_stats, float* colsum_out, void* workspace,
+                  size_t workspace_bytes, lafs_stream_t stream);
+/* grad_student[v*B+b, k] = grad_out * d loss / d student; grad_out is a device scalar
+ * (the upstream gradient; autograd hands it over on the device). */
+LAFS_API int lafs_dino_bwd(const void* student, const void* teacher, const float* center,
+                  const float* row_stats, const float* grad_out, int B, int K, int ncrops,
+                  float inv_student_temp, float inv_teacher_temp, int dtype, void* grad_student,
+                  lafs_stream_t stream);
+/* center_out = center*momentum + (colsum/count)*(1-momentum)   lafs_train.py:676-679
+ * (count = 2B*world_size; colsum already all-reduced by the caller when world>1).
+ * center_out may alias center; the reference re-binds a NEW tensor, and the
+ * backward pass needs the old centre, so the Python module passes a fresh buffer. */
+LAFS_API int lafs_center_ema(const float* center, const float* colsum, float count, float momentum,
+                    float one_minus_momentum, int K, float* center_out, lafs_stream_t stream);
+/* Column sum over `rows` rows of x [rows,K] (torch.sum(teacher_output, dim=0),
+ * lafs_train.py:674) for update_center called on its own; workspace >= 16*K*4 bytes. */
+LAFS_API int lafs_colsum(const void* x, int rows, int K, int dtype, float* out, void* workspace,
+                size_t workspace_bytes, lafs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (1) Landmark post-processing and patch gather
+ *
+ * lafs_landmark_post replaces face_pre_pro/ViT_face.py:1347-1378 (and :694-705):
+ *   theta = (raw - min)/(max - min)*scale  jointly over the 2n numbers of a sample,
+ *   view [n,2], + noise (may be NULL), gather rows extract_id (may be NULL; int64 [B,keep]).
+ * theta_out [B, keep or n, 2] fp32.  minmax_out (may be NULL) [B,2] receives (min,max).
+ */
+LAFS_API int lafs_landmark_post(const float* raw, const float* noise, const int64_t* extract_id,
+                       float* theta_out, float* minmax_out, int B, int n, int keep, float scale,
+                       lafs_stream_t stream);
+/* backward of the plain (no gather) form: grad_raw [B,2n] from grad_theta [B,n,2]. */
+LAFS_API int lafs_landmark_post_bwd(const float* raw, const float* grad_theta, float* grad_raw, int B,
+                           int n, float scale, lafs_stream_t stream);
+
+/* lafs_gather_fwd replaces extract_patches_pytorch_gridsample,
+ * face_pre_pro/ViT_face.py:1615-1656 (+ the einops rearrange lafs_train.py:538 when
+ * layout = LAFS_LAYOUT_TOKENS).  imgs [Bv,C,H,W] fp32, theta [Bv,n,2] fp32 (x,y) pixels,
+ * 8x8 patches, bilinear, zero padding, align_corners=False.
+ *   LAFS_LAYOUT_MOSAIC : out [Bv,C,8r,8r], r*r = n   (the reference's return value)
+ *   LAFS_LAYOUT_TOKENS : out [Bv,n,64*C], feature (i*8+j)*C+c
+ * coord_mode LAFS_COORD_DIV reproduces the reference's CPU arithmetic bit for bit
+ * (grid = (offset+theta)/(H/2) - 1 with an IEEE division); LAFS_COORD_RECIP reproduces
+ * eager CUDA, which multiplies by fp32(2/H).
+ */
+#define LAFS_LAYOUT_MOSAIC 0
+#define LAFS_LAYOUT_TOKENS 1
+#define LAFS_COORD_DIV 0
+#define LAFS_COORD_RECIP 1
+LAFS_API int lafs_gather_fwd(const float* imgs, const float* theta, float* out, int Bv, int C, int H, int W,
+                    int n, int layout, int coord_mode, lafs_stream_t stream);
+/* grad_out in `layout`; grad_imgs (may be NULL) [Bv,C,H,W] must be zero-filled by the
+ * caller (scatter-add); grad_theta (may be NULL) [Bv,n,2]. */
+LAFS_API int lafs_gather_bwd(const float* imgs, const float* theta, const float* grad_out, float* grad_imgs,
+                    float* grad_theta, int Bv, int C, int H, int W, int n, int layout,
+                    int coord_mode, lafs_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LAFS_B200_H_ */

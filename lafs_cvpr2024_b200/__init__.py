@@ -1,0 +1,16 @@
+"""lafs_cvpr2024_b200 -- B200-native (sm_100a) implementation of the LAFS per-step hot path.
+
+Drop-in objects (same names / signatures / state-dict keys as the reference):
+    DINOLoss                               lafs_train.py:626-679
+    ema_update_                            lafs_train.py:610-613 (inline loop in the reference)
+    extract_patches_pytorch_gridsample     face_pre_pro/ViT_face.py:1615-1656
+    landmark_post                          face_pre_pro/ViT_face.py:1347-1378
+All compute goes through liblafs_b200.so (C ABI in include/lafs_b200.h); there is no CPU path.
+"""
+from . import _lib  # noqa: F401
+from .dino_loss import DINOLoss  # noqa: F401
+from .ema import EmaPlan, ema_update_  # noqa: F401
+from .patches import extract_patches_pytorch_gridsample, extract_tokens, landmark_post  # noqa: F401
+
+__all__ = ["DINOLoss", "EmaPlan", "ema_update_", "extract_patches_pytorch_gridsample", "extract_tokens",
+           "landmark_post"]

@@ -1,0 +1,39 @@
+// Error plumbing + version of liblafs_b200.
+#include <stdarg.h>
+#include <stdio.h>
+#include "common.cuh"
+#include "../../include/lafs_b200.h"
+
+namespace lafs {
+static thread_local char g_err[512] = "";
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error("%s: %s", what, cudaGetErrorString(e));
+    return LAFS_ERR_CUDA;
+  }
+  return LAFS_OK;
+}
+}  // namespace lafs
+
+extern "C" int lafs_version(void) { return 100; }
+
+extern "C" const char* lafs_last_error_string(void) { return lafs::g_err; }
+
+extern "C" int lafs_device_ok(void) {
+  int dev = 0;
+  cudaDeviceProp p;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&p, dev) != cudaSuccess) {
+    lafs::set_last_error("lafs_device_ok: %s", cudaGetErrorString(cudaGetLastError()));
+    return LAFS_ERR_CUDA;
+  }
+  return p.major == 10 ? 1 : 0;
+}

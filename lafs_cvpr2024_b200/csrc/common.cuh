@@ -1,0 +1,113 @@
+// Shared device/host helpers for liblafs_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "liblafs_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace lafs {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+// ---- error plumbing (no exceptions cross the C ABI) --------------------------------------
+void set_last_error(const char* fmt, ...);
+int check_launch(const char* what);  // cudaGetLastError -> 0 or negative code, records message
+
+#define LAFS_REQUIRE(cond, code, ...)                 \
+  do {                                                \
+    if (!(cond)) {                                    \
+      ::lafs::set_last_error(__VA_ARGS__);            \
+      return (code);                                  \
+    }                                                 \
+  } while (0)
+
+enum : int {
+  LAFS_OK = 0,
+  LAFS_ERR_ARG = -1,       // bad argument (null pointer, unsupported size / dtype, misalignment)
+  LAFS_ERR_CUDA = -2,      // a CUDA runtime call or launch failed (see lafs_last_error_string)
+  LAFS_ERR_WORKSPACE = -3  // workspace too small
+};
+
+enum : int { LAFS_F32 = 0, LAFS_BF16 = 1, LAFS_F16 = 2 };
+
+// ---- device helpers ------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// float max over the warp with one REDUX on an order-preserving integer key.
+__device__ __forceinline__ float warp_max_redux(float v) {
+  int i = __float_as_int(v);
+  i ^= (i >> 31) & 0x7fffffff;
+  i = __reduce_max_sync(0xffffffffu, i);
+  i ^= (i >> 31) & 0x7fffffff;
+  return __int_as_float(i);
+}
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// streaming 128-bit accesses (data touched once: keep it out of L1)
+__device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float4 ld_stream_f4(const void* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream_u4(void* p, uint4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_stream_f4(void* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// 16-bit pair unpack / pack.  T = __nv_bfloat16 or __half.
+template <typename T> struct Half2Ops;
+template <> struct Half2Ops<__nv_bfloat16> {
+  static __device__ __forceinline__ float lo(uint32_t u) { return __uint_as_float(u << 16); }
+  static __device__ __forceinline__ float hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+  static __device__ __forceinline__ uint32_t pack(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+};
+template <> struct Half2Ops<__half> {
+  static __device__ __forceinline__ float lo(uint32_t u) {
+    return __half2float(__ushort_as_half((unsigned short)(u & 0xffffu)));
+  }
+  static __device__ __forceinline__ float hi(uint32_t u) {
+    return __half2float(__ushort_as_half((unsigned short)(u >> 16)));
+  }
+  static __device__ __forceinline__ uint32_t pack(float a, float b) {
+    __half2 v = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+};
+
+}  // namespace lafs

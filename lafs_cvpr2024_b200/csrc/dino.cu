@@ -1,0 +1,557 @@
+// (2) DINO loss: teacher centring + temperature softmax, student log-softmax over all crops,
+// cross-entropy and the centre column-sum in ONE streaming pass over the logits, plus the
+// gradient pass and the centre EMA.  Replaces DINOLoss.forward/update_center
+// (lafs_train.py:643-679), which launches ~60-100 kernels each materialising [B,K] fp32.
+//
+// Single-pass identity (sum_k q = 1):
+//   loss = 1/(n_terms*B) * sum_b [ sum_v n_v*lse(s_v/ts) - (1/ts) * sum_iq sum_k q_iq,k*(S_k - s_iq,k) ]
+//   q_iq = softmax((t_iq - c)/tt), S_k = sum_v s_v,k, n_v = #{iq != v}, n_terms = 2*ncrops-2.
+//
+// Work decomposition (HBM-bound, coalesced, warp-shuffle reduced):
+//   * a lane owns NC = U*VEC fixed columns of a K-slice and keeps the centre and the
+//     column-sum accumulators for them in registers;
+//   * a warp walks over samples; per sample it loads the 2 teacher + ncrops student row
+//     segments with 128-bit streaming loads (next sample prefetched), finds the per-row slice
+//     maxima with one REDUX each, and produces per-(sample,slice) partial statistics;
+//   * partials are merged across slices by dino_rows_finalize (deterministic, no atomics).
+// All math in fp32, exponentials in the log2 domain (ex2.approx).
+#include "common.cuh"
+#include "../../include/lafs_b200.h"
+
+namespace lafs {
+
+constexpr int kDinoThreads = 256;
+constexpr int kDinoWarps = kDinoThreads / 32;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr int kMaxGroups = 16;
+
+template <typename T> struct VecOf { static constexpr int VEC = 16 / sizeof(T); };
+
+template <typename T>
+__device__ __forceinline__ void unpack(const uint4& u, float* v) {
+  if constexpr (sizeof(T) == 4) {
+    v[0] = __uint_as_float(u.x); v[1] = __uint_as_float(u.y);
+    v[2] = __uint_as_float(u.z); v[3] = __uint_as_float(u.w);
+  } else {
+    v[0] = Half2Ops<T>::lo(u.x); v[1] = Half2Ops<T>::hi(u.x);
+    v[2] = Half2Ops<T>::lo(u.y); v[3] = Half2Ops<T>::hi(u.y);
+    v[4] = Half2Ops<T>::lo(u.z); v[5] = Half2Ops<T>::hi(u.z);
+    v[6] = Half2Ops<T>::lo(u.w); v[7] = Half2Ops<T>::hi(u.w);
+  }
+}
+template <typename T>
+__device__ __forceinline__ uint4 pack(const float* v) {
+  uint4 u;
+  if constexpr (sizeof(T) == 4) {
+    u.x = __float_as_uint(v[0]); u.y = __float_as_uint(v[1]);
+    u.z = __float_as_uint(v[2]); u.w = __float_as_uint(v[3]);
+  } else {
+    u.x = Half2Ops<T>::pack(v[0], v[1]); u.y = Half2Ops<T>::pack(v[2], v[3]);
+    u.z = Half2Ops<T>::pack(v[4], v[5]); u.w = Half2Ops<T>::pack(v[6], v[7]);
+  }
+  return u;
+}
+
+// record of partial statistics per (sample, slice):
+//   [0..2] teacher view 0: max (log2 domain), Z, A      [3..5] teacher view 1
+//   [6+2v], [7+2v] student crop v: max, sum
+__host__ __device__ constexpr int rec_floats(int ncrops) { return 6 + 2 * ncrops; }
+
+template <typename T, int NCROPS, int U>
+struct Rows {
+  uint4 t[2][U];
+  uint4 s[NCROPS][U];
+};
+
+template <typename T, int U>
+__device__ __forceinline__ void load_row(uint4 (&dst)[U], const T* __restrict__ base, size_t row, int K,
+                                         const int (&col)[U], const bool (&ok)[U]) {
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    dst[u] = ok[u] ? ld_stream_u4(base + row * (size_t)K + col[u]) : make_uint4(0, 0, 0, 0);
+}
+
+template <typename T, int NCROPS, int U>
+__global__ void __launch_bounds__(kDinoThreads, 2)
+dino_fwd_partial(const T* __restrict__ student, const T* __restrict__ teacher,
+                 const float* __restrict__ center, int B, int K, float a_s, float a_t,
+                 int nslices, int ngroups, float* __restrict__ part, float* __restrict__ colsum_part) {
+  constexpr int VEC = VecOf<T>::VEC;
+  constexpr int NC = U * VEC;
+  constexpr int REC = rec_floats(NCROPS);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int slice = blockIdx.x, group = blockIdx.y;
+  const int b_lo = (int)(((long long)B * group) / ngroups);
+  const int b_hi = (int)(((long long)B * (group + 1)) / ngroups);
+
+  int col[U];
+  bool ok[U];
+  float cen[NC], csum[NC];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    col[u] = (slice * U + u) * (32 * VEC) + lane * VEC;
+    ok[u] = col[u] < K;  // K % VEC == 0 is checked by the host
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      cen[u * VEC + j] = ok[u] ? __ldg(center + col[u] + j) * a_t : 0.f;
+      csum[u * VEC + j] = 0.f;
+    }
+  }
+
+  // Register-rotating software pipeline: `rows` always holds the not-yet-consumed segments of
+  // the current sample; as soon as a row has been unpacked its registers are re-filled with the
+  // same row of the warp's next sample, so ncrops+2 128-bit loads stay in flight per lane.
+  Rows<T, NCROPS, U> rows;
+  int b = b_lo + warp;
+  if (b < b_hi) {
+#pragma unroll
+    for (int iq = 0; iq < 2; ++iq) load_row<T, U>(rows.t[iq], teacher, (size_t)iq * B + b, K, col, ok);
+#pragma unroll
+    for (int v = 0; v < NCROPS; ++v) load_row<T, U>(rows.s[v], student, (size_t)v * B + b, K, col, ok);
+  }
+  for (; b < b_hi; b += kDinoWarps) {
+    const int bn = b + kDinoWarps;
+    const bool has_next = bn < b_hi;
+
+    float rec[REC];
+    float e[2][NC];  // teacher: first x (log2-domain logits), then exp2(x - max)
+    // ---- teacher rows ------------------------------------------------------------------
+#pragma unroll
+    for (int iq = 0; iq < 2; ++iq) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float tv[VEC];
+        unpack<T>(rows.t[iq][u], tv);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const int c = u * VEC + j;
+          csum[c] += tv[j];
+          const float x = ok[u] ? fmaf(tv[j], a_t, -cen[c]) : -INFINITY;
+          e[iq][c] = x;
+          mx = fmaxf(mx, x);
+        }
+      }
+      if (has_next) load_row<T, U>(rows.t[iq], teacher, (size_t)iq * B + bn, K, col, ok);
+      mx = warp_max_redux(mx);
+      float z = 0.f;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        e[iq][c] = ex2(e[iq][c] - mx);
+        z += e[iq][c];
+      }
+      rec[3 * iq + 0] = mx;
+      rec[3 * iq + 1] = z;
+    }
+    // ---- student rows ------------------------------------------------------------------
+    float S[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) S[c] = 0.f;
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int v = 0; v < NCROPS; ++v) {
+      float sv[NC];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        unpack<T>(rows.s[v][u], sv + u * VEC);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) mx = fmaxf(mx, ok[u] ? sv[u * VEC + j] : -INFINITY);
+      }
+      if (has_next) load_row<T, U>(rows.s[v], student, (size_t)v * B + bn, K, col, ok);
+      mx = warp_max_redux(mx) * a_s;  // a_s > 0: max commutes with the scaling
+      float sum = 0.f;
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const int c = u * VEC + j;
+          sum += ok[u] ? ex2(fmaf(sv[c], a_s, -mx)) : 0.f;
+          S[c] += sv[c];
+        }
+      // the two self-view products are removed from the S-dot below
+      if (v == 0) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) a0 = fmaf(e[0][c], -sv[c], a0);
+      }
+      if (v == 1) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) a1 = fmaf(e[1][c], -sv[c], a1);
+      }
+      rec[6 + 2 * v] = mx;
+      rec[7 + 2 * v] = warp_sum(sum);
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      a0 = fmaf(e[0][c], S[c], a0);
+      a1 = fmaf(e[1][c], S[c], a1);
+    }
+    // ---- warp reduction of the additive statistics ---------------------------------------
+    rec[1] = warp_sum(rec[1]); rec[2] = warp_sum(a0);
+    rec[4] = warp_sum(rec[4]); rec[5] = warp_sum(a1);
+    if (lane == 0) {
+      float* dst = part + ((size_t)b * nslices + slice) * REC;  // REC is even -> 8-byte aligned
+#pragma unroll
+      for (int i = 0; i < REC; i += 2) *reinterpret_cast<float2*>(dst + i) = make_float2(rec[i], rec[i + 1]);
+    }
+  }
+
+  // ---- column sums of this CTA's samples: reduce the 8 warps through shared memory ---------
+  __shared__ float sm[kDinoWarps][32 * NC + 1];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) sm[warp][c * 32 + lane] = csum[c];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * NC; i += kDinoThreads) {
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < kDinoWarps; ++w) acc += sm[w][i];
+    const int c = i >> 5, l = i & 31;
+    const int u = c / VEC, j = c % VEC;
+    const int column = (slice * U + u) * (32 * VEC) + l * VEC + j;
+    if (column < K) colsum_part[(size_t)group * K + column] = acc;
+  }
+}
+
+// One warp per sample: merge the slice partials, emit row statistics and the sample's loss.
+template <int NCROPS>
+__global__ void __launch_bounds__(kDinoThreads)
+dino_rows_finalize(const float* __restrict__ part, int B, int nslices, float inv_ts,
+                   float* __restrict__ row_stats, float* __restrict__ sample_loss) {
+  constexpr int REC = rec_floats(NCROPS);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x * kDinoWarps + warp;
+  if (b >= B) return;
+  float m[2 + NCROPS], z[2 + NCROPS], a[2];
+#pragma unroll
+  for (int i = 0; i < 2 + NCROPS; ++i) { m[i] = -INFINITY; z[i] = 0.f; }
+  a[0] = a[1] = 0.f;
+  for (int s = lane; s < nslices; s += 32) {
+    const float* r = part + ((size_t)b * nslices + s) * REC;
+#pragma unroll
+    for (int iq = 0; iq < 2; ++iq) {
+      const float ms = r[3 * iq], zs = r[3 * iq + 1], as = r[3 * iq + 2];
+      const float mn = fmaxf(m[iq], ms);
+      const float f_old = ex2(m[iq] - mn), f_new = ex2(ms - mn);  // ex2(-inf) = 0
+      z[iq] = z[iq] * f_old + zs * f_new;
+      a[iq] = a[iq] * f_old + as * f_new;
+      m[iq] = mn;
+    }
+#pragma unroll
+    for (int v = 0; v < NCROPS; ++v) {
+      const float ms = r[6 + 2 * v], zs = r[7 + 2 * v];
+      const float mn = fmaxf(m[2 + v], ms);
+      z[2 + v] = z[2 + v] * ex2(m[2 + v] - mn) + zs * ex2(ms - mn);
+      m[2 + v] = mn;
+    }
+  }
+  // butterfly merge across lanes (lanes without slices carry m=-inf, z=0)
+#pragma unroll
+  for (int i = 0; i < 2 + NCROPS; ++i) {
+    const float mw = warp_max(m[i]);
+    const float f = (m[i] == -INFINITY) ? 0.f : ex2(m[i] - mw);
+    z[i] = warp_sum(z[i] * f);
+    if (i < 2) a[i] = warp_sum(a[i] * f);
+    m[i] = mw;
+  }
+  if (lane == 0) {
+    float loss = 0.f;
+#pragma unroll
+    for (int v = 0; v < NCROPS; ++v) {
+      const float l2 = m[2 + v] + lg2(z[2 + v]);  // log2-domain lse of s_v/ts
+      row_stats[(size_t)v * B + b] = l2;
+      loss += (v < 2 ? 1.f : 2.f) * l2;
+    }
+    loss *= kLn2;
+#pragma unroll
+    for (int iq = 0; iq < 2; ++iq) {
+      row_stats[(size_t)(NCROPS + iq) * B + b] = m[iq] + lg2(z[iq]);
+      loss -= inv_ts * (a[iq] / z[iq]);
+    }
+    sample_loss[b] = loss;
+  }
+}
+
+// block 0: fixed-order sum of the per-sample losses; all blocks: merge column-sum partials.
+__global__ void __launch_bounds__(kDinoThreads)
+dino_tail(const float* __restrict__ sample_loss, int B, float inv_norm, float* __restrict__ loss_out,
+          const float* __restrict__ colsum_part, int ngroups, int K, float* __restrict__ colsum_out) {
+  const int k = blockIdx.x * kDinoThreads + threadIdx.x;
+  if (k < K) {
+    float acc = 0.f;
+    for (int g = 0; g < ngroups; ++g) acc += colsum_part[(size_t)g * K + k];
+    colsum_out[k] = acc;
+  }
+  if (blockIdx.x == 0) {
+    __shared__ float red[kDinoThreads];
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < B; i += kDinoThreads) acc += sample_loss[i];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = kDinoThreads / 2; o > 0; o >>= 1) {
+      if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) *loss_out = red[0] * inv_norm;
+  }
+}
+
+// Gradient pass: ds[v,b,k] = g * ( n_v * softmax(s_v/ts)_k - sum_{iq != v} q_iq,k ),
+// g = grad_out / (ts * n_terms * B).  Purely element-wise given the saved row statistics.
+template <typename T, int NCROPS>
+__global__ void __launch_bounds__(kDinoThreads)
+dino_bwd_kernel(const T* __restrict__ student, const T* __restrict__ teacher,
+                const float* __restrict__ center, const float* __restrict__ row_stats,
+                const float* __restrict__ grad_out, int B, int K, float a_s, float a_t,
+                float gcoef, T* __restrict__ grad_student) {
+  constexpr int VEC = VecOf<T>::VEC;
+  const int b = blockIdx.y;
+  const int col = (blockIdx.x * kDinoThreads + threadIdx.x) * VEC;
+  if (col >= K) return;
+  uint4 tv[2], sv[NCROPS];
+#pragma unroll
+  for (int iq = 0; iq < 2; ++iq) tv[iq] = ld_stream_u4(teacher + (size_t)(iq * B + b) * K + col);
+#pragma unroll
+  for (int v = 0; v < NCROPS; ++v) sv[v] = ld_stream_u4(student + (size_t)(v * B + b) * K + col);
+  const float g = __ldg(grad_out) * gcoef;
+  float q[2][VEC];
+#pragma unroll
+  for (int iq = 0; iq < 2; ++iq) {
+    const float r = __ldg(row_stats + (size_t)(NCROPS + iq) * B + b);
+    float t[VEC];
+    unpack<T>(tv[iq], t);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j)
+      q[iq][j] = ex2(fmaf(t[j], a_t, -fmaf(__ldg(center + col + j), a_t, r)));
+  }
+#pragma unroll
+  for (int v = 0; v < NCROPS; ++v) {
+    const float l2 = __ldg(row_stats + (size_t)v * B + b);
+    float s[VEC], d[VEC];
+    unpack<T>(sv[v], s);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float p = ex2(fmaf(s[j], a_s, -l2));
+      float r;
+      if (v == 0) r = p - q[1][j];
+      else if (v == 1) r = p - q[0][j];
+      else r = 2.f * p - q[0][j] - q[1][j];
+      d[j] = g * r;
+    }
+    st_stream_u4(grad_student + (size_t)(v * B + b) * K + col, pack<T>(d));
+  }
+}
+
+// Stand-alone teacher column sum for DINOLoss.update_center called outside forward
+// (lafs_train.py:674).  Off the hot path: forward already produces the column sums.
+template <typename T>
+__global__ void __launch_bounds__(kDinoThreads)
+colsum_partial_kernel(const T* __restrict__ x, int rows, int K, int ngroups, float* __restrict__ part) {
+  constexpr int VEC = VecOf<T>::VEC;
+  const int col = (blockIdx.x * kDinoThreads + threadIdx.x) * VEC;
+  if (col >= K) return;
+  const int g = blockIdx.y;
+  const int r_lo = (int)(((long long)rows * g) / ngroups), r_hi = (int)(((long long)rows * (g + 1)) / ngroups);
+  float acc[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+  for (int r = r_lo; r < r_hi; ++r) {
+    float v[VEC];
+    unpack<T>(ld_stream_u4(x + (size_t)r * K + col), v);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[j] += v[j];
+  }
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) part[(size_t)g * K + col + j] = acc[j];
+}
+__global__ void colsum_combine_kernel(const float* __restrict__ part, int ngroups, int K, float* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float acc = 0.f;
+  for (int g = 0; g < ngroups; ++g) acc += part[(size_t)g * K + k];
+  out[k] = acc;
+}
+
+__global__ void center_ema_kernel(const float* __restrict__ center, const float* __restrict__ colsum,
+                                  float count, float mom, float om, int K, float* __restrict__ center_out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  // reference: center*momentum + (batch_center/n)*(1-momentum): separately rounded fp32 ops,
+  // IEEE division as on the reference's CPU path
+  if (k < K) center_out[k] = __fadd_rn(__fmul_rn(center[k], mom), __fmul_rn(__fdiv_rn(colsum[k], count), om));
+}
+
+// ---- host side ---------------------------------------------------------------------------
+struct DinoPlan {
+  int U, cols_per_slice, nslices, ngroups;
+  size_t off_part, off_colsum, off_sample, total;
+};
+
+static DinoPlan make_plan(int B, int K, int ncrops, int elem_bytes) {
+  DinoPlan p;
+  const int vec = 16 / elem_bytes;
+  p.U = 1;
+  p.cols_per_slice = 32 * vec * p.U;
+  p.nslices = (K + p.cols_per_slice - 1) / p.cols_per_slice;
+  // choose the number of sample groups so that the grid fills whole waves (2 CTAs per SM)
+  const int cap = kNumSMs * 2;
+  int best = 1;
+  double best_eff = 0.0;
+  const int gmax = B / kDinoWarps < 1 ? 1 : (B / kDinoWarps > kMaxGroups ? kMaxGroups : B / kDinoWarps);
+  for (int g = 1; g <= gmax; ++g) {
+    const long long n = (long long)p.nslices * g;
+    const long long waves = (n + cap - 1) / cap;
+    const double eff = (double)n / (double)(waves * cap);
+    if (eff > best_eff + 1e-9 || (eff > best_eff - 0.02 && g > best)) {
+      if (eff > best_eff) best_eff = eff;
+      best = g;
+    }
+  }
+  p.ngroups = best;
+  size_t o = 0;
+  p.off_part = o;   o += (size_t)B * p.nslices * rec_floats(ncrops) * sizeof(float);
+  o = (o + 255) & ~(size_t)255;
+  p.off_colsum = o; o += (size_t)p.ngroups * K * sizeof(float);
+  o = (o + 255) & ~(size_t)255;
+  p.off_sample = o; o += (size_t)B * sizeof(float);
+  p.total = (o + 255) & ~(size_t)255;
+  return p;
+}
+
+template <typename T, int NCROPS>
+static int launch_fwd(const void* student, const void* teacher, const float* center, int B, int K,
+                      float inv_ts, float inv_tt, float* loss_out, float* row_stats,
+                      float* colsum_out, char* ws, const DinoPlan& p, cudaStream_t st) {
+  float* part = reinterpret_cast<float*>(ws + p.off_part);
+  float* colsum_part = reinterpret_cast<float*>(ws + p.off_colsum);
+  float* sample_loss = reinterpret_cast<float*>(ws + p.off_sample);
+  dim3 grid(p.nslices, p.ngroups);
+  dino_fwd_partial<T, NCROPS, 1><<<grid, kDinoThreads, 0, st>>>(
+      (const T*)student, (const T*)teacher, center, B, K, inv_ts * kLog2e, inv_tt * kLog2e,
+      p.nslices, p.ngroups, part, colsum_part);
+  dino_rows_finalize<NCROPS><<<(B + kDinoWarps - 1) / kDinoWarps, kDinoThreads, 0, st>>>(
+      part, B, p.nslices, inv_ts, row_stats, sample_loss);
+  const float inv_norm = 1.f / ((float)(2 * NCROPS - 2) * (float)B);
+  dino_tail<<<(K + kDinoThreads - 1) / kDinoThreads, kDinoThreads, 0, st>>>(
+      sample_loss, B, inv_norm, loss_out, colsum_part, p.ngroups, K, colsum_out);
+  return check_launch("lafs_dino_fwd");
+}
+
+template <typename T, int NCROPS>
+static int launch_bwd(const void* student, const void* teacher, const float* center,
+                      const float* row_stats, const float* grad_out, int B, int K, float inv_ts,
+                      float inv_tt, void* grad_student, cudaStream_t st) {
+  constexpr int VEC = VecOf<T>::VEC;
+  dim3 grid((K / VEC + kDinoThreads - 1) / kDinoThreads, B);
+  const float gcoef = inv_ts / ((float)(2 * NCROPS - 2) * (float)B);
+  dino_bwd_kernel<T, NCROPS><<<grid, kDinoThreads, 0, st>>>(
+      (const T*)student, (const T*)teacher, center, row_stats, grad_out, B, K, inv_ts * kLog2e,
+      inv_tt * kLog2e, gcoef, (T*)grad_student);
+  return check_launch("lafs_dino_bwd");
+}
+
+#define LAFS_DINO_CROPS(M) M(2) M(3) M(4) M(5) M(6) M(7) M(8) M(9) M(10) M(11) M(12)
+
+}  // namespace lafs
+
+extern "C" size_t lafs_dino_workspace_bytes(int B, int K, int ncrops) {
+  if (B <= 0 || K <= 0 || ncrops < 2 || ncrops > 12) return 0;
+  // sized for the worst case over dtypes (fp32 has the most slices)
+  return lafs::make_plan(B, K, ncrops, 4).total;
+}
+
+static int dino_check(const void* s, const void* t, const float* c, int B, int K, int ncrops, int dtype,
+                      const char* who) {
+  using namespace lafs;
+  LAFS_REQUIRE(s && t && c, LAFS_ERR_ARG, "%s: null pointer", who);
+  LAFS_REQUIRE(B > 0 && K > 0, LAFS_ERR_ARG, "%s: B=%d K=%d must be positive", who, B, K);
+  LAFS_REQUIRE(ncrops >= 2 && ncrops <= 12, LAFS_ERR_ARG, "%s: ncrops=%d outside [2,12]", who, ncrops);
+  LAFS_REQUIRE(dtype >= 0 && dtype <= 2, LAFS_ERR_ARG, "%s: dtype=%d", who, dtype);
+  const int vec = dtype == LAFS_F32 ? 4 : 8;
+  LAFS_REQUIRE(K % vec == 0, LAFS_ERR_ARG, "%s: K=%d must be a multiple of %d for this dtype", who, K, vec);
+  LAFS_REQUIRE((((uintptr_t)s | (uintptr_t)t | (uintptr_t)c) & 15u) == 0, LAFS_ERR_ARG,
+               "%s: pointers must be 16-byte aligned", who);
+  return LAFS_OK;
+}
+
+extern "C" int lafs_dino_fwd(const void* student, const void* teacher, const float* center, int B, int K,
+                             int ncrops, float inv_student_temp, float inv_teacher_temp, int dtype,
+                             float* loss_out, float* row_stats, float* colsum_out, void* workspace,
+                             size_t workspace_bytes, lafs_stream_t stream) {
+  using namespace lafs;
+  int rc = dino_check(student, teacher, center, B, K, ncrops, dtype, "lafs_dino_fwd");
+  if (rc) return rc;
+  LAFS_REQUIRE(loss_out && row_stats && colsum_out && workspace, LAFS_ERR_ARG, "lafs_dino_fwd: null output");
+  const DinoPlan p = make_plan(B, K, ncrops, dtype == LAFS_F32 ? 4 : 2);
+  LAFS_REQUIRE(workspace_bytes >= p.total, LAFS_ERR_WORKSPACE, "lafs_dino_fwd: workspace %zu < %zu",
+               workspace_bytes, p.total);
+  LAFS_REQUIRE(((uintptr_t)workspace & 255u) == 0, LAFS_ERR_ARG, "lafs_dino_fwd: workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+#define LAFS_CASE(N)                                                                                     \
+  case N:                                                                                                \
+    if (dtype == LAFS_F32)                                                                               \
+      return launch_fwd<float, N>(student, teacher, center, B, K, inv_student_temp, inv_teacher_temp,    \
+                                  loss_out, row_stats, colsum_out, ws, p, st);                           \
+    if (dtype == LAFS_BF16)                                                                              \
+      return launch_fwd<__nv_bfloat16, N>(student, teacher, center, B, K, inv_student_temp,              \
+                                          inv_teacher_temp, loss_out, row_stats, colsum_out, ws, p, st); \
+    return launch_fwd<__half, N>(student, teacher, center, B, K, inv_student_temp, inv_teacher_temp,     \
+                                 loss_out, row_stats, colsum_out, ws, p, st);
+  switch (ncrops) { LAFS_DINO_CROPS(LAFS_CASE) }
+#undef LAFS_CASE
+  return LAFS_ERR_ARG;
+}
+
+extern "C" int lafs_dino_bwd(const void* student, const void* teacher, const float* center,
+                             const float* row_stats, const float* grad_out, int B, int K, int ncrops,
+                             float inv_student_temp, float inv_teacher_temp, int dtype, void* grad_student,
+                             lafs_stream_t stream) {
+  using namespace lafs;
+  int rc = dino_check(student, teacher, center, B, K, ncrops, dtype, "lafs_dino_bwd");
+  if (rc) return rc;
+  LAFS_REQUIRE(row_stats && grad_out && grad_student, LAFS_ERR_ARG, "lafs_dino_bwd: null pointer");
+  LAFS_REQUIRE(((uintptr_t)grad_student & 15u) == 0, LAFS_ERR_ARG, "lafs_dino_bwd: grad_student misaligned");
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAFS_CASE(N)                                                                                       \
+  case N:                                                                                                  \
+    if (dtype == LAFS_F32)                                                                                 \
+      return launch_bwd<float, N>(student, teacher, center, row_stats, grad_out, B, K, inv_student_temp,   \
+                                  inv_teacher_temp, grad_student, st);                                     \
+    if (dtype == LAFS_BF16)                                                                                \
+      return launch_bwd<__nv_bfloat16, N>(student, teacher, center, row_stats, grad_out, B, K,             \
+                                          inv_student_temp, inv_teacher_temp, grad_student, st);           \
+    return launch_bwd<__half, N>(student, teacher, center, row_stats, grad_out, B, K, inv_student_temp,    \
+                                 inv_teacher_temp, grad_student, st);
+  switch (ncrops) { LAFS_DINO_CROPS(LAFS_CASE) }
+#undef LAFS_CASE
+  return LAFS_ERR_ARG;
+}
+
+extern "C" int lafs_center_ema(const float* center, const float* colsum, float count, float momentum,
+                               float one_minus_momentum, int K, float* center_out, lafs_stream_t stream) {
+  using namespace lafs;
+  LAFS_REQUIRE(center && colsum && center_out && K > 0, LAFS_ERR_ARG, "lafs_center_ema: bad argument");
+  center_ema_kernel<<<(K + 255) / 256, 256, 0, (cudaStream_t)stream>>>(center, colsum, count, momentum,
+                                                                      one_minus_momentum, K, center_out);
+  return check_launch("lafs_center_ema");
+}
+
+extern "C" int lafs_colsum(const void* x, int rows, int K, int dtype, float* out, void* workspace,
+                           size_t workspace_bytes, lafs_stream_t stream) {
+  using namespace lafs;
+  LAFS_REQUIRE(x && out && workspace && rows > 0 && K > 0, LAFS_ERR_ARG, "lafs_colsum: bad argument");
+  LAFS_REQUIRE(dtype >= 0 && dtype <= 2, LAFS_ERR_ARG, "lafs_colsum: dtype=%d", dtype);
+  const int vec = dtype == LAFS_F32 ? 4 : 8;
+  LAFS_REQUIRE(K % vec == 0 && ((uintptr_t)x & 15u) == 0, LAFS_ERR_ARG, "lafs_colsum: K %% %d != 0 or misaligned", vec);
+  const int ngroups = rows < kMaxGroups ? rows : kMaxGroups;
+  LAFS_REQUIRE(workspace_bytes >= (size_t)ngroups * K * sizeof(float), LAFS_ERR_WORKSPACE,
+               "lafs_colsum: workspace too small (need %zu)", (size_t)ngroups * K * sizeof(float));
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((K / vec + kDinoThreads - 1) / kDinoThreads, ngroups);
+  float* part = (float*)workspace;
+  if (dtype == LAFS_F32) colsum_partial_kernel<float><<<grid, kDinoThreads, 0, st>>>((const float*)x, rows, K, ngroups, part);
+  else if (dtype == LAFS_BF16) colsum_partial_kernel<__nv_bfloat16><<<grid, kDinoThreads, 0, st>>>((const __nv_bfloat16*)x, rows, K, ngroups, part);
+  else colsum_partial_kernel<__half><<<grid, kDinoThreads, 0, st>>>((const __half*)x, rows, K, ngroups, part);
+  colsum_combine_kernel<<<(K + 255) / 256, 256, 0, st>>>(part, ngroups, K, out);
+  return check_launch("lafs_colsum");
+}

@@ -1,0 +1,122 @@
+"""DINOLoss with the reference's module surface (lafs_train.py:626-679) on fused sm_100a kernels.
+
+    DINOLoss(out_dim, ncrops, warmup_teacher_temp, teacher_temp, warmup_teacher_temp_epochs,
+             nepochs, student_temp=0.1, center_momentum=0.9)
+    .forward(student_output, teacher_output, epoch) -> scalar loss
+    .update_center(teacher_output)                  (no_grad; all-reduce over the process group)
+    buffer `center` [1, out_dim] fp32  (the only state-dict entry)
+
+Forward is one streaming pass over the logits that also yields the teacher column sums, so
+update_center costs one [K] all-reduce plus a [K] kernel.  As in the reference, the loss uses
+the OLD centre and `self.center` is re-bound to a new tensor afterwards.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import _lib
+
+
+def _workspace(dev, nbytes):
+    return torch.empty(nbytes, dtype=torch.uint8, device=dev)
+
+
+class _DinoLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, student, teacher, center, ncrops, inv_ts, inv_tt, stash):
+        _lib.require_cuda(student, teacher, center)
+        if student.dim() != 2 or teacher.dim() != 2:
+            raise ValueError("student_output / teacher_output must be 2-D [rows, out_dim]")
+        K = student.shape[1]
+        if student.shape[0] % ncrops or teacher.shape[0] % 2:
+            raise ValueError("row counts must be ncrops*B (student) and 2*B (teacher)")
+        B = student.shape[0] // ncrops
+        if teacher.shape != (2 * B, K) or center.numel() != K:
+            raise ValueError(f"shape mismatch: student {tuple(student.shape)}, teacher {tuple(teacher.shape)}, "
+                             f"center {tuple(center.shape)}")
+        s = student.detach().contiguous()
+        t = teacher.detach().to(s.dtype).contiguous()
+        c = center.detach().float().contiguous()
+        dev = s.device
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        row_stats = torch.empty((ncrops + 2) * B, dtype=torch.float32, device=dev)
+        colsum = torch.empty(K, dtype=torch.float32, device=dev)
+        nbytes = _lib.lib().lafs_dino_workspace_bytes(B, K, ncrops)
+        if nbytes == 0:
+            raise ValueError(f"unsupported DINO shape B={B} K={K} ncrops={ncrops}")
+        ws = _workspace(dev, nbytes)
+        _lib.call("lafs_dino_fwd", s.data_ptr(), t.data_ptr(), c.data_ptr(), B, K, ncrops,
+                  float(inv_ts), float(inv_tt), _lib.dtype_code(s), loss.data_ptr(),
+                  row_stats.data_ptr(), colsum.data_ptr(), ws.data_ptr(), nbytes, _lib.stream())
+        ctx.save_for_backward(s, t, c, row_stats)
+        ctx.meta = (B, K, ncrops, float(inv_ts), float(inv_tt))
+        if stash is not None:
+            stash["colsum"] = colsum
+            stash["teacher"] = (teacher.data_ptr(), teacher._version, tuple(teacher.shape))
+        ctx.mark_non_differentiable(colsum)
+        return loss, colsum
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_colsum):
+        s, t, c, row_stats = ctx.saved_tensors
+        B, K, ncrops, inv_ts, inv_tt = ctx.meta
+        g = grad_loss.detach().float().contiguous()
+        grad_s = torch.empty_like(s)
+        _lib.call("lafs_dino_bwd", s.data_ptr(), t.data_ptr(), c.data_ptr(), row_stats.data_ptr(),
+                  g.data_ptr(), B, K, ncrops, inv_ts, inv_tt, _lib.dtype_code(s), grad_s.data_ptr(),
+                  _lib.stream())
+        return grad_s, None, None, None, None, None, None
+
+
+class DINOLoss(nn.Module):
+    def __init__(self, out_dim, ncrops, warmup_teacher_temp, teacher_temp,
+                 warmup_teacher_temp_epochs, nepochs, student_temp=0.1,
+                 center_momentum=0.9):
+        super().__init__()
+        self.student_temp = student_temp
+        self.center_momentum = center_momentum
+        self.ncrops = ncrops
+        self.register_buffer("center", torch.zeros(1, out_dim))
+        # same schedule object as the reference (lafs_train.py:637-641), indexed by epoch
+        self.teacher_temp_schedule = np.concatenate((
+            np.linspace(warmup_teacher_temp, teacher_temp, warmup_teacher_temp_epochs),
+            np.ones(nepochs - warmup_teacher_temp_epochs) * teacher_temp
+        ))
+        self._stash = {}
+
+    def forward(self, student_output, teacher_output, epoch):
+        temp = self.teacher_temp_schedule[epoch]
+        loss, _ = _DinoLossFn.apply(student_output, teacher_output, self.center, self.ncrops,
+                                    1.0 / self.student_temp, 1.0 / float(temp), self._stash)
+        self.update_center(teacher_output)
+        return loss
+
+    @torch.no_grad()
+    def update_center(self, teacher_output):
+        """center <- center*m + (all_reduce(sum_rows teacher)/(rows*world))*(1-m)."""
+        _lib.require_cuda(teacher_output)
+        K = self.center.shape[-1]
+        tag = (teacher_output.data_ptr(), teacher_output._version, tuple(teacher_output.shape))
+        if self._stash.get("teacher") == tag:
+            colsum = self._stash.pop("colsum")       # by-product of forward: no extra pass
+            self._stash.pop("teacher", None)
+        else:
+            t = teacher_output.detach().contiguous()
+            colsum = torch.empty(K, dtype=torch.float32, device=t.device)
+            nbytes = 16 * K * 4
+            ws = _workspace(t.device, nbytes)
+            _lib.call("lafs_colsum", t.data_ptr(), t.shape[0], K, _lib.dtype_code(t), colsum.data_ptr(),
+                      ws.data_ptr(), nbytes, _lib.stream())
+        world = 1
+        if dist.is_available() and dist.is_initialized():
+            world = dist.get_world_size()
+            if world > 1:
+                dist.all_reduce(colsum)
+        center = self.center.float().contiguous()
+        new_center = torch.empty_like(center)
+        m = float(self.center_momentum)
+        _lib.call("lafs_center_ema", center.data_ptr(), colsum.data_ptr(),
+                  float(len(teacher_output) * world), float(np.float32(m)), float(np.float32(1.0 - m)),
+                  K, new_center.data_ptr(), _lib.stream())
+        self.center = new_center   # re-bound, like the reference (lafs_train.py:679)

@@ -1,0 +1,116 @@
+"""Landmark tail and bilinear patch gather with the reference's function surface.
+
+    extract_patches_pytorch_gridsample(imgs, landmarks, patch_shape, num_landm=49)
+        face_pre_pro/ViT_face.py:1615-1656 -- returns the [B,C,8r,8r] mosaic, differentiable
+        w.r.t. imgs and landmarks (the finetune path back-propagates into the landmark CNN).
+    extract_tokens(imgs, landmarks)            mosaic + einops rearrange of lafs_train.py:538 fused
+    landmark_post(raw, noise=None, extract_id=None)   ViT_face.py:1347-1378
+"""
+import torch
+
+from . import _lib
+
+# LAFS_COORD_DIV reproduces the reference's CPU arithmetic (and the committed golden vectors)
+# bit for bit; set to _lib.COORD_RECIP to reproduce eager-CUDA's reciprocal multiply instead.
+COORD_MODE = _lib.COORD_DIV
+
+
+class _GatherFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, imgs, theta, layout, coord_mode):
+        _lib.require_cuda(imgs, theta)
+        if imgs.dim() != 4 or theta.dim() != 3 or theta.shape[-1] != 2 or theta.shape[0] != imgs.shape[0]:
+            raise ValueError(f"imgs [B,C,H,W] / landmarks [B,n,2] expected, got {tuple(imgs.shape)} {tuple(theta.shape)}")
+        x = imgs.detach().float().contiguous()
+        th = theta.detach().float().contiguous()
+        Bv, Cc, H, W = x.shape
+        n = th.shape[1]
+        if layout == _lib.LAYOUT_TOKENS:
+            out = torch.empty(Bv, n, 64 * Cc, dtype=torch.float32, device=x.device)
+        else:
+            r = int(round(n ** 0.5))
+            if r * r != n:
+                raise ValueError(f"num_landm={n} is not a square number")
+            out = torch.empty(Bv, Cc, 8 * r, 8 * r, dtype=torch.float32, device=x.device)
+        _lib.call("lafs_gather_fwd", x.data_ptr(), th.data_ptr(), out.data_ptr(), Bv, Cc, H, W, n,
+                  layout, coord_mode, _lib.stream())
+        ctx.save_for_backward(x, th)
+        ctx.cfg = (layout, coord_mode)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, th = ctx.saved_tensors
+        layout, coord_mode = ctx.cfg
+        Bv, Cc, H, W = x.shape
+        n = th.shape[1]
+        g = grad_out.detach().float().contiguous()
+        need_img, need_th = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gi = torch.zeros_like(x) if need_img else None
+        gt = torch.empty_like(th) if need_th else None
+        _lib.call("lafs_gather_bwd", x.data_ptr(), th.data_ptr(), g.data_ptr(), _lib.ptr(gi), _lib.ptr(gt),
+                  Bv, Cc, H, W, n, layout, coord_mode, _lib.stream())
+        return gi, gt, None, None
+
+
+def extract_patches_pytorch_gridsample(imgs, landmarks, patch_shape, num_landm=49):
+    """Drop-in for the reference function.  `patch_shape` must describe 8x8 patches (the only
+    value the reference ever passes: ViT_face.py:606,1264)."""
+    ps = [int(v) for v in (patch_shape.tolist() if torch.is_tensor(patch_shape) else patch_shape)]
+    if ps != [8, 8]:
+        raise ValueError(f"only 8x8 patches are implemented (reference default), got {ps}")
+    return _GatherFn.apply(imgs, landmarks[:, :num_landm], _lib.LAYOUT_MOSAIC, COORD_MODE)
+
+
+def extract_tokens(imgs, landmarks, num_landm=None):
+    """[B, n, 192] tokens in '(p1 p2 c)' feature order, without materialising the mosaic."""
+    if num_landm is not None:
+        landmarks = landmarks[:, :num_landm]
+    return _GatherFn.apply(imgs, landmarks, _lib.LAYOUT_TOKENS, COORD_MODE)
+
+
+class _LandmarkPostFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, raw, scale):
+        x = raw.detach().float().contiguous()
+        B, m = x.shape
+        out = torch.empty(B, m // 2, 2, dtype=torch.float32, device=x.device)
+        _lib.call("lafs_landmark_post", x.data_ptr(), None, None, out.data_ptr(), None, B, m // 2, 0,
+                  float(scale), _lib.stream())
+        ctx.save_for_backward(x)
+        ctx.scale = float(scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        B, m = x.shape
+        g = g.detach().float().contiguous()
+        gr = torch.empty_like(x)
+        _lib.call("lafs_landmark_post_bwd", x.data_ptr(), g.data_ptr(), gr.data_ptr(), B, m // 2, ctx.scale,
+                  _lib.stream())
+        return gr, None
+
+
+def landmark_post(raw, noise=None, extract_id=None, scale=111.0):
+    """theta = (raw-min)/(max-min)*scale jointly per sample, view [B,n,2], + noise, gather.
+    With noise / extract_id (the SSL, no-grad use) the fused kernel applies them; the plain
+    form is differentiable w.r.t. raw (finetune path, ViT_face.py:694-706)."""
+    _lib.require_cuda(raw, noise, extract_id)
+    if raw.dim() != 2 or raw.shape[1] % 2:
+        raise ValueError(f"raw must be [B, 2n], got {tuple(raw.shape)}")
+    if noise is None and extract_id is None:
+        return _LandmarkPostFn.apply(raw, scale)
+    x = raw.detach().float().contiguous()
+    B, m = x.shape
+    n = m // 2
+    nz = None if noise is None else noise.detach().float().contiguous()
+    idx = None
+    keep = 0
+    if extract_id is not None:
+        idx = extract_id.detach().reshape(B, -1).to(torch.int64).contiguous()
+        keep = idx.shape[1]
+    out = torch.empty(B, keep if idx is not None else n, 2, dtype=torch.float32, device=x.device)
+    _lib.call("lafs_landmark_post", x.data_ptr(), _lib.ptr(nz), _lib.ptr(idx), out.data_ptr(), None,
+              B, n, keep, float(scale), _lib.stream())
+    return out

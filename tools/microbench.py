@@ -1,0 +1,84 @@
+"""Per-kernel timings on one B200 (development aid; bench.py is the judged entry point).
+Prints achieved GB/s against MEASURED_PEAKS.json for the HBM-bound kernels."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import lafs_cvpr2024_b200 as P  # noqa: E402
+from lafs_cvpr2024_b200 import _lib  # noqa: E402
+
+
+def timeit(fn, warmup=5, iters=20):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for a, b in ev:
+        a.record(); fn(); b.record()
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in ev)
+    return ts[len(ts) // 2], ts[0]
+
+
+def main():
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    res = {}
+    torch.manual_seed(0)
+    # ---- EMA: ViT-B student+head parameter list (147 tensors, ~110M params)
+    shapes = [(1, 197, 768), (1, 1, 768), (768, 192), (768,), (30000, 768)]
+    for _ in range(12):
+        shapes += [(768,), (768,), (2112, 768), (768, 704), (768,), (768,), (768,), (2048, 768), (2048,), (768, 2048), (768,)]
+    shapes += [(768,), (768,), (2048, 768), (2048,), (2048, 2048), (2048,), (256, 2048), (256,), (65536, 1), (65536, 256)]
+    q = [torch.randn(*s, device="cuda") for s in shapes]
+    k = [torch.randn(*s, device="cuda") for s in shapes]
+    nparam = sum(a.numel() for a in q)
+    plan = P.ema_update_(k, q, 0.996)
+    med, best = timeit(lambda: plan.step(0.996))
+    res["ema"] = {"tensors": len(shapes), "params": nparam, "ms": med, "ms_best": best,
+                  "GBps": 12 * nparam / med / 1e6, "frac_hbm": 12 * nparam / med / 1e6 / hbm}
+    del q, k
+    # ---- DINO config 2: B=256, K=65536, ncrops=6, bf16
+    for (B, K, ncrops) in [(256, 65536, 6), (256, 65536, 10)]:
+        s = torch.randn(ncrops * B, K, device="cuda", dtype=torch.bfloat16)
+        t = torch.randn(2 * B, K, device="cuda", dtype=torch.bfloat16)
+        c = torch.randn(K, device="cuda") * 0.1
+        loss = torch.empty((), device="cuda"); rs = torch.empty((ncrops + 2) * B, device="cuda"); cs = torch.empty(K, device="cuda")
+        nb = _lib.lib().lafs_dino_workspace_bytes(B, K, ncrops)
+        ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+        gs = torch.empty_like(s); go = torch.ones((), device="cuda")
+        f = lambda: _lib.call("lafs_dino_fwd", s.data_ptr(), t.data_ptr(), c.data_ptr(), B, K, ncrops, 10.0, 25.0, 1,
+                              loss.data_ptr(), rs.data_ptr(), cs.data_ptr(), ws.data_ptr(), nb, _lib.stream())
+        b = lambda: _lib.call("lafs_dino_bwd", s.data_ptr(), t.data_ptr(), c.data_ptr(), rs.data_ptr(), go.data_ptr(),
+                              B, K, ncrops, 10.0, 25.0, 1, gs.data_ptr(), _lib.stream())
+        mf, bf = timeit(f)
+        mb, bb = timeit(b)
+        fb = (ncrops + 2) * B * K * 2 + 8 * K
+        bbytes = (2 * ncrops + 2) * B * K * 2
+        res[f"dino_B{B}_K{K}_c{ncrops}"] = {
+            "fwd_ms": mf, "fwd_GBps": fb / mf / 1e6, "fwd_frac": fb / mf / 1e6 / hbm,
+            "bwd_ms": mb, "bwd_GBps": bbytes / mb / 1e6, "bwd_frac": bbytes / mb / 1e6 / hbm}
+        del s, t, gs
+    # ---- stand-alone gather, config 2 globals: 512 faces x 196 landmarks -> tokens fp32
+    imgs = torch.rand(512, 3, 112, 112, device="cuda") * 2 - 1
+    th = torch.rand(512, 196, 2, device="cuda") * 111
+    out = torch.empty(512, 196, 192, device="cuda")
+    g = lambda: _lib.call("lafs_gather_fwd", imgs.data_ptr(), th.data_ptr(), out.data_ptr(), 512, 3, 112, 112, 196, 1, 0, _lib.stream())
+    mg, bg = timeit(g)
+    gb = imgs.numel() * 4 + out.numel() * 4
+    res["gather_512x196"] = {"ms": mg, "GBps": gb / mg / 1e6, "frac_hbm": gb / mg / 1e6 / hbm}
+    print(json.dumps(res, indent=1))
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "microbench.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
