@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""LAFS hot-path benchmark (BASELINE.json metric: hot-path faces/sec, % of HBM/TC roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...     (N > 1)
+
+Workload at every N: BASELINE.json configs[1] -- "LAFS SSL pretrain step, Part-fViT ViT-B
+(196 landmark patches) + DINO head out_dim 65536, batch 256 synthetic faces" PER GPU (weak
+scaling; the only data-path collective is the reference's all-reduce of the DINO centre).
+One step = one pass of the hot path over one batch (lafs_cvpr2024_b200/ssl_step.py):
+landmark tail + patch gather for 2 global + 4 local views, DINO loss forward+backward+centre
+update on [6*256, 65536] / [2*256, 65536] bf16 logits, and the teacher EMA over the 147
+ViT-B + DINO-head parameter tensors.  The transformer blocks, DINO head MLP and landmark-CNN
+trunk are outside the path and are not run.
+
+`value`  : faces/s with every input resident in HBM when the timed region starts.
+`e2e`    : the same step through the public Python API with the per-step HOST inputs (the
+           data loader's images, CPU-generator noise and indices) copied from pinned memory
+           inside the timed region and the loss read back.  The logits and the parameters are
+           device-resident in the real system (they are produced/owned by the device-side
+           model), so they are not copied.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_PER_GPU = 256
+N_LOCAL = 4
+OUT_DIM = 65536
+N_LAND = 196
+KEEP_LOCAL = 36
+METRIC = "lafs_ssl_hot_path_faces_per_sec"
+
+
+def vit_b_param_shapes(out_dim=OUT_DIM):
+    """The 147 parameter tensors EMA'd every step: Part-fViT ViT-B backbone (incl. the unused
+    CosFace weight [30000,768]) + DINOHead.  110,261,248 parameters."""
+    shapes = [(1, 197, 768), (768, 192), (768,), (1, 1, 768)]
+    for _ in range(12):
+        shapes += [(768,), (768,), (2112, 768), (768, 704), (768,), (768,), (768,), (2048, 768), (2048,),
+                   (768, 2048), (768,)]
+    shapes += [(768,), (768,), (30000, 768)]
+    shapes += [(2048, 768), (2048,), (2048, 2048), (2048,), (256, 2048), (256,), (out_dim, 1), (out_dim, 256)]
+    return shapes
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return {"hbm": float(p["hbm_gbs"]), "tc": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                "src": "measured (MEASURED_PEAKS.json)"}
+    except Exception:
+        return {"hbm": 6650.0, "tc": 1590.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop_flag, self.th = index, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def start(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.th:
+            self.th.join(timeout=10)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+def make_host_inputs(B, seed):
+    """Per-step host-side inputs exactly as the reference produces them: the data loader's
+    augmented views (fp32, normalised to [-1,1]) and the CPU-generator noise / indices
+    (ViT_face.py:1361,1366).  Pinned."""
+    g = torch.Generator().manual_seed(seed)
+    L = N_LOCAL
+    h = {
+        "img_g": (torch.rand(2 * B, 3, 112, 112, generator=g) * 2 - 1),
+        "img_l": (torch.rand(L * B, 3, 112, 112, generator=g) * 2 - 1),
+        "noise_g": torch.randn(2 * B, N_LAND, 2, generator=g) * 5,
+        "noise_l": torch.randn(L * B, N_LAND, 2, generator=g) * 5,
+        "idx_l": torch.randint(0, N_LAND, (L * B, KEEP_LOCAL), generator=g),
+    }
+    return {k: v.pin_memory() for k, v in h.items()}
+
+
+def make_device_state(B, seed, dev):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    L = N_LOCAL
+    st = {
+        # outputs of the (out-of-path) landmark CNN / student / teacher networks
+        "raw_g": torch.randn(2 * B, 2 * N_LAND, device=dev, generator=g),
+        "raw_l": torch.randn(L * B, 2 * N_LAND, device=dev, generator=g),
+        "student_out": torch.randn((L + 2) * B, OUT_DIM, device=dev, generator=g).bfloat16(),
+        "teacher_out": torch.randn(2 * B, OUT_DIM, device=dev, generator=g).bfloat16(),
+    }
+    shapes = vit_b_param_shapes()
+    st["student_params"] = [torch.randn(*s, device=dev, generator=g) * 0.02 for s in shapes]
+    st["teacher_params"] = [p.clone() for p in st["student_params"]]
+    return st
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import lafs_cvpr2024_b200 as P
+    from lafs_cvpr2024_b200 import _lib
+    from lafs_cvpr2024_b200.ssl_step import SSLHotPath
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N>1 with torch.distributed.run")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if _lib.lib().lafs_device_ok() != 1:
+        raise SystemExit("bench.py needs a compute-capability 10.x device (B200)")
+
+    B, L = B_PER_GPU, N_LOCAL
+    host = make_host_inputs(B, 1000 + rank)
+    st = make_device_state(B, 2000 + rank, dev)
+    dev_in = {k: v.to(dev) for k, v in host.items()}
+    path = SSLHotPath(OUT_DIM, L, st["teacher_params"], st["student_params"])
+    path.loss.center = torch.randn(1, OUT_DIM, device=dev) * 0.1
+    sched = 0.996 + 0.5 * (1 - 0.996) * (1 - np.cos(np.pi * np.arange(100000) / 100000))  # utils.py:187-198
+    names = ["landmark+gather", "dino_fwd+center", "dino_bwd", "ema"]
+
+    def step(inp, it, evs=None):
+        def mark(i):
+            if evs is not None:
+                evs[i].record()
+        mark(0)
+        path.landmarks_and_tokens(st["raw_g"], inp["noise_g"], inp["img_g"], st["raw_l"], inp["noise_l"],
+                                  inp["idx_l"], inp["img_l"])
+        mark(1)
+        s = st["student_out"].requires_grad_(True)
+        s.grad = None
+        loss = path.loss(s, st["teacher_out"], it % 41)
+        mark(2)
+        loss.backward()
+        mark(3)
+        path.ema_step(sched[it])
+        mark(4)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, per_kernel=False):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(steps)] if per_kernel else None
+        barrier()
+        e0.record()
+        for i in range(steps):
+            fn(i, evs[i] if per_kernel else None)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        parts = None
+        if per_kernel:
+            parts = [float(np.mean([evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(steps)])) for j in range(4)]
+        return float(t.item()), parts
+
+    # ---- device-resident arm --------------------------------------------------------------
+    for i in range(args.warmup):
+        step(dev_in, i)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_total, parts = timed(lambda i, ev: step(dev_in, args.warmup + i, ev), args.steps, per_kernel=True)
+    clocks = sampler.stop() if sampler else None
+
+    # ---- end-to-end arm: per-step host inputs copied from pinned memory, loss read back --------
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    stage = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
+
+    def e2e_step(i, _ev):
+        for k, v in host.items():
+            stage[k].copy_(v, non_blocking=True)
+        loss = step(stage, args.warmup + i)
+        return float(loss.item())            # device -> host read of the step's result
+
+    for i in range(min(3, args.warmup)):
+        e2e_step(i, None)
+    ms_e2e, _ = timed(e2e_step, args.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    ms_step = ms_total / args.steps
+    faces = B * world
+    K, nc = OUT_DIM, L + 2
+    nparam = sum(int(np.prod(s)) for s in vit_b_param_shapes())
+    alg = {
+        "landmark+gather": {"bytes": (2 + L) * B * (3 * 112 * 112 * 4) + 2 * B * 196 * 192 * 4 + L * B * 36 * 192 * 4},
+        "dino_fwd+center": {"bytes": (nc + 2) * B * K * 2 + 8 * K},
+        "dino_bwd": {"bytes": (2 * nc + 2) * B * K * 2},
+        "ema": {"bytes": 12 * nparam},
+    }
+    kernels = {}
+    for n, ms in zip(names, parts):
+        gbps = alg[n]["bytes"] / ms / 1e6
+        kernels[n] = {"ms": round(ms, 5), "alg_bytes": alg[n]["bytes"], "GBps": round(gbps, 1),
+                      "frac_hbm": round(gbps / pk["hbm"], 4)}
+    dom = max(kernels, key=lambda n: kernels[n]["ms"])
+    line = {
+        "metric": METRIC, "value": round(faces / (ms_step / 1e3), 1), "unit": "faces/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 5),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 logits / fp32 images, params",
+        "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1]: LAFS SSL pretrain hot path, ViT-B, 196 landmark patches, "
+                               "out_dim 65536, 2 global + 4 local crops, batch 256 per GPU",
+                   "batch_per_gpu": B, "out_dim": K, "ncrops": nc, "ema_params": nparam, "ema_tensors": len(vit_b_param_shapes()),
+                   "l2": "inputs larger than L2 (logits 335 MB, images 231 MB, parameters 882 MB per step)",
+                   "parallelism": f"dp{world}"},
+        "e2e": {"value": round(faces / (ms_e2e / args.steps / 1e3), 1), "unit": "faces/s",
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 5)},
+        "gpu_launches": 13,
+        "clocks": clocks,
+        "roofline": {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["GBps"], "peak": pk["hbm"], "unit": "GB/s",
+                     "frac": kernels[dom]["frac_hbm"], "traffic": None, "peak_source": pk["src"]},
+        "kernels": kernels,
+    }
+    line["cpu_baseline"] = cpu_baseline(sample_faces=args.cpu_faces)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_step_time(sample_faces, threads, reps=1):
+    """The oracle port of the same step on the host cores: per-face parts on `sample_faces`
+    faces, the (batch-independent) EMA on the full parameter list.  Returns seconds per
+    256-face step, extrapolated linearly in the per-face parts."""
+    from oracle import lafs_oracle as O
+    torch.set_num_threads(threads)
+    Bs, L = sample_faces, N_LOCAL
+    g = torch.Generator().manual_seed(0)
+    img_g = torch.rand(2 * Bs, 3, 112, 112, generator=g) * 2 - 1
+    img_l = torch.rand(L * Bs, 3, 112, 112, generator=g) * 2 - 1
+    raw_g = torch.randn(2 * Bs, 392, generator=g)
+    raw_l = torch.randn(L * Bs, 392, generator=g)
+    s = torch.randn((L + 2) * Bs, OUT_DIM, generator=g)
+    t = torch.randn(2 * Bs, OUT_DIM, generator=g)
+    center = torch.zeros(1, OUT_DIM)
+    shapes = vit_b_param_shapes()
+    q = [torch.randn(*sh, generator=g) for sh in shapes]
+    k = [p.clone() for p in q]
+    best_face, best_ema = float("inf"), float("inf")
+    for _ in range(reps + 1):
+        t0 = time.perf_counter()
+        th_g = O.landmark_post(raw_g, torch.randn(2 * Bs, 196, 2) * 5)
+        O.extract_tokens(img_g, th_g)
+        th_l = O.landmark_post(raw_l, torch.randn(L * Bs, 196, 2) * 5, torch.randint(0, 196, (L * Bs, 36, 1)))
+        O.extract_tokens(img_l, th_l)
+        O.dino_loss_and_grad(s, t, center, L + 2, 0.04)
+        O.dino_center_update(center, t)
+        t1 = time.perf_counter()
+        O.ema_update_(k, q, 0.996)
+        t2 = time.perf_counter()
+        best_face, best_ema = min(best_face, t1 - t0), min(best_ema, t2 - t1)
+    return best_face * (B_PER_GPU / Bs) + best_ema, best_face, best_ema
+
+
+def cpu_baseline(sample_faces=256):
+    cores = os.cpu_count() or 1
+    sec, t_face, t_ema = cpu_step_time(sample_faces, cores, reps=3)
+    return {"value": round(B_PER_GPU / sec, 2), "unit": "faces/s", "cores": cores, "kind": "port",
+            "sample": f"oracle port (torch-CPU fp32, {cores} threads): per-face parts timed on {sample_faces} of 256 faces "
+                      f"({t_face:.2f} s) and scaled x{B_PER_GPU // sample_faces}; full 147-tensor EMA timed once ({t_ema:.2f} s)"}
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the path.  The reference is
+    Python and cannot travel to the GPU box (no /root/reference there), so this is the oracle
+    port (pinned bit-for-bit to the reference by tests/golden), on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    faces = args.cpu_faces
+    cpu_step_time(min(faces, 8), cores, reps=0)     # untimed: thread pool / allocator warm-up
+    secs = []
+    for _ in range(max(1, min(args.steps, 5))):
+        sec, t_face, t_ema = cpu_step_time(faces, cores, reps=1)
+        secs.append(sec)
+    sec = float(np.median(secs))
+    val = round(B_PER_GPU / sec, 2)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "faces/s", "n_gpus": args.gpus,
+        "steps": len(secs), "warmup": 1, "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1] hot path on host cores (bounded sample)", "batch_per_gpu": B_PER_GPU,
+                   "out_dim": OUT_DIM, "ncrops": N_LOCAL + 2},
+        "cpu_baseline": {"value": val, "unit": "faces/s", "cores": cores, "kind": "port",
+                         "sample": f"per-face parts on {faces} of 256 faces scaled x{B_PER_GPU // faces} + full EMA; "
+                                   "oracle port of the reference (Python reference cannot travel to the GPU box)"},
+        "e2e": {"value": val, "unit": "faces/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-faces", type=int, default=256, help="faces in the bounded CPU sample (256 = the full step)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

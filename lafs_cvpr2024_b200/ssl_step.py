@@ -1,0 +1,48 @@
+"""Host-side composition of the SSL hot path for one training step (what
+lafs_train.py:train_one_epoch does between the data loader and the optimizer, minus the
+transformer blocks / DINO head / landmark-CNN trunk, which stay stock PyTorch and are outside
+the path -- SURVEY.md section 8).
+
+Order of operations per step (reference line numbers in lafs_train.py):
+  :535,:541  landmark tail (min-max, +noise) for the two global views      -> theta_g [2B,196,2]
+  :565       landmark tail (+noise, 36 re-sampled landmarks) for L locals  -> theta_l [LB,36,2]
+  :538-:569  patch gather (+ rearrange) for every view                      -> tokens
+  :583       DINOLoss forward (+ centre update), :600 its backward
+  :610-613   teacher EMA over every parameter pair
+"""
+import torch
+
+from . import _lib
+from .dino_loss import DINOLoss
+from .ema import EmaPlan
+from .patches import extract_tokens, landmark_post
+
+
+class SSLHotPath:
+    """Holds the persistent state of the path (centre, EMA plan) and runs one step on the
+    current CUDA stream.  All inputs are CUDA tensors; nothing here touches the host."""
+
+    def __init__(self, out_dim, n_local, teacher_params, student_params, nepochs=41,
+                 warmup_teacher_temp=0.04, teacher_temp=0.07, warmup_teacher_temp_epochs=30):
+        self.n_local = n_local
+        self.loss = DINOLoss(out_dim, n_local + 2, warmup_teacher_temp, teacher_temp,
+                             warmup_teacher_temp_epochs, nepochs).cuda()
+        self.ema = EmaPlan(list(teacher_params), list(student_params))
+
+    def landmarks_and_tokens(self, raw_g, noise_g, img_g, raw_l, noise_l, idx_l, img_l):
+        """raw_* [*,392] landmark regressions, noise_* [*,196,2], idx_l [LB,36] int64,
+        img_* the augmented views the patches are cut from."""
+        theta_g = landmark_post(raw_g, noise_g)
+        tok_g = extract_tokens(img_g, theta_g)
+        theta_l = landmark_post(raw_l, noise_l, idx_l)
+        tok_l = extract_tokens(img_l, theta_l)
+        return theta_g, tok_g, theta_l, tok_l
+
+    def loss_and_grad(self, student_out, teacher_out, epoch):
+        s = student_out.detach().requires_grad_(True)
+        loss = self.loss(s, teacher_out, epoch)
+        loss.backward()
+        return loss.detach(), s.grad
+
+    def ema_step(self, m):
+        self.ema.step(m)

@@ -144,8 +144,9 @@ def test_dino_full_size_properties(P):
     loss = crit(sg, t, 10)
     loss.backward()
     # (a) every gradient row sums to zero:  n_v*sum(p) - sum_{iq != v} sum(q) = 0
+    #     (up to the bf16 rounding of the stored gradient: 2^-9 relative per element)
     rs = sg.grad.float().sum(1)
-    assert rs.abs().max() < 5e-4 * sg.grad.float().abs().sum(1).max()
+    assert rs.abs().max() < 2 ** -8 * sg.grad.float().abs().sum(1).max()
     # (b) centre update equals the closed form from an independent column sum
     ref_c = c0 * 0.9 + (t.float().sum(0, keepdim=True) / (2 * B)) * 0.1
     torch.testing.assert_close(crit.center, ref_c, rtol=1e-4, atol=1e-6)
