@@ -131,6 +131,45 @@ LAFS_API int lafs_gather_bwd(const float* imgs, const float* theta, const float*
                     float* grad_theta, int Bv, int C, int H, int W, int n, int layout,
                     int coord_mode, lafs_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * (4) CosFace / ArcFace margin head with fused softmax cross-entropy
+ *     replaces CosFace.forward (face_pre_pro/ViT_face.py:49-89) + the loss applied to its
+ *     output (train_largescale.py:601-604,820).  ArcFace is named by the reference
+ *     (ViT_face.py:416-417,654-655) but never defined there: paper form, parity unpinned.
+ *
+ * Operands are bf16 and L2-normalised per row: lafs_normalize_rows(x [R,D] of dtype) writes
+ * x/max(||x||,1e-12) as bf16 (F.normalize, ViT_face.py:53) and optionally 1/max(||x||,eps).
+ * Classes are sharded with torch.chunk's rule (ViT_face.py:56): a rank owns global classes
+ * [class_lo, class_lo + C_local).  label_a [B] int64 global ids; label_b (may be NULL) is the
+ * mixup partner (util/mixup_my.py:18-24) with weight 1-lam; kind 0 = CosFace s*(cos - m*t),
+ * 1 = ArcFace (hard labels).  D must be a multiple of 64, D <= 768.
+ *
+ * lafs_head_fwd   -> row_stats [B,4] = (max, sum-exp, z[label_a], z[label_b]) over the LOCAL
+ *                    classes, max in the log2 domain; no [B,C] tensor is written.
+ * lafs_head_merge -> merges nparts records [nparts,B,4] (one per rank) into [B,4].
+ * lafs_head_loss  -> row_lse2 [B] (log2-domain lse, kept for backward) and the mean loss.
+ * lafs_head_logits-> the full fp32 logits [B, C_local] (row stride ldc) for API parity with
+ *                    CosFace.forward.
+ * lafs_head_grad_logits -> (softmax - target)*gscale as bf16 [B, C_local] (row stride ldg),
+ *                    recomputing the logits on the tensor cores.
+ */
+LAFS_API int lafs_normalize_rows(const void* x, int dtype, int R, int D, void* out_bf16, float* inv_norm,
+                                 lafs_stream_t stream);
+LAFS_API size_t lafs_head_workspace_bytes(int B, int C_local, int D);
+LAFS_API int lafs_head_fwd(const void* e_hat, const void* w_hat, const int64_t* label_a, const int64_t* label_b,
+                           float lam, int B, int C_local, int D, int class_lo, float s, float m, int kind,
+                           float* row_stats, void* workspace, size_t workspace_bytes, lafs_stream_t stream);
+LAFS_API int lafs_head_merge(const float* parts, int nparts, int B, float* row_stats, lafs_stream_t stream);
+LAFS_API int lafs_head_loss(const float* row_stats, const int64_t* label_a, const int64_t* label_b, float lam, int B,
+                            float* row_lse2, float* loss_out, lafs_stream_t stream);
+LAFS_API int lafs_head_logits(const void* e_hat, const void* w_hat, const int64_t* label_a, const int64_t* label_b,
+                              float lam, int B, int C_local, int D, int class_lo, float s, float m, int kind,
+                              float* logits, long long ldc, lafs_stream_t stream);
+LAFS_API int lafs_head_grad_logits(const void* e_hat, const void* w_hat, const int64_t* label_a, const int64_t* label_b,
+                                   float lam, int B, int C_local, int D, int class_lo, float s, float m, int kind,
+                                   const float* row_lse2, float gscale, void* grad_bf16, long long ldg,
+                                   lafs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,7 +10,8 @@ All compute goes through liblafs_b200.so (C ABI in include/lafs_b200.h); there i
 from . import _lib  # noqa: F401
 from .dino_loss import DINOLoss  # noqa: F401
 from .ema import EmaPlan, ema_update_  # noqa: F401
+from .margin_head import ArcFace, CosFace, label_to_shard, shard_bounds  # noqa: F401
 from .patches import extract_patches_pytorch_gridsample, extract_tokens, landmark_post  # noqa: F401
 
-__all__ = ["DINOLoss", "EmaPlan", "ema_update_", "extract_patches_pytorch_gridsample", "extract_tokens",
+__all__ = ["ArcFace", "CosFace", "label_to_shard", "shard_bounds", "DINOLoss", "EmaPlan", "ema_update_", "extract_patches_pytorch_gridsample", "extract_tokens",
            "landmark_post"]

@@ -1,0 +1,467 @@
+// (4) CosFace / ArcFace margin head: normalised-embedding x normalised-weight GEMM on tcgen05
+// tensor cores with the margin, online softmax and cross-entropy statistics fused into the
+// TMEM epilogue -- the [B, C] logits are never materialised on the loss path.
+// Replaces CosFace.forward (face_pre_pro/ViT_face.py:49-89: CPU one_hot + H2D, two normalize
+// passes, ~8 element-wise passes over [B,C] fp32) + CrossEntropyLoss / SoftTargetCrossEntropy
+// (train_largescale.py:601-604,820).
+//
+// GEMM orientation: M = batch rows (128 per CTA, the E tile stays resident in shared memory),
+// N = classes (BN per UMMA), K = D.  One TMEM lane = one batch row, so the per-row softmax
+// statistics are plain sequential reductions over the columns a thread reads back (no shuffles).
+// Warp roles: 0 = TMA producer, 1 = UMMA issuer (+TMEM owner), 2..5 = epilogue.
+// Classes are sharded across GPUs with torch.chunk's rule (ViT_face.py:56); a rank passes its
+// shard [class_lo, class_lo + C_local) and gets per-row (max, sum-exp, target-logit) partials.
+#include "umma.cuh"
+#include "../../include/lafs_b200.h"
+
+namespace lafs {
+
+using namespace umma;
+
+constexpr int kHeadThreads = 192;
+constexpr int kBM = 128;
+constexpr float kLog2eH = 1.4426950408889634f;
+constexpr float kLn2H = 0.6931471805599453f;
+
+enum : int { HEAD_STATS = 0, HEAD_LOGITS = 1, HEAD_GRAD = 2 };
+
+struct HeadParams {
+  int B, C_local, D, class_lo;       // class_lo: global id of local class 0
+  int kch;                           // D / 64
+  int stages;                        // B-operand ring depth
+  int nranges;                       // CTAs per M tile
+  int nchunks;                       // ceil(C_local / BN)
+  float s, m, lam;                   // scale, margin, mixup lambda (1 for hard labels)
+  int kind;                          // 0 CosFace, 1 ArcFace
+  float cos_m, sin_m, th, mm;        // ArcFace constants
+  const int64_t* label_a;            // [B] global class ids
+  const int64_t* label_b;            // [B] or nullptr
+  float* part;                       // STATS: [B][nranges][4]
+  float* logits;                     // LOGITS: [B][ldc] fp32
+  long long ldc;
+  const float* row_lse2;             // GRAD: [B] log2-domain lse of the full row
+  __nv_bfloat16* grad;               // GRAD: [B][ldg] bf16  (softmax - target) * gscale
+  long long ldg;
+  float gscale;
+};
+
+// margin-adjusted, s-scaled logit (natural units) of a class whose target weight is t (0..1)
+__device__ __forceinline__ float margin_logit(float cosv, float t, const HeadParams& p) {
+  if (t == 0.f) return p.s * cosv;
+  if (p.kind == 0) return p.s * (cosv - p.m * t);  // CosFace, soft targets: s*(cos - m*t)
+  const float sine = sqrtf(fminf(fmaxf(1.f - cosv * cosv, 0.f), 1.f));
+  float phi = cosv * p.cos_m - sine * p.sin_m;
+  phi = cosv > p.th ? phi : cosv - p.mm;
+  return p.s * phi;  // ArcFace (hard labels only)
+}
+
+template <int BN, int MODE>
+__global__ void __launch_bounds__(kHeadThreads, 1)
+head_gemm_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_constant__ CUtensorMap tmap_w,
+                 const HeadParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [E tile: kch x 16 KB][B ring: stages x BN*128 B][barriers]
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_e = smem;
+  uint8_t* smem_b = smem_e + (size_t)p.kch * (kBM * 128);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.stages * (BN * 128));
+  uint64_t* e_full = bars;                      // 1
+  uint64_t* b_full = bars + 1;                  // stages
+  uint64_t* b_empty = b_full + p.stages;        // stages
+  uint64_t* acc_full = b_empty + p.stages;      // 2
+  uint64_t* acc_empty = acc_full + 2;           // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = blockIdx.x, range = blockIdx.y;
+  const int row0 = mt * kBM;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmap_e);
+    prefetch_tensormap(&tmap_w);
+    mbar_init(e_full, 1);
+    for (int i = 0; i < p.stages; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // chunks handled by this CTA: range, range + nranges, ...
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(e_full, (uint32_t)p.kch * (kBM * 128));
+      for (int k = 0; k < p.kch; ++k) tma_load_2d(smem_e + (size_t)k * (kBM * 128), &tmap_e, e_full, k * 64, row0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int chunk = range; chunk < p.nchunks; chunk += p.nranges) {
+        for (int k = 0; k < p.kch; ++k) {
+          mbar_wait(b_empty + stage, phase ^ 1);
+          mbar_arrive_expect_tx(b_full + stage, (uint32_t)(BN * 128));
+          tma_load_2d(smem_b + (size_t)stage * (BN * 128), &tmap_w, b_full + stage, k * 64, chunk * BN);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== UMMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN);
+      mbar_wait(e_full, 0);
+      tc_fence_after();
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int chunk = range; chunk < p.nchunks; chunk += p.nranges, ++it) {
+        const int buf = it & 1;
+        const uint32_t use = (uint32_t)(it >> 1);
+        mbar_wait(acc_empty + buf, (use & 1) ^ 1);   // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+        for (int k = 0; k < p.kch; ++k) {
+          mbar_wait(b_full + stage, phase);
+          tc_fence_after();
+          const uint64_t da = make_desc_k_sw128(smem_u32(smem_e + (size_t)k * (kBM * 128)));
+          const uint64_t db = make_desc_k_sw128(smem_u32(smem_b + (size_t)stage * (BN * 128)));
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            mma_f16_ss(d_tmem, desc_advance_k(da, kk * 16), desc_advance_k(db, kk * 16), idesc, (k | kk) != 0);
+          mma_commit(b_empty + stage);               // frees the smem stage when these UMMAs finish
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        mma_commit(acc_full + buf);                  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue warps (TMEM lane quarter = warp % 4) =====================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int b = row0 + row;
+    const bool row_ok = b < p.B;
+    long long la = -1, lb = -1;
+    float ta = 1.f, tb = 0.f;   // target weights of label_a / label_b
+    if (row_ok) {
+      la = p.label_a[b] - p.class_lo;
+      if (p.label_b != nullptr) {
+        lb = p.label_b[b] - p.class_lo;
+        ta = p.lam; tb = 1.f - p.lam;
+        if (lb == la) { ta = 1.f; tb = 0.f; lb = -1; }     // same class twice: weights add up
+      }
+    }
+    const float k2 = kLog2eH;                // natural logit -> log2 domain
+    float m_run = -INFINITY, l_run = 0.f, tgt_a = 0.f, tgt_b = 0.f;
+    float lse2 = 0.f;
+    if (MODE == HEAD_GRAD && row_ok) lse2 = p.row_lse2[b];
+    int it = 0;
+    for (int chunk = range; chunk < p.nchunks; chunk += p.nranges, ++it) {
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      mbar_wait(acc_full + buf, use & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+      for (int piece = 0; piece < BN / 32; ++piece) {
+        uint32_t raw[32];
+        tmem_ld_32x32b_x32(taddr + (uint32_t)(piece * 32), raw);
+        tmem_ld_wait();
+        const int cbase = chunk * BN + piece * 32;            // local class id of column 0
+        if (cbase >= p.C_local) break;                        // fully out-of-range piece
+        float z[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) z[j] = p.s * __uint_as_float(raw[j]);
+        // rare paths: target column(s) inside this piece, or ragged tail of the shard
+        const bool has_a = (unsigned long long)(la - cbase) < 32ull;
+        const bool has_b = (unsigned long long)(lb - cbase) < 32ull;
+        const bool tail = cbase + 32 > p.C_local;
+        if (has_a || has_b || tail) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int c = cbase + j;
+            if (has_a && c == (int)la) { z[j] = margin_logit(__uint_as_float(raw[j]), ta, p); tgt_a = z[j]; }
+            if (has_b && c == (int)lb) { z[j] = margin_logit(__uint_as_float(raw[j]), tb, p); tgt_b = z[j]; }
+            if (c >= p.C_local) z[j] = -INFINITY;
+          }
+        }
+        if (MODE == HEAD_STATS) {
+          float pm = z[0];
+#pragma unroll
+          for (int j = 1; j < 32; ++j) pm = fmaxf(pm, z[j]);
+          const float m_new = fmaxf(m_run, pm * k2);
+          l_run *= ex2(m_run - m_new);
+          float acc = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc += ex2(fmaf(z[j], k2, -m_new));
+          l_run += acc;
+          m_run = m_new;
+        } else if (MODE == HEAD_LOGITS) {
+          if (row_ok) {
+            float* dst = p.logits + (long long)b * p.ldc + cbase;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (cbase + j < p.C_local) dst[j] = z[j];
+          }
+        } else {  // HEAD_GRAD: (softmax - target) * gscale, bf16
+          if (row_ok) {
+            __nv_bfloat16* dst = p.grad + (long long)b * p.ldg + cbase;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int c = cbase + j;
+              float g = ex2(fmaf(z[j], k2, -lse2));
+              if (has_a && c == (int)la) g -= ta;
+              if (has_b && c == (int)lb) g -= tb;
+              if (c < p.C_local) dst[j] = __float2bfloat16_rn(g * p.gscale);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty + buf);
+    }
+    if (MODE == HEAD_STATS && row_ok) {
+      float4 o = make_float4(m_run, l_run, tgt_a, tgt_b);
+      *reinterpret_cast<float4*>(p.part + ((size_t)b * p.nranges + range) * 4) = o;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+// merge `nparts` partial (max2, sumexp, tgt_a, tgt_b) records per row -> one record per row
+__global__ void head_merge_kernel(const float* __restrict__ part, int B, int nparts, long long part_stride,
+                                  long long row_stride, float* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float m = -INFINITY, l = 0.f, ta = 0.f, tb = 0.f;
+  for (int r = 0; r < nparts; ++r) {
+    const float4 v = *reinterpret_cast<const float4*>(part + (size_t)r * part_stride + (size_t)b * row_stride);
+    if (v.x == -INFINITY) continue;     // CTA saw no valid class for this row
+    const float mn = fmaxf(m, v.x);
+    l = l * ex2(m - mn) + v.y * ex2(v.x - mn);
+    m = mn;
+    ta += v.z;
+    tb += v.w;
+  }
+  *reinterpret_cast<float4*>(out + (size_t)b * 4) = make_float4(m, l, ta, tb);
+}
+
+// per-row loss from merged statistics: lse(z) - (ta_w*z_a + tb_w*z_b); mean over rows.
+__global__ void __launch_bounds__(256)
+head_loss_kernel(const float* __restrict__ stats, const int64_t* __restrict__ label_a,
+                 const int64_t* __restrict__ label_b, float lam, int B, float* __restrict__ row_lse2,
+                 float* __restrict__ loss_out) {
+  __shared__ float red[256];
+  float acc = 0.f;
+  for (int b = threadIdx.x; b < B; b += 256) {
+    const float4 v = *reinterpret_cast<const float4*>(stats + (size_t)b * 4);
+    const float lse2 = v.x + lg2(v.y);
+    row_lse2[b] = lse2;
+    float wa = 1.f, wb = 0.f;
+    if (label_b != nullptr && label_b[b] != label_a[b]) { wa = lam; wb = 1.f - lam; }
+    acc += kLn2H * lse2 - (wa * v.z + wb * v.w);
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *loss_out = red[0] / (float)B;
+}
+
+// ---- operand preparation --------------------------------------------------------------------
+// rows of x [R, D] -> L2-normalised bf16 rows (+ 1/max(||x||, eps), F.normalize's eps=1e-12)
+template <typename T>
+__global__ void __launch_bounds__(256)
+normalize_rows_kernel(const T* __restrict__ x, int R, int D, __nv_bfloat16* __restrict__ out,
+                      float* __restrict__ inv_norm) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + warp;
+  if (r >= R) return;
+  const T* src = x + (size_t)r * D;
+  float ss = 0.f;
+  for (int i = lane; i < D; i += 32) {
+    const float v = (float)src[i];
+    ss = fmaf(v, v, ss);
+  }
+  ss = warp_sum(ss);
+  const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+  if (lane == 0 && inv_norm != nullptr) inv_norm[r] = inv;
+  for (int i = lane; i < D; i += 32) out[(size_t)r * D + i] = __float2bfloat16_rn((float)src[i] * inv);
+}
+
+TmaEncoder::EncodeTiled TmaEncoder::get() {
+  static EncodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiled>(p);
+  }
+  return fn;
+}
+
+int TmaEncoder::bf16_2d_sw128(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                              uint64_t row_stride_bytes, uint32_t box_rows) {
+  EncodeTiled enc = get();
+  LAFS_REQUIRE(enc != nullptr, LAFS_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LAFS_REQUIRE(r == CUDA_SUCCESS, LAFS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu", (int)r,
+               (unsigned long long)rows, (unsigned long long)cols);
+  return LAFS_OK;
+}
+
+struct HeadLaunch {
+  int BN, stages, nranges, nchunks, mtiles;
+  size_t smem;
+};
+
+static int plan_head(int B, int C_local, int D, HeadLaunch* hl) {
+  LAFS_REQUIRE(D % 64 == 0 && D >= 64 && D <= 768, LAFS_ERR_ARG, "margin head: D=%d must be a multiple of 64 in [64,768]", D);
+  const int kch = D / 64;
+  const size_t e_bytes = (size_t)kch * kBM * 128;
+  const size_t budget = 227 * 1024 - 2048;   // barriers + 1 KB alignment slack
+  int BN = 256;
+  if (e_bytes + 2 * (size_t)BN * 128 > budget) BN = 128;
+  int stages = (int)((budget - e_bytes) / ((size_t)BN * 128));
+  if (stages > 6) stages = 6;
+  LAFS_REQUIRE(stages >= 2, LAFS_ERR_ARG, "margin head: D=%d leaves no room for a 2-stage pipeline", D);
+  hl->BN = BN;
+  hl->stages = stages;
+  hl->mtiles = (B + kBM - 1) / kBM;
+  hl->nchunks = (C_local + BN - 1) / BN;
+  int per = kNumSMs / hl->mtiles;
+  if (per < 1) per = 1;
+  hl->nranges = hl->nchunks < per ? hl->nchunks : per;
+  hl->smem = e_bytes + (size_t)stages * BN * 128 + 1024 /*align*/ + 256 /*barriers*/;
+  return LAFS_OK;
+}
+
+template <int BN, int MODE>
+static int launch_head(const CUtensorMap& te, const CUtensorMap& tw, const HeadParams& p, const HeadLaunch& hl,
+                       cudaStream_t st) {
+  auto kern = head_gemm_kernel<BN, MODE>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hl.smem);
+  LAFS_REQUIRE(e == cudaSuccess, LAFS_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", hl.smem, cudaGetErrorString(e));
+  dim3 grid(hl.mtiles, hl.nranges);
+  kern<<<grid, kHeadThreads, hl.smem, st>>>(te, tw, p);
+  return check_launch("head_gemm_kernel");
+}
+
+static int head_common(const void* e_hat, const void* w_hat, const int64_t* label_a, const int64_t* label_b, float lam,
+                       int B, int C_local, int D, int class_lo, float s, float m, int kind, HeadParams* p,
+                       HeadLaunch* hl, CUtensorMap* te, CUtensorMap* tw, const char* who) {
+  LAFS_REQUIRE(e_hat && w_hat && label_a, LAFS_ERR_ARG, "%s: null pointer", who);
+  LAFS_REQUIRE(B > 0 && C_local > 0, LAFS_ERR_ARG, "%s: B=%d C_local=%d", who, B, C_local);
+  LAFS_REQUIRE(kind == 0 || kind == 1, LAFS_ERR_ARG, "%s: kind=%d (0 CosFace, 1 ArcFace)", who, kind);
+  LAFS_REQUIRE(!(kind == 1 && label_b != nullptr), LAFS_ERR_ARG, "%s: ArcFace takes hard labels only", who);
+  LAFS_REQUIRE((((uintptr_t)e_hat | (uintptr_t)w_hat) & 15u) == 0, LAFS_ERR_ARG, "%s: operands must be 16-byte aligned", who);
+  int rc = plan_head(B, C_local, D, hl);
+  if (rc) return rc;
+  rc = TmaEncoder::bf16_2d_sw128(te, e_hat, (uint64_t)B, (uint64_t)D, (uint64_t)D * 2, kBM);
+  if (rc) return rc;
+  rc = TmaEncoder::bf16_2d_sw128(tw, w_hat, (uint64_t)C_local, (uint64_t)D, (uint64_t)D * 2, (uint32_t)hl->BN);
+  if (rc) return rc;
+  *p = HeadParams{};
+  p->B = B; p->C_local = C_local; p->D = D; p->class_lo = class_lo;
+  p->kch = D / 64; p->stages = hl->stages; p->nranges = hl->nranges; p->nchunks = hl->nchunks;
+  p->s = s; p->m = m; p->lam = lam; p->kind = kind;
+  p->cos_m = cosf(m); p->sin_m = sinf(m);
+  p->th = cosf(3.14159265358979323846f - m); p->mm = sinf(3.14159265358979323846f - m) * m;
+  p->label_a = label_a; p->label_b = label_b;
+  return LAFS_OK;
+}
+
+}  // namespace lafs
+
+using namespace lafs;
+
+extern "C" int lafs_normalize_rows(const void* x, int dtype, int R, int D, void* out_bf16, float* inv_norm,
+                                   lafs_stream_t stream) {
+  LAFS_REQUIRE(x && out_bf16 && R >= 0 && D > 0, LAFS_ERR_ARG, "lafs_normalize_rows: bad argument");
+  LAFS_REQUIRE(dtype >= 0 && dtype <= 2, LAFS_ERR_ARG, "lafs_normalize_rows: dtype=%d", dtype);
+  if (R == 0) return LAFS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = (R + 7) / 8;
+  if (dtype == LAFS_F32) normalize_rows_kernel<float><<<grid, 256, 0, st>>>((const float*)x, R, D, (__nv_bfloat16*)out_bf16, inv_norm);
+  else if (dtype == LAFS_BF16) normalize_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, R, D, (__nv_bfloat16*)out_bf16, inv_norm);
+  else normalize_rows_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, R, D, (__nv_bfloat16*)out_bf16, inv_norm);
+  return check_launch("lafs_normalize_rows");
+}
+
+extern "C" size_t lafs_head_workspace_bytes(int B, int C_local, int D) {
+  HeadLaunch hl;
+  if (B <= 0 || C_local <= 0 || plan_head(B, C_local, D, &hl) != LAFS_OK) return 0;
+  return (size_t)hl.mtiles * kBM * hl.nranges * 4 * sizeof(float);
+}
+
+extern "C" int lafs_head_fwd(const void* e_hat, const void* w_hat, const int64_t* label_a, const int64_t* label_b,
+                             float lam, int B, int C_local, int D, int class_lo, float s, float m, int kind,
+                             float* row_stats, void* workspace, size_t workspace_bytes, lafs_stream_t stream) {
+  HeadParams p; HeadLaunch hl; CUtensorMap te, tw;
+  int rc = head_common(e_hat, w_hat, label_a, label_b, lam, B, C_local, D, class_lo, s, m, kind, &p, &hl, &te, &tw, "lafs_head_fwd");
+  if (rc) return rc;
+  LAFS_REQUIRE(row_stats && workspace, LAFS_ERR_ARG, "lafs_head_fwd: null output");
+  const size_t need = (size_t)hl.mtiles * kBM * hl.nranges * 4 * sizeof(float);
+  LAFS_REQUIRE(workspace_bytes >= need, LAFS_ERR_WORKSPACE, "lafs_head_fwd: workspace %zu < %zu", workspace_bytes, need);
+  p.part = (float*)workspace;
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = hl.BN == 256 ? launch_head<256, HEAD_STATS>(te, tw, p, hl, st) : launch_head<128, HEAD_STATS>(te, tw, p, hl, st);
+  if (rc) return rc;
+  head_merge_kernel<<<(B + 127) / 128, 128, 0, st>>>(p.part, B, hl.nranges, 4, (long long)hl.nranges * 4, row_stats);
+  return check_launch("lafs_head_fwd/merge");
+}
+
+extern "C" int lafs_head_logits(const void* e_hat, const void* w_hat, const int64_t* label_a, const int64_t* label_b,
+                                float lam, int B, int C_local, int D, int class_lo, float s, float m, int kind,
+                                float* logits, long long ldc, lafs_stream_t stream) {
+  HeadParams p; HeadLaunch hl; CUtensorMap te, tw;
+  int rc = head_common(e_hat, w_hat, label_a, label_b, lam, B, C_local, D, class_lo, s, m, kind, &p, &hl, &te, &tw, "lafs_head_logits");
+  if (rc) return rc;
+  LAFS_REQUIRE(logits && ldc >= C_local, LAFS_ERR_ARG, "lafs_head_logits: bad output");
+  p.logits = logits; p.ldc = ldc;
+  cudaStream_t st = (cudaStream_t)stream;
+  return hl.BN == 256 ? launch_head<256, HEAD_LOGITS>(te, tw, p, hl, st) : launch_head<128, HEAD_LOGITS>(te, tw, p, hl, st);
+}
+
+extern "C" int lafs_head_merge(const float* parts, int nparts, int B, float* row_stats, lafs_stream_t stream) {
+  LAFS_REQUIRE(parts && row_stats && nparts > 0 && B > 0, LAFS_ERR_ARG, "lafs_head_merge: bad argument");
+  head_merge_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(parts, B, nparts, (long long)B * 4, 4, row_stats);
+  return check_launch("lafs_head_merge");
+}
+
+extern "C" int lafs_head_loss(const float* row_stats, const int64_t* label_a, const int64_t* label_b, float lam, int B,
+                              float* row_lse2, float* loss_out, lafs_stream_t stream) {
+  LAFS_REQUIRE(row_stats && label_a && row_lse2 && loss_out && B > 0, LAFS_ERR_ARG, "lafs_head_loss: bad argument");
+  head_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(row_stats, label_a, label_b, lam, B, row_lse2, loss_out);
+  return check_launch("lafs_head_loss");
+}
+
+extern "C" int lafs_head_grad_logits(const void* e_hat, const void* w_hat, const int64_t* label_a, const int64_t* label_b,
+                                     float lam, int B, int C_local, int D, int class_lo, float s, float m, int kind,
+                                     const float* row_lse2, float gscale, void* grad_bf16, long long ldg,
+                                     lafs_stream_t stream) {
+  HeadParams p; HeadLaunch hl; CUtensorMap te, tw;
+  int rc = head_common(e_hat, w_hat, label_a, label_b, lam, B, C_local, D, class_lo, s, m, kind, &p, &hl, &te, &tw, "lafs_head_grad_logits");
+  if (rc) return rc;
+  LAFS_REQUIRE(row_lse2 && grad_bf16 && ldg >= C_local, LAFS_ERR_ARG, "lafs_head_grad_logits: bad argument");
+  p.row_lse2 = row_lse2; p.grad = (__nv_bfloat16*)grad_bf16; p.ldg = ldg; p.gscale = gscale;
+  cudaStream_t st = (cudaStream_t)stream;
+  return hl.BN == 256 ? launch_head<256, HEAD_GRAD>(te, tw, p, hl, st) : launch_head<128, HEAD_GRAD>(te, tw, p, hl, st);
+}

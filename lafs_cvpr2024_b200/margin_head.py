@@ -1,0 +1,164 @@
+"""CosFace / ArcFace margin heads with the reference's module surface on tcgen05 kernels.
+
+    CosFace(in_features, out_features, device_id, s=64.0, m=0.4)     face_pre_pro/ViT_face.py:26-96
+      .forward(input, label) -> [B, C] fp32 logits   (label [B] int or [B, C] float soft targets)
+      .forward_loss(input, label, label_b=None, lam=1.0) -> scalar CE loss, logits never materialised
+      parameter `weight` [C, D]  (registered as `loss` in the backbone -> checkpoint key loss.weight)
+    ArcFace(...)  same surface; the reference names it (ViT_face.py:416-417) but never defines it,
+      so its formula follows the ArcFace paper (parity unpinned, see oracle/lafs_oracle.py).
+
+Class sharding: `shard=(rank, world)` keeps only rows [lo, hi) of torch.chunk(weight, world)
+(ViT_face.py:56) on this rank; forward_loss then exchanges only per-row (max, sum-exp,
+target-logit) records over the process group.
+"""
+import math
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F  # noqa: F401  (kept for parity of the module namespace)
+from torch.nn import Parameter
+
+from . import _lib
+
+KIND_COSFACE, KIND_ARCFACE = 0, 1
+
+
+def shard_bounds(num_classes, world):
+    """[lo, hi) per rank, identical to torch.chunk(weight, world, dim=0): chunk = ceil(C/R)."""
+    step = -(-num_classes // world)
+    return [(min(r * step, num_classes), min((r + 1) * step, num_classes)) for r in range(world)]
+
+
+def label_to_shard(label, num_classes, world):
+    """(owning rank, local row) of each label -- integer, bit-exact with torch.chunk's layout."""
+    step = -(-num_classes // world)
+    return torch.div(label, step, rounding_mode="floor"), label % step
+
+
+def two_hot_from_dense(target):
+    """Recovers (label_a, label_b, lam) from a dense mixup target [B, C] (util/mixup_my.py:18-24:
+    lam at label[i], 1-lam at label[B-1-i], exactly <= 2 non-zeros per row)."""
+    vals, idx = target.topk(2, dim=1)
+    if bool(((target != 0).sum(1) > 2).any()):
+        raise ValueError("dense soft targets with more than two non-zeros per row are not supported "
+                         "by the fused head (the reference's Mixup produces at most two)")
+    la, lb = idx[:, 0], idx[:, 1]
+    lb = torch.where(vals[:, 1] == 0, la, lb)
+    # rows whose two classes coincide (or hard rows) have val0 == 1; lam is a batch scalar otherwise
+    mixed = vals[:, 1] != 0
+    lam = float(vals[mixed, 0].max()) if bool(mixed.any()) else 1.0
+    return la, lb, lam
+
+
+def _prep(x, want_inv=False):
+    x = x.detach().contiguous()
+    R, D = x.shape
+    out = torch.empty(R, D, dtype=torch.bfloat16, device=x.device)
+    inv = torch.empty(R, dtype=torch.float32, device=x.device) if want_inv else None
+    _lib.call("lafs_normalize_rows", x.data_ptr(), _lib.dtype_code(x), R, D, out.data_ptr(), _lib.ptr(inv),
+              _lib.stream())
+    return out, inv
+
+
+class _MarginHead(nn.Module):
+    kind = KIND_COSFACE
+
+    def __init__(self, in_features, out_features, device_id, s=64.0, m=0.4, shard=None):
+        super().__init__()
+        self.in_features = in_features
+        self.out_features = out_features
+        self.device_id = device_id
+        self.s = s
+        self.m = m
+        self.shard = shard
+        lo, hi = (0, out_features) if shard is None else shard_bounds(out_features, shard[1])[shard[0]]
+        self.class_lo, self.class_hi = lo, hi
+        full = torch.empty(out_features, in_features)
+        nn.init.xavier_uniform_(full)                     # same init as the reference (ViT_face.py:46-47)
+        self.weight = Parameter(full[lo:hi].clone())
+
+    # ---- helpers -----------------------------------------------------------------------------
+    def _labels(self, label, label_b, lam):
+        if label.dim() > 1:                                # dense [B, C] soft targets (reference API)
+            if self.kind == KIND_ARCFACE:
+                raise ValueError("ArcFace takes hard labels")
+            la, lb, lam = two_hot_from_dense(label)
+            return la.to(torch.int64).contiguous(), lb.to(torch.int64).contiguous(), lam
+        la = label.to(torch.int64).contiguous()
+        lb = None if label_b is None else label_b.to(torch.int64).contiguous()
+        return la, lb, float(lam)
+
+    def _operands(self, input):
+        _lib.require_cuda(input, self.weight)
+        if input.dim() != 2 or input.shape[1] != self.in_features:
+            raise ValueError(f"input must be [B, {self.in_features}], got {tuple(input.shape)}")
+        e_hat, _ = _prep(input)
+        w_hat, _ = _prep(self.weight)
+        return e_hat, w_hat
+
+    # ---- reference surface ---------------------------------------------------------------------
+    def forward(self, input, label):
+        """Full logits s*(cos - m*target) for the local classes (all classes when unsharded)."""
+        la, lb, lam = self._labels(label, None, 1.0)
+        e_hat, w_hat = self._operands(input)
+        B, C = input.shape[0], self.weight.shape[0]
+        out = torch.empty(B, C, dtype=torch.float32, device=input.device)
+        _lib.call("lafs_head_logits", e_hat.data_ptr(), w_hat.data_ptr(), la.data_ptr(), _lib.ptr(lb), lam,
+                  B, C, self.in_features, self.class_lo, float(self.s), float(self.m), self.kind,
+                  out.data_ptr(), C, _lib.stream())
+        return out
+
+    def forward_stats(self, input, label, label_b=None, lam=1.0):
+        """Per-row (max2, sum-exp, z_a, z_b) over this rank's classes; [B,4] fp32."""
+        la, lb, lam = self._labels(label, label_b, lam)
+        e_hat, w_hat = self._operands(input)
+        B, C = input.shape[0], self.weight.shape[0]
+        stats = torch.empty(B, 4, dtype=torch.float32, device=input.device)
+        nbytes = _lib.lib().lafs_head_workspace_bytes(B, C, self.in_features)
+        if nbytes == 0:
+            raise ValueError(f"unsupported head shape B={B} C={C} D={self.in_features}")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=input.device)
+        _lib.call("lafs_head_fwd", e_hat.data_ptr(), w_hat.data_ptr(), la.data_ptr(), _lib.ptr(lb), lam,
+                  B, C, self.in_features, self.class_lo, float(self.s), float(self.m), self.kind,
+                  stats.data_ptr(), ws.data_ptr(), nbytes, _lib.stream())
+        return stats, (la, lb, lam, e_hat, w_hat)
+
+    @torch.no_grad()
+    def forward_loss(self, input, label, label_b=None, lam=1.0):
+        """Fused head + cross-entropy (mean over the batch every rank sees).  Forward only in
+        this revision; returns (loss, row_lse2)."""
+        stats, (la, lb, lam, _, _) = self.forward_stats(input, label, label_b, lam)
+        B = input.shape[0]
+        if self.shard is not None and self.shard[1] > 1:
+            parts = torch.empty(self.shard[1], B, 4, dtype=torch.float32, device=input.device)
+            dist.all_gather_into_tensor(parts, stats)
+            merged = torch.empty_like(stats)
+            _lib.call("lafs_head_merge", parts.data_ptr(), self.shard[1], B, merged.data_ptr(), _lib.stream())
+            stats = merged
+        loss = torch.empty((), dtype=torch.float32, device=input.device)
+        lse2 = torch.empty(B, dtype=torch.float32, device=input.device)
+        _lib.call("lafs_head_loss", stats.data_ptr(), la.data_ptr(), _lib.ptr(lb), lam, B, lse2.data_ptr(),
+                  loss.data_ptr(), _lib.stream())
+        return loss, lse2
+
+    def __repr__(self):
+        return self.__class__.__name__ + '(' \
+            + 'in_features = ' + str(self.in_features) \
+            + ', out_features = ' + str(self.out_features) \
+            + ', s = ' + str(self.s) \
+            + ', m = ' + str(self.m) + ')'
+
+
+class CosFace(_MarginHead):
+    kind = KIND_COSFACE
+
+    def __init__(self, in_features, out_features, device_id, s=64.0, m=0.4, shard=None):
+        super().__init__(in_features, out_features, device_id, s, m, shard)
+
+
+class ArcFace(_MarginHead):
+    kind = KIND_ARCFACE
+
+    def __init__(self, in_features, out_features, device_id, s=64.0, m=0.5, shard=None):
+        super().__init__(in_features, out_features, device_id, s, m, shard)

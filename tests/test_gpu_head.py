@@ -1,0 +1,132 @@
+"""GPU parity: CosFace / ArcFace margin head (tcgen05 GEMM + fused softmax-CE epilogue)
+against golden vectors (reference CosFace) and the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lafs_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+@pytest.fixture(scope="module")
+def P():
+    import lafs_cvpr2024_b200 as pkg
+    return pkg
+
+
+def bf16_round(x):
+    return x.bfloat16().float()
+
+
+def oracle_on_bf16_operands(x, w, label, kind="cosface", label_b=None, lam=1.0):
+    """compare against the oracle evaluated in fp32 on the same bf16-rounded
+    normalised operands the tensor cores see."""
+    xh = bf16_round(torch.nn.functional.normalize(x))
+    wh = bf16_round(torch.nn.functional.normalize(w))
+    # operands are (almost) unit rows already; renormalisation inside the oracle is harmless
+    return O.head_loss_and_grads(xh, wh, label, kind, label_b=label_b, lam=lam)
+
+
+def make_head(P, cls, w, **kw):
+    h = cls(w.shape[1], w.shape[0], None, **kw).cuda()
+    with torch.no_grad():
+        h.weight.copy_(w)
+    return h
+
+
+def test_cosface_golden_logits_and_loss(P, golden):
+    g = golden("cosface")
+    x, w, lab = T(g["x"]), T(g["weight"]), T(g["label"])
+    h = make_head(P, P.CosFace, w)
+    logits = h(x.cuda(), lab.cuda()).cpu()
+    ref = T(g["logits_hard"])
+    assert logits.shape == ref.shape
+    assert (logits - ref).abs().max() <= 1e-3 * ref.abs().max() * 8   # bf16 operands: ~2^-9 * 64
+    loss, _ = h.forward_loss(x.cuda(), lab.cuda())
+    assert abs(float(loss) - float(g["loss_hard"])) <= 5e-3 * abs(float(g["loss_hard"]))
+    # soft (mixup) targets through the dense [B, C] reference API and through the two-label form
+    soft = O.mixup_target(lab, w.shape[0], float(g["lam"]))
+    logits_s = h(x.cuda(), soft.cuda()).cpu()
+    assert (logits_s - T(g["logits_soft"])).abs().max() <= 8e-3 * ref.abs().max()
+    loss_s, _ = h.forward_loss(x.cuda(), lab.cuda(), T(g["label_b"]).cuda(), float(g["lam"]))
+    assert abs(float(loss_s) - float(g["loss_soft"])) <= 5e-3 * abs(float(g["loss_soft"]))
+    loss_d, _ = h.forward_loss(x.cuda(), soft.cuda())
+    assert abs(float(loss_d) - float(loss_s)) <= 1e-5 * abs(float(loss_s))
+
+
+@pytest.mark.parametrize("B,C,D", [(8, 1000, 64), (130, 777, 128), (512, 5000, 512), (64, 3001, 768), (1, 9, 64),
+                                   (300, 40000, 512)])
+@pytest.mark.parametrize("kind", ["cosface", "arcface"])
+def test_head_vs_oracle_on_same_bf16_operands(P, B, C, D, kind):
+    torch.manual_seed(B + C + D)
+    x = torch.randn(B, D)
+    w = torch.randn(C, D) * 0.05
+    lab = torch.randint(0, C, (B,))
+    lab[0] = C - 1
+    cls = P.CosFace if kind == "cosface" else P.ArcFace
+    h = make_head(P, cls, w)
+    ref_loss, ref_logits, _, _ = oracle_on_bf16_operands(x, w, lab, kind)
+    logits = h(x.cuda(), lab.cuda()).cpu()
+    scale = ref_logits.abs().max()
+    assert (logits - ref_logits).abs().max() <= 1e-3 * scale, float((logits - ref_logits).abs().max())
+    loss, lse2 = h.forward_loss(x.cuda(), lab.cuda())
+    assert abs(float(loss) - float(ref_loss)) <= 1e-3 * abs(float(ref_loss)), (float(loss), float(ref_loss))
+    ref_lse = torch.logsumexp(ref_logits, 1)
+    assert (lse2.cpu() * np.log(2.0) - ref_lse).abs().max() <= 1e-3 * ref_lse.abs().max()
+
+
+def test_head_mixup_soft_labels_vs_oracle(P):
+    torch.manual_seed(5)
+    B, C, D = 257, 3333, 256
+    x, w = torch.randn(B, D), torch.randn(C, D)
+    lab = torch.randint(0, C, (B,))
+    lam = 0.37
+    h = make_head(P, P.CosFace, w)
+    ref_loss, ref_logits, _, _ = oracle_on_bf16_operands(x, w, lab, "cosface", label_b=lab.flip(0), lam=lam)
+    loss, _ = h.forward_loss(x.cuda(), lab.cuda(), lab.flip(0).cuda(), lam)
+    assert abs(float(loss) - float(ref_loss)) <= 1e-3 * abs(float(ref_loss))
+    dense = O.mixup_target(lab, C, lam)
+    logits = h(x.cuda(), dense.cuda()).cpu()
+    assert (logits - ref_logits).abs().max() <= 1e-3 * ref_logits.abs().max()
+
+
+def test_shard_mapping_bit_exact(P, golden):
+    for row in golden("shards")["table"]:
+        C, R, sizes = int(row[0]), int(row[1]), [int(v) for v in row[2:] if v > 0]
+        b = [hi - lo for lo, hi in P.shard_bounds(C, R) if hi > lo]
+        assert b == sizes
+    lab = torch.tensor([0, 11678, 11679, 93430])
+    sh, loc = P.label_to_shard(lab, 93431, 8)
+    assert sh.tolist() == [0, 0, 1, 7] and loc.tolist() == [0, 11678, 0, 93430 - 7 * 11679]
+
+
+def test_sharded_stats_merge_equals_unsharded(P):
+    """Class-parallel path on one GPU: every shard's partial statistics merged == full softmax."""
+    torch.manual_seed(7)
+    B, C, D, R = 96, 10007, 512, 8
+    x, w = torch.randn(B, D), torch.randn(C, D)
+    lab = torch.randint(0, C, (B,))
+    full = make_head(P, P.CosFace, w)
+    loss_full, lse_full = full.forward_loss(x.cuda(), lab.cuda())
+    from lafs_cvpr2024_b200 import _lib
+    parts = []
+    for r, (lo, hi) in enumerate(P.shard_bounds(C, R)):
+        h = P.CosFace(D, C, None, shard=(r, R)).cuda()
+        assert h.weight.shape[0] == hi - lo
+        with torch.no_grad():
+            h.weight.copy_(w[lo:hi])
+        st, _ = h.forward_stats(x.cuda(), lab.cuda())
+        parts.append(st)
+    parts = torch.stack(parts).contiguous()
+    merged = torch.empty(B, 4, device="cuda")
+    _lib.call("lafs_head_merge", parts.data_ptr(), R, B, merged.data_ptr(), _lib.stream())
+    loss = torch.empty((), device="cuda"); lse2 = torch.empty(B, device="cuda")
+    la = lab.cuda()
+    _lib.call("lafs_head_loss", merged.data_ptr(), la.data_ptr(), None, 1.0, B, lse2.data_ptr(), loss.data_ptr(), _lib.stream())
+    assert abs(float(loss) - float(loss_full)) <= 1e-5 * abs(float(loss_full))
+    torch.testing.assert_close(lse2, lse_full, rtol=1e-5, atol=1e-5)

@@ -75,6 +75,24 @@ def main():
     mg, bg = timeit(g)
     gb = imgs.numel() * 4 + out.numel() * 4
     res["gather_512x196"] = {"ms": mg, "GBps": gb / mg / 1e6, "frac_hbm": gb / mg / 1e6 / hbm}
+    if "--head" in sys.argv or True:
+        tc = peaks.get("bf16_tflops_sustained", 1400.0)
+        for (B, C, D) in [(512, 93431, 512), (1024, 205990, 512), (512, 93431, 768)]:
+            h = P.CosFace(D, C, None).cuda()
+            x = torch.randn(B, D, device="cuda")
+            lab = torch.randint(0, C, (B,), device="cuda")
+            st, (la, lb, lam, e_hat, w_hat) = h.forward_stats(x, lab)
+            nb = _lib.lib().lafs_head_workspace_bytes(B, C, D)
+            ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+            f = lambda: _lib.call("lafs_head_fwd", e_hat.data_ptr(), w_hat.data_ptr(), la.data_ptr(), None, 1.0, B, C, D, 0,
+                                  64.0, 0.4, 0, st.data_ptr(), ws.data_ptr(), nb, _lib.stream())
+            mf, bf = timeit(f)
+            prep = lambda: _lib.call("lafs_normalize_rows", h.weight.data_ptr(), 0, C, D, w_hat.data_ptr(), None, _lib.stream())
+            mp, bp = timeit(prep)
+            fl = 2.0 * B * C * D
+            res[f"head_fwd_B{B}_C{C}_D{D}"] = {"ms": mf, "TFLOPs": fl / mf / 1e9, "frac_tc": fl / mf / 1e9 / tc,
+                                               "w_prep_ms": mp, "w_prep_GBps": C * D * 6 / mp / 1e6}
+            del h, w_hat
     print(json.dumps(res, indent=1))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", "microbench.json"), "w"), indent=1)
