@@ -186,10 +186,16 @@ def cosine_scheduler(base_value, final_value, epochs, niter_per_ep):
 # --------------------------------------------------------------------------------------
 # (4) margin heads + cross entropy + class sharding
 # --------------------------------------------------------------------------------------
-def cosface_logits(x, weight, label, s=64.0, m=0.4):
+def _cosine(x, weight, pre_normalized):
+    if pre_normalized:   # operands already unit rows (e.g. the bf16-rounded rows a tensor core sees)
+        return F.linear(x, weight)
+    return F.linear(F.normalize(x), F.normalize(weight))
+
+
+def cosface_logits(x, weight, label, s=64.0, m=0.4, pre_normalized=False):
     """CosFace.forward, face_pre_pro/ViT_face.py:49-89 (device_id=None branch).
     label [B] integer or [B,C] float soft targets."""
-    cosine = F.linear(F.normalize(x), F.normalize(weight))
+    cosine = _cosine(x, weight, pre_normalized)
     phi = cosine - m
     if label.dim() > 1:
         one_hot = label
@@ -199,9 +205,9 @@ def cosface_logits(x, weight, label, s=64.0, m=0.4):
     return (one_hot * phi + (1.0 - one_hot) * cosine) * s
 
 
-def arcface_logits(x, weight, label, s=64.0, m=0.5):
+def arcface_logits(x, weight, label, s=64.0, m=0.5, pre_normalized=False):
     """PARITY UNPINNED (see module docstring): ArcFace with the 'easy_margin=False' form."""
-    cosine = F.linear(F.normalize(x), F.normalize(weight))
+    cosine = _cosine(x, weight, pre_normalized)
     sine = torch.sqrt((1.0 - cosine * cosine).clamp(0, 1))
     cos_m, sin_m = math.cos(m), math.sin(m)
     th, mm = math.cos(math.pi - m), math.sin(math.pi - m) * m
@@ -231,7 +237,7 @@ def mixup_target(label, num_classes, lam):
 
 
 def head_loss_and_grads(x, weight, label, kind="cosface", s=64.0, m=None, label_b=None, lam=1.0,
-                        grad_out=1.0):
+                        grad_out=1.0, pre_normalized=False):
     """logits -> CE (hard, or two-hot soft targets when label_b is given) with autograd
     gradients w.r.t. x and weight.  fp32."""
     x = x.detach().float().clone().requires_grad_(True)
@@ -240,16 +246,16 @@ def head_loss_and_grads(x, weight, label, kind="cosface", s=64.0, m=None, label_
     if kind == "cosface":
         mm = 0.4 if m is None else m
         if label_b is None:
-            logits = cosface_logits(x, w, label, s, mm)
+            logits = cosface_logits(x, w, label, s, mm, pre_normalized)
             loss = cross_entropy(logits, label)
         else:
             tgt = (F.one_hot(label.long(), C).float() * lam
                    + F.one_hot(label_b.long(), C).float() * (1.0 - lam))
-            logits = cosface_logits(x, w, tgt, s, mm)
+            logits = cosface_logits(x, w, tgt, s, mm, pre_normalized)
             loss = soft_target_cross_entropy(logits, tgt)
     else:
         mm = 0.5 if m is None else m
-        logits = arcface_logits(x, w, label, s, mm)
+        logits = arcface_logits(x, w, label, s, mm, pre_normalized)
         loss = cross_entropy(logits, label)
     gx, gw = torch.autograd.grad(loss, (x, w), torch.tensor(grad_out))
     return loss.detach(), logits.detach(), gx, gw

@@ -28,8 +28,7 @@ def oracle_on_bf16_operands(x, w, label, kind="cosface", label_b=None, lam=1.0):
     normalised operands the tensor cores see."""
     xh = bf16_round(torch.nn.functional.normalize(x))
     wh = bf16_round(torch.nn.functional.normalize(w))
-    # operands are (almost) unit rows already; renormalisation inside the oracle is harmless
-    return O.head_loss_and_grads(xh, wh, label, kind, label_b=label_b, lam=lam)
+    return O.head_loss_and_grads(xh, wh, label, kind, label_b=label_b, lam=lam, pre_normalized=True)
 
 
 def make_head(P, cls, w, **kw):
