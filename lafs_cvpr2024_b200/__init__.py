@@ -11,7 +11,8 @@ from . import _lib  # noqa: F401
 from .dino_loss import DINOLoss  # noqa: F401
 from .ema import EmaPlan, ema_update_  # noqa: F401
 from .margin_head import ArcFace, CosFace, label_to_shard, shard_bounds  # noqa: F401
-from .patches import extract_patches_pytorch_gridsample, extract_tokens, landmark_post  # noqa: F401
+from .patches import (PatchEmbedWeights, extract_patches_pytorch_gridsample, extract_tokens,  # noqa: F401
+                      gather_embed, landmark_post)
 
 __all__ = ["ArcFace", "CosFace", "label_to_shard", "shard_bounds", "DINOLoss", "EmaPlan", "ema_update_", "extract_patches_pytorch_gridsample", "extract_tokens",
-           "landmark_post"]
+           "landmark_post", "gather_embed", "PatchEmbedWeights"]

@@ -1,0 +1,315 @@
+// (1b) Fused landmark patch gather -> patch_to_embedding on tcgen05 tensor cores.
+// Replaces extract_patches_pytorch_gridsample + einops rearrange + nn.Linear(192, dim)
+// (face_pre_pro/ViT_face.py:1615-1656, lafs_train.py:538, ViT_face.py:760-761): the fp32 mosaic,
+// the re-laid-out token tensor and (for the two global SSL views) the second gather for the
+// teacher are never written to HBM -- one pass reads each image once and writes only the
+// embedded tokens of up to two models (student + teacher) that share the gathered patches.
+//
+// One persistent CTA per SM walks over faces.  Per face:
+//   plane producer : cp.async.bulk of the three 112x112 fp32 channel planes into a 2-slot ring
+//   gather warps   : bilinear 8x8 patches from the staged plane -> bf16 token tile in the UMMA
+//                    K-major/128B-swizzle layout (tokens x 192), K order = c*64 + j*8 + i
+//   W producer     : TMA of [128 x 64] bf16 weight chunks (weights pre-permuted to that K order)
+//   UMMA issuer    : D[128 dims x N tokens] += Wchunk[128 x 192] * Tok[N x 192]^T   (tokens on the
+//                    N side: N = 208 for 196 landmarks, 48 for 36 -- no 128-row padding waste)
+//   epilogue warps : TMEM -> +bias -> bf16 -> out[model][face, token, dim]
+// The bf16 path does not need the reference's fp32 coordinate round trip: sample
+// positions are theta + (idx - 4.5) directly; the error (<1e-5 px) is far below bf16 rounding.
+// The stand-alone fp32 gather (gather.cu) keeps the exact sequence for the 1e-5 parity clause.
+#include "umma.cuh"
+#include "../../include/lafs_b200.h"
+
+namespace lafs {
+using namespace umma;
+
+namespace pe {
+constexpr int kH = 112, kW = 112, kC = 3;
+constexpr int kPlaneBytes = kH * kW * 4;           // 50,176
+constexpr int kFeat = 192;                         // 3 * 8 * 8
+constexpr int kMaxTok = 208;                       // token rows held in smem (N_pad <= 208)
+constexpr int kTokChunkBytes = kMaxTok * 128;      // one 64-feature chunk: 26,624 B (26 x 1024)
+constexpr int kWStageBytes = 128 * 128;            // [128 dims x 64 k] bf16
+constexpr int kWStages = 2;
+constexpr int kThreads = 512;                      // 16 warps
+constexpr int kGatherWarps = 8;
+constexpr int kGatherThreads = kGatherWarps * 32;
+// warp roles
+constexpr int kWarpPlane = 0, kWarpW = 1, kWarpMma = 2, kWarpEpi0 = 4, kWarpGather0 = 8;
+
+constexpr int kOffPlanes = 0;
+constexpr int kOffTok = 2 * kPlaneBytes;                       // 100,352 (1024-aligned: 98 x 1024)
+constexpr int kOffW = kOffTok + 3 * kTokChunkBytes;            // 180,224
+constexpr int kOffBar = kOffW + kWStages * kWStageBytes;       // 212,992
+constexpr int kSmemBytes = kOffBar + 256 + 1024;               // + barriers + alignment slack
+static_assert(kOffTok % 1024 == 0 && kOffW % 1024 == 0, "UMMA tiles need 1024-byte alignment");
+}  // namespace pe
+
+struct EmbedParams {
+  const float* imgs;        // [Bv, 3, 112, 112]
+  const float* theta;       // [Bv, n, 2]
+  const float* bias;        // [n_models * dim]
+  void* out[2];             // per model: [Bv, n, dim] bf16 or fp32
+  int Bv, n, n_pad, dim, n_models;
+  int mchunks;              // n_models * dim / 128
+};
+
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(pe::kThreads, 1)
+gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParams p) {
+  using namespace pe;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* s_planes = smem + kOffPlanes;
+  uint8_t* s_tok = smem + kOffTok;
+  uint8_t* s_w = smem + kOffW;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* plane_full = bars;            // 2
+  uint64_t* plane_empty = bars + 2;       // 2
+  uint64_t* tok_full = bars + 4;          // 3
+  uint64_t* tok_empty = bars + 7;         // 1
+  uint64_t* w_full = bars + 8;            // kWStages
+  uint64_t* w_empty = bars + 10;          // kWStages
+  uint64_t* acc_full = bars + 12;         // 2
+  uint64_t* acc_empty = bars + 14;        // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmap_w);
+    for (int i = 0; i < 2; ++i) { mbar_init(plane_full + i, 1); mbar_init(plane_empty + i, kGatherWarps); }
+    for (int i = 0; i < 3; ++i) mbar_init(tok_full + i, kGatherWarps);
+    mbar_init(tok_empty, 1);
+    for (int i = 0; i < kWStages; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
+    fence_mbar_init();
+  }
+  if (warp == kWarpMma) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int nfaces_mine = (p.Bv - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == kWarpPlane) {
+    // ===================== image plane producer =====================
+    if (lane == 0) {
+      uint32_t cnt = 0;
+      for (int fi = 0; fi < nfaces_mine; ++fi) {
+        const int f = blockIdx.x + fi * gridDim.x;
+        for (int c = 0; c < kC; ++c, ++cnt) {
+          const int slot = cnt & 1;
+          mbar_wait(plane_empty + slot, ((cnt >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(plane_full + slot, kPlaneBytes);
+          bulk_load(s_planes + slot * kPlaneBytes, p.imgs + ((size_t)f * kC + c) * (kH * kW), kPlaneBytes,
+                    plane_full + slot);
+        }
+      }
+    }
+  } else if (warp == kWarpW) {
+    // ===================== weight chunk producer =====================
+    if (lane == 0) {
+      uint32_t cnt = 0;
+      for (int fi = 0; fi < nfaces_mine; ++fi)
+        for (int mc = 0; mc < p.mchunks; ++mc)
+          for (int c = 0; c < kC; ++c, ++cnt) {
+            const int st = cnt % kWStages;
+            mbar_wait(w_empty + st, ((cnt / kWStages) & 1) ^ 1);
+            mbar_arrive_expect_tx(w_full + st, kWStageBytes);
+            tma_load_2d(s_w + st * kWStageBytes, &tmap_w, w_full + st, c * 64, mc * 128);
+          }
+    }
+  } else if (warp == kWarpMma) {
+    // ===================== UMMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, p.n_pad);
+      uint32_t wcnt = 0, acnt = 0;
+      for (int fi = 0; fi < nfaces_mine; ++fi) {
+        for (int mc = 0; mc < p.mchunks; ++mc, ++acnt) {
+          const int buf = acnt & 1;
+          mbar_wait(acc_empty + buf, ((acnt >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
+          for (int c = 0; c < kC; ++c, ++wcnt) {
+            if (mc == 0) { mbar_wait(tok_full + c, fi & 1); }
+            const int st = wcnt % kWStages;
+            mbar_wait(w_full + st, (wcnt / kWStages) & 1);
+            tc_fence_after();
+            const uint64_t da = make_desc_k_sw128(smem_u32(s_w + st * kWStageBytes));
+            const uint64_t db = make_desc_k_sw128(smem_u32(s_tok + c * kTokChunkBytes));
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              mma_f16_ss(d_tmem, desc_advance_k(da, kk * 16), desc_advance_k(db, kk * 16), idesc, (c | kk) != 0);
+            mma_commit(w_empty + st);
+          }
+          mma_commit(acc_full + buf);
+        }
+        mma_commit(tok_empty);   // all UMMAs reading this face's tokens have completed
+      }
+    }
+  } else if (warp >= kWarpEpi0 && warp < kWarpEpi0 + 4) {
+    // ===================== epilogue =====================
+    const int quarter = warp & 3;
+    uint32_t acnt = 0;
+    for (int fi = 0; fi < nfaces_mine; ++fi) {
+      const int f = blockIdx.x + fi * gridDim.x;
+      for (int mc = 0; mc < p.mchunks; ++mc, ++acnt) {
+        const int buf = acnt & 1;
+        const int d = mc * 128 + quarter * 32 + lane;      // row of the stacked [n_models*dim] weight
+        const int model = d / p.dim, dd = d - model * p.dim;
+        const float bias = __ldg(p.bias + d);
+        OutT* dst = reinterpret_cast<OutT*>(model == 0 ? p.out[0] : p.out[1]) + (size_t)f * p.n * p.dim + dd;
+        mbar_wait(acc_full + buf, (acnt >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t)(buf * 256) + ((uint32_t)(quarter * 32) << 16);
+        for (int t0 = 0; t0 < p.n_pad; t0 += 16) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(taddr + (uint32_t)t0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (t0 + j < p.n) {
+              const float o = __uint_as_float(v[j]) + bias;
+              if constexpr (sizeof(OutT) == 4) dst[(size_t)(t0 + j) * p.dim] = o;
+              else dst[(size_t)(t0 + j) * p.dim] = __float2bfloat16_rn(o);
+            }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty + buf);
+      }
+    }
+  } else if (warp >= kWarpGather0) {
+    // ===================== gather warps =====================
+    const int gt = threadIdx.x - kWarpGather0 * 32;        // 0..255
+    uint32_t pcnt = 0;
+    for (int fi = 0; fi < nfaces_mine; ++fi) {
+      const int f = blockIdx.x + fi * gridDim.x;
+      const float* th = p.theta + (size_t)f * p.n * 2;
+      mbar_wait(tok_empty, (fi & 1) ^ 1);                  // previous face's UMMAs are done with the tile
+      for (int c = 0; c < kC; ++c, ++pcnt) {
+        const int slot = pcnt & 1;
+        mbar_wait(plane_full + slot, (pcnt >> 1) & 1);
+        const float* plane = reinterpret_cast<const float*>(s_planes + slot * kPlaneBytes);
+        uint8_t* tok = s_tok + c * kTokChunkBytes;
+        // item = (token t, half h): output columns j = 4h..4h+3, all 8 i  -> four 16-byte stores
+        for (int item = gt; item < 2 * p.n; item += kGatherThreads) {
+          const int t = item >> 1, h = item & 1;
+          const float2 thv = __ldg(reinterpret_cast<const float2*>(th) + t);
+          const float sx = thv.x - 4.5f, sy = thv.y - 4.5f + (float)(4 * h);
+          const float fxf = floorf(sx), fyf = floorf(sy);
+          const float wx = sx - fxf, wy = sy - fyf;
+          const int x0 = (int)fminf(fmaxf(fxf, -16.f), 128.f);
+          const int y0 = (int)fminf(fmaxf(fyf, -16.f), 128.f);
+          const bool inside = (x0 >= 0) && (x0 + 8 < kW) && (y0 >= 0) && (y0 + 4 < kH);
+          float hprev[8];
+#pragma unroll
+          for (int r = 0; r < 5; ++r) {
+            float px[9];
+            const int y = y0 + r;
+            if (inside) {
+              const float* rowp = plane + y * kW + x0;
+#pragma unroll
+              for (int q = 0; q < 9; ++q) px[q] = rowp[q];
+            } else {
+              const bool yok = (y >= 0) && (y < kH);
+              const float* rowp = plane + min(max(y, 0), kH - 1) * kW;
+#pragma unroll
+              for (int q = 0; q < 9; ++q) {
+                const int x = x0 + q;
+                const float v = rowp[min(max(x, 0), kW - 1)];
+                px[q] = (yok && x >= 0 && x < kW) ? v : 0.f;
+              }
+            }
+            float hcur[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) hcur[i] = fmaf(wx, px[i + 1] - px[i], px[i]);
+            if (r > 0) {
+              const int j = 4 * h + r - 1;
+              uint4 pk;
+              float o[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] = fmaf(wy, hcur[i] - hprev[i], hprev[i]);
+              pk.x = Half2Ops<__nv_bfloat16>::pack(o[0], o[1]);
+              pk.y = Half2Ops<__nv_bfloat16>::pack(o[2], o[3]);
+              pk.z = Half2Ops<__nv_bfloat16>::pack(o[4], o[5]);
+              pk.w = Half2Ops<__nv_bfloat16>::pack(o[6], o[7]);
+              *reinterpret_cast<uint4*>(tok + sw128_offset(t, j * 8)) = pk;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) hprev[i] = hcur[i];
+          }
+        }
+        fence_proxy_async_smem();      // token stores -> visible to the UMMA (async proxy) reads
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(tok_full + c);
+          mbar_arrive(plane_empty + slot);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kWarpMma) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// W fp32 [dim, 192] (feature f = (i*8+j)*3 + c) -> bf16 [dim, 192] with K order c*64 + j*8 + i
+__global__ void embed_weight_prep_kernel(const float* __restrict__ w, int dim, __nv_bfloat16* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= dim * pe::kFeat) return;
+  const int d = idx / pe::kFeat, k = idx - d * pe::kFeat;
+  const int c = k >> 6, j = (k >> 3) & 7, i = k & 7;
+  out[idx] = __float2bfloat16_rn(w[(size_t)d * pe::kFeat + (i * 8 + j) * 3 + c]);
+}
+
+}  // namespace lafs
+
+using namespace lafs;
+
+extern "C" int lafs_embed_weight_prep(const float* weight, int dim, void* out_bf16, lafs_stream_t stream) {
+  LAFS_REQUIRE(weight && out_bf16 && dim > 0, LAFS_ERR_ARG, "lafs_embed_weight_prep: bad argument");
+  const int total = dim * pe::kFeat;
+  embed_weight_prep_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(weight, dim, (__nv_bfloat16*)out_bf16);
+  return check_launch("lafs_embed_weight_prep");
+}
+
+extern "C" int lafs_gather_embed_fwd(const float* imgs, const float* theta, const void* w_perm_bf16, const float* bias,
+                                     void* out0, void* out1, int out_dtype, int Bv, int H, int W, int n, int dim,
+                                     int n_models, lafs_stream_t stream) {
+  void* out0_bf16 = out0; void* out1_bf16 = out1;
+  LAFS_REQUIRE(imgs && theta && w_perm_bf16 && bias && out0_bf16, LAFS_ERR_ARG, "lafs_gather_embed_fwd: null pointer");
+  LAFS_REQUIRE(out_dtype == LAFS_BF16 || out_dtype == LAFS_F32, LAFS_ERR_ARG, "lafs_gather_embed_fwd: out_dtype=%d (bf16 or fp32)", out_dtype);
+  LAFS_REQUIRE(H == pe::kH && W == pe::kW, LAFS_ERR_ARG, "lafs_gather_embed_fwd: fused path is built for 112x112 faces, got %dx%d", H, W);
+  LAFS_REQUIRE(n_models == 1 || (n_models == 2 && out1_bf16), LAFS_ERR_ARG, "lafs_gather_embed_fwd: n_models=%d", n_models);
+  LAFS_REQUIRE(n > 0 && n <= pe::kMaxTok, LAFS_ERR_ARG, "lafs_gather_embed_fwd: n=%d outside [1,%d]", n, pe::kMaxTok);
+  LAFS_REQUIRE(dim > 0 && dim % 128 == 0, LAFS_ERR_ARG, "lafs_gather_embed_fwd: dim=%d must be a multiple of 128", dim);
+  LAFS_REQUIRE(((uintptr_t)imgs & 15u) == 0 && ((uintptr_t)theta & 7u) == 0, LAFS_ERR_ARG, "lafs_gather_embed_fwd: misaligned input");
+  if (Bv == 0) return LAFS_OK;
+  LAFS_REQUIRE(Bv > 0, LAFS_ERR_ARG, "lafs_gather_embed_fwd: Bv=%d", Bv);
+  CUtensorMap tw;
+  int rc = TmaEncoder::bf16_2d_sw128(&tw, w_perm_bf16, (uint64_t)n_models * dim, pe::kFeat, pe::kFeat * 2, 128);
+  if (rc) return rc;
+  EmbedParams p{};
+  p.imgs = imgs; p.theta = theta; p.bias = bias;
+  p.out[0] = out0_bf16; p.out[1] = out1_bf16;
+  p.Bv = Bv; p.n = n; p.n_pad = (n + 15) & ~15; p.dim = dim; p.n_models = n_models;
+  p.mchunks = n_models * dim / 128;
+  auto kern = out_dtype == LAFS_F32 ? gather_embed_kernel<float> : gather_embed_kernel<__nv_bfloat16>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pe::kSmemBytes);
+  LAFS_REQUIRE(e == cudaSuccess, LAFS_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  const int grid = Bv < kNumSMs ? Bv : kNumSMs;
+  kern<<<grid, pe::kThreads, pe::kSmemBytes, (cudaStream_t)stream>>>(tw, p);
+  return check_launch("lafs_gather_embed_fwd");
+}

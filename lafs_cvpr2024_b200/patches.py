@@ -114,3 +114,51 @@ def landmark_post(raw, noise=None, extract_id=None, scale=111.0):
     _lib.call("lafs_landmark_post", x.data_ptr(), _lib.ptr(nz), _lib.ptr(idx), out.data_ptr(), None,
               B, n, keep, float(scale), _lib.stream())
     return out
+
+
+class PatchEmbedWeights:
+    """bf16, K-permuted copy of one or two `patch_to_embedding = nn.Linear(192, dim)` layers
+    (ViT_face.py:619) for the fused gather->embed kernel.  Two layers (student, teacher) share
+    one gather of the patches.  Call refresh() after the weights change (optimizer / EMA step)."""
+
+    def __init__(self, linears):
+        self.linears = [(w, b) for (w, b) in linears]
+        if not 1 <= len(self.linears) <= 2:
+            raise ValueError("one or two (weight, bias) pairs expected")
+        w0 = self.linears[0][0]
+        _lib.require_cuda(w0)
+        self.dim = w0.shape[0]
+        if any(w.shape != (self.dim, 192) for w, _ in self.linears):
+            raise ValueError("patch_to_embedding weights must be [dim, 192]")
+        m = len(self.linears)
+        self.w_perm = torch.empty(m * self.dim, 192, dtype=torch.bfloat16, device=w0.device)
+        self.bias = torch.empty(m * self.dim, dtype=torch.float32, device=w0.device)
+        self.refresh()
+
+    @torch.no_grad()
+    def refresh(self):
+        for i, (w, b) in enumerate(self.linears):
+            wd = w.detach().float().contiguous()
+            _lib.call("lafs_embed_weight_prep", wd.data_ptr(), self.dim,
+                      self.w_perm.data_ptr() + i * self.dim * 192 * 2, _lib.stream())
+            self.bias[i * self.dim:(i + 1) * self.dim].copy_(b.detach().float() if b is not None else 0)
+
+
+@torch.no_grad()
+def gather_embed(imgs, landmarks, weights: PatchEmbedWeights, out_dtype=torch.bfloat16):
+    """tokens(imgs, landmarks) @ W^T + b for every model in `weights`, without materialising the
+    patches: list of [B, n, dim] tensors.  Forward only (the SSL landmark CNN is frozen and
+    the teacher has no gradient)."""
+    _lib.require_cuda(imgs, landmarks)
+    x = imgs.detach().float().contiguous()
+    th = landmarks.detach().float().contiguous()
+    Bv, Cc, H, W = x.shape
+    if Cc != 3:
+        raise ValueError("the fused path expects 3-channel images")
+    n = th.shape[1]
+    m = len(weights.linears)
+    outs = [torch.empty(Bv, n, weights.dim, dtype=out_dtype, device=x.device) for _ in range(m)]
+    _lib.call("lafs_gather_embed_fwd", x.data_ptr(), th.data_ptr(), weights.w_perm.data_ptr(),
+              weights.bias.data_ptr(), outs[0].data_ptr(), outs[1].data_ptr() if m > 1 else None,
+              _lib.dtype_code(outs[0]), Bv, H, W, n, weights.dim, m, _lib.stream())
+    return outs

@@ -1,0 +1,72 @@
+"""GPU parity: fused landmark gather -> patch embedding (tcgen05) against golden vectors and
+the oracle evaluated on bf16-rounded tokens / weights."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lafs_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+@pytest.fixture(scope="module")
+def P():
+    import lafs_cvpr2024_b200 as pkg
+    return pkg
+
+
+def check(out, ref, fp32):
+    scale = ref.abs().max()
+    err = (out.float().cpu() - ref).abs().max()
+    tol = 2e-4 if fp32 else 1e-3 + 2 ** -8     # bf16 output rounding on top
+    assert err <= tol * scale, (float(err), float(scale))
+
+
+@pytest.mark.parametrize("n", [196, 36])
+@pytest.mark.parametrize("dim", [768, 384, 128])
+def test_gather_embed_vs_oracle(P, n, dim):
+    torch.manual_seed(n + dim)
+    B = 5
+    imgs = torch.rand(B, 3, 112, 112) * 2 - 1
+    th = torch.rand(B, n, 2) * 111 + torch.randn(B, n, 2) * 5
+    th[0, 0] = torch.tensor([-30.0, 200.0]); th[0, 1] = torch.tensor([0.2, 111.7])
+    lin = torch.nn.Linear(192, dim)
+    ref = O.gather_embed(imgs, th, lin.weight.detach(), lin.bias.detach(), round_bf16=True)
+    wts = P.PatchEmbedWeights([(lin.weight.cuda(), lin.bias.cuda())])
+    (o32,) = P.gather_embed(imgs.cuda(), th.cuda(), wts, out_dtype=torch.float32)
+    check(o32, ref, fp32=True)
+    (o16,) = P.gather_embed(imgs.cuda(), th.cuda(), wts)
+    assert o16.dtype == torch.bfloat16
+    check(o16, ref, fp32=False)
+
+
+def test_two_models_share_one_gather_many_faces(P):
+    """student + teacher projections of the same patches; more faces than SMs (persistent loop)."""
+    torch.manual_seed(3)
+    B, n, dim = 333, 196, 256
+    imgs = torch.rand(B, 3, 112, 112) * 2 - 1
+    th = torch.rand(B, n, 2) * 111 + torch.randn(B, n, 2) * 5
+    s, t = torch.nn.Linear(192, dim), torch.nn.Linear(192, dim)
+    wts = P.PatchEmbedWeights([(s.weight.cuda(), s.bias.cuda()), (t.weight.cuda(), t.bias.cuda())])
+    os_, ot = P.gather_embed(imgs.cuda(), th.cuda(), wts, out_dtype=torch.float32)
+    for o, lin in ((os_, s), (ot, t)):
+        for b in (0, 147, 148, 149, 332):
+            ref = O.gather_embed(imgs[b:b + 1], th[b:b + 1], lin.weight.detach(), lin.bias.detach(), round_bf16=True)
+            check(o[b:b + 1], ref, fp32=True)
+
+
+def test_patch_embed_golden(P, golden):
+    g, pg = golden("patch_embed"), golden("patches")
+    imgs, th = T(pg["imgs"]), T(pg["theta196"])
+    w, b = T(g["weight"]), T(g["bias"])           # dim 64 is not a multiple of 128: pad to 128 rows
+    wp = torch.zeros(128, 192); wp[:64] = w
+    bp = torch.zeros(128); bp[:64] = b
+    wts = P.PatchEmbedWeights([(wp.cuda(), bp.cuda())])
+    (o,) = P.gather_embed(imgs.cuda(), th.cuda(), wts, out_dtype=torch.float32)
+    ref = T(g["embedded"])                        # reference fp32 patch_to_embedding output
+    err = (o[:, :, :64].cpu() - ref).abs().max()
+    assert err <= 1e-2 * ref.abs().max(), float(err)   # bf16 operands vs the fp32 reference
