@@ -75,6 +75,24 @@ def main():
     mg, bg = timeit(g)
     gb = imgs.numel() * 4 + out.numel() * 4
     res["gather_512x196"] = {"ms": mg, "GBps": gb / mg / 1e6, "frac_hbm": gb / mg / 1e6 / hbm}
+    # ---- fused gather -> patch embed (config 2: 512 global faces x2 models, 1024 local faces)
+    tcp = peaks.get("bf16_tflops_sustained", 1400.0)
+    lin_s, lin_t = torch.nn.Linear(192, 768).cuda(), torch.nn.Linear(192, 768).cuda()
+    w2 = P.PatchEmbedWeights([(lin_s.weight, lin_s.bias), (lin_t.weight, lin_t.bias)])
+    w1 = P.PatchEmbedWeights([(lin_s.weight, lin_s.bias)])
+    imgs_l = torch.rand(1024, 3, 112, 112, device="cuda") * 2 - 1
+    th_l = torch.rand(1024, 36, 2, device="cuda") * 111
+    mg2, _ = timeit(lambda: P.gather_embed(imgs, th, w2))
+    ml1, _ = timeit(lambda: P.gather_embed(imgs_l, th_l, w1))
+    by_g = 512 * (3 * 112 * 112 * 4 + 196 * 8) + 2 * 512 * 196 * 768 * 2
+    fl_g = 2.0 * 192 * 768 * 2 * 512 * 196
+    by_l = 1024 * (3 * 112 * 112 * 4 + 36 * 8) + 1024 * 36 * 768 * 2
+    fl_l = 2.0 * 192 * 768 * 1024 * 36
+    res["gather_embed_global_512x196x2models"] = {"ms": mg2, "GBps": by_g / mg2 / 1e6, "frac_hbm": by_g / mg2 / 1e6 / hbm,
+                                                  "TFLOPs": fl_g / mg2 / 1e9, "frac_tc": fl_g / mg2 / 1e9 / tcp}
+    res["gather_embed_local_1024x36"] = {"ms": ml1, "GBps": by_l / ml1 / 1e6, "frac_hbm": by_l / ml1 / 1e6 / hbm,
+                                         "TFLOPs": fl_l / ml1 / 1e9, "frac_tc": fl_l / ml1 / 1e9 / tcp}
+    del imgs_l
     if "--head" in sys.argv or True:
         tc = peaks.get("bf16_tflops_sustained", 1400.0)
         for (B, C, D) in [(512, 93431, 512), (1024, 205990, 512), (512, 93431, 768)]:
