@@ -26,15 +26,19 @@ namespace pe {
 constexpr int kH = 112, kW = 112, kC = 3;
 constexpr int kPlaneBytes = kH * kW * 4;           // 50,176
 constexpr int kFeat = 192;                         // 3 * 8 * 8
-constexpr int kMaxTok = 208;                       // token rows held in smem (N_pad <= 208)
-constexpr int kTokChunkBytes = kMaxTok * 128;      // one 64-feature chunk: 26,624 B (26 x 1024)
+constexpr int kMaxTok = 208;                       // largest UMMA N (196 landmarks -> N_pad 208)
+constexpr int kTokRows = 200;                      // token rows owned per chunk (25 x 8); a UMMA with
+                                                   // N_pad = 208 also reads 8 rows of the NEXT region:
+                                                   // harmless garbage columns that are never stored
+constexpr int kTokChunkBytes = kTokRows * 128;     // one 64-feature chunk: 25,600 B (25 x 1024)
 constexpr int kWStageBytes = 128 * 128;            // [128 dims x 64 k] bf16
-constexpr int kWStages = 2;
-constexpr int kThreads = 512;                      // 16 warps
+constexpr int kWStages = 3;
+constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quarter
 constexpr int kGatherWarps = 8;
 constexpr int kGatherThreads = kGatherWarps * 32;
 // warp roles
-constexpr int kWarpPlane = 0, kWarpW = 1, kWarpMma = 2, kWarpEpi0 = 4, kWarpGather0 = 8;
+constexpr int kWarpPlane = 0, kWarpW = 1, kWarpMma = 2, kWarpEpi0 = 4, kWarpGather0 = kWarpEpi0 + kEpiWarps;
+constexpr int kThreads = (kWarpGather0 + kGatherWarps) * 32;   // 20 warps
 
 constexpr int kOffPlanes = 0;
 constexpr int kOffTok = 2 * kPlaneBytes;                       // 100,352 (1024-aligned: 98 x 1024)
@@ -59,7 +63,11 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
                : "memory");
 }
 
-template <typename OutT>
+__device__ __forceinline__ void store_out(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store_out(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// DIM > 0: compile-time embedding width (store offsets become immediates); DIM == 0: runtime p.dim
+template <typename OutT, int DIM>
 __global__ void __launch_bounds__(pe::kThreads, 1)
 gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParams p) {
   using namespace pe;
@@ -73,11 +81,11 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
   uint64_t* plane_empty = bars + 2;       // 2
   uint64_t* tok_full = bars + 4;          // 3
   uint64_t* tok_empty = bars + 7;         // 1
-  uint64_t* w_full = bars + 8;            // kWStages
-  uint64_t* w_empty = bars + 10;          // kWStages
-  uint64_t* acc_full = bars + 12;         // 2
-  uint64_t* acc_empty = bars + 14;        // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* w_full = bars + 8;            // kWStages (<= 4)
+  uint64_t* w_empty = bars + 12;          // kWStages
+  uint64_t* acc_full = bars + 16;         // 2
+  uint64_t* acc_empty = bars + 18;        // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -87,7 +95,7 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
     for (int i = 0; i < 3; ++i) mbar_init(tok_full + i, kGatherWarps);
     mbar_init(tok_empty, 1);
     for (int i = 0; i < kWStages; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, kEpiWarps); }
     fence_mbar_init();
   }
   if (warp == kWarpMma) tmem_alloc(tmem_slot, 512);
@@ -154,32 +162,46 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
         mma_commit(tok_empty);   // all UMMAs reading this face's tokens have completed
       }
     }
-  } else if (warp >= kWarpEpi0 && warp < kWarpEpi0 + 4) {
+  } else if (warp >= kWarpEpi0 && warp < kWarpEpi0 + kEpiWarps) {
     // ===================== epilogue =====================
+    // lane = output feature (TMEM lane), registers = 32 consecutive tokens.  A warp-wide 2-byte
+    // store covers 32 consecutive features of one token (64 contiguous bytes = 2 full sectors).
+    // The two warps of a lane quarter take alternate 32-token pieces.
     const int quarter = warp & 3;
+    const int half = (warp - kWarpEpi0) >> 2;
+    const int dim = DIM > 0 ? DIM : p.dim;
     uint32_t acnt = 0;
     for (int fi = 0; fi < nfaces_mine; ++fi) {
       const int f = blockIdx.x + fi * gridDim.x;
       for (int mc = 0; mc < p.mchunks; ++mc, ++acnt) {
         const int buf = acnt & 1;
         const int d = mc * 128 + quarter * 32 + lane;      // row of the stacked [n_models*dim] weight
-        const int model = d / p.dim, dd = d - model * p.dim;
+        const int model = d >= dim ? 1 : 0, dd = d - model * dim;
         const float bias = __ldg(p.bias + d);
-        OutT* dst = reinterpret_cast<OutT*>(model == 0 ? p.out[0] : p.out[1]) + (size_t)f * p.n * p.dim + dd;
+        OutT* dst = reinterpret_cast<OutT*>(model == 0 ? p.out[0] : p.out[1]) + (size_t)f * p.n * dim + dd;
         mbar_wait(acc_full + buf, (acnt >> 1) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t)(buf * 256) + ((uint32_t)(quarter * 32) << 16);
-        for (int t0 = 0; t0 < p.n_pad; t0 += 16) {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(taddr + (uint32_t)t0, v);
-          tmem_ld_wait();
+        for (int t0 = half * 32; t0 < p.n; t0 += 64) {
+          uint32_t v[32];
+          if (t0 + 32 <= p.n_pad) {
+            tmem_ld_32x32b_x32(taddr + (uint32_t)t0, v);
+          } else {                                          // n_pad is a multiple of 16: 16-column tail
+            uint32_t lo[16];
+            tmem_ld_32x32b_x16(taddr + (uint32_t)t0, lo);
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (t0 + j < p.n) {
-              const float o = __uint_as_float(v[j]) + bias;
-              if constexpr (sizeof(OutT) == 4) dst[(size_t)(t0 + j) * p.dim] = o;
-              else dst[(size_t)(t0 + j) * p.dim] = __float2bfloat16_rn(o);
-            }
+            for (int j = 0; j < 16; ++j) { v[j] = lo[j]; v[16 + j] = 0u; }
+          }
+          tmem_ld_wait();
+          OutT* q = dst + (size_t)t0 * dim;
+          if (t0 + 32 <= p.n) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) store_out(q + (size_t)j * dim, __uint_as_float(v[j]) + bias);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (t0 + j < p.n) store_out(q + (size_t)j * dim, __uint_as_float(v[j]) + bias);
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -306,7 +328,10 @@ extern "C" int lafs_gather_embed_fwd(const float* imgs, const float* theta, cons
   p.out[0] = out0_bf16; p.out[1] = out1_bf16;
   p.Bv = Bv; p.n = n; p.n_pad = (n + 15) & ~15; p.dim = dim; p.n_models = n_models;
   p.mchunks = n_models * dim / 128;
-  auto kern = out_dtype == LAFS_F32 ? gather_embed_kernel<float> : gather_embed_kernel<__nv_bfloat16>;
+  void (*kern)(const CUtensorMap, const EmbedParams);
+  if (out_dtype == LAFS_F32) kern = dim == 768 ? gather_embed_kernel<float, 768> : gather_embed_kernel<float, 0>;
+  else kern = dim == 768 ? gather_embed_kernel<__nv_bfloat16, 768>
+            : dim == 384 ? gather_embed_kernel<__nv_bfloat16, 384> : gather_embed_kernel<__nv_bfloat16, 0>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pe::kSmemBytes);
   LAFS_REQUIRE(e == cudaSuccess, LAFS_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   const int grid = Bv < kNumSMs ? Bv : kNumSMs;
