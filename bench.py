@@ -8,7 +8,8 @@ Workload at every N: BASELINE.json configs[1] -- "LAFS SSL pretrain step, Part-f
 (196 landmark patches) + DINO head out_dim 65536, batch 256 synthetic faces" PER GPU (weak
 scaling; the only data-path collective is the reference's all-reduce of the DINO centre).
 One step = one pass of the hot path over one batch (lafs_cvpr2024_b200/ssl_step.py):
-landmark tail + patch gather for 2 global + 4 local views, DINO loss forward+backward+centre
+landmark tail + fused patch gather -> patch_to_embedding (student+teacher on the 2 global views,
+student on the 4 local views), DINO loss forward+backward+centre
 update on [6*256, 65536] / [2*256, 65536] bf16 logits, and the teacher EMA over the 147
 ViT-B + DINO-head parameter tensors.  The transformer blocks, DINO head MLP and landmark-CNN
 trunk are outside the path and are not run.
@@ -152,18 +153,21 @@ def run_ours(args):
     host = make_host_inputs(B, 1000 + rank)
     st = make_device_state(B, 2000 + rank, dev)
     dev_in = {k: v.to(dev) for k, v in host.items()}
-    path = SSLHotPath(OUT_DIM, L, st["teacher_params"], st["student_params"])
+    # parameter list order: [pos_embedding, patch_to_embedding.weight, patch_to_embedding.bias, ...]
+    s_embed = (st["student_params"][1], st["student_params"][2])
+    t_embed = (st["teacher_params"][1], st["teacher_params"][2])
+    path = SSLHotPath(OUT_DIM, L, st["teacher_params"], st["student_params"], student_embed=s_embed, teacher_embed=t_embed)
     path.loss.center = torch.randn(1, OUT_DIM, device=dev) * 0.1
     sched = 0.996 + 0.5 * (1 - 0.996) * (1 - np.cos(np.pi * np.arange(100000) / 100000))  # utils.py:187-198
-    names = ["landmark+gather", "dino_fwd+center", "dino_bwd", "ema"]
+    names = ["landmark+gather_embed", "dino_fwd+center", "dino_bwd", "ema"]
 
     def step(inp, it, evs=None):
         def mark(i):
             if evs is not None:
                 evs[i].record()
         mark(0)
-        path.landmarks_and_tokens(st["raw_g"], inp["noise_g"], inp["img_g"], st["raw_l"], inp["noise_l"],
-                                  inp["idx_l"], inp["img_l"])
+        path.landmarks_and_embeddings(st["raw_g"], inp["noise_g"], inp["img_g"], st["raw_l"], inp["noise_l"],
+                                      inp["idx_l"], inp["img_l"])
         mark(1)
         s = st["student_out"].requires_grad_(True)
         s.grad = None
@@ -231,7 +235,10 @@ def run_ours(args):
     K, nc = OUT_DIM, L + 2
     nparam = sum(int(np.prod(s)) for s in vit_b_param_shapes())
     alg = {
-        "landmark+gather": {"bytes": (2 + L) * B * (3 * 112 * 112 * 4) + 2 * B * 196 * 192 * 4 + L * B * 36 * 192 * 4},
+        # images + landmarks in, bf16 tokens of both models out
+        "landmark+gather_embed": {"bytes": (2 + L) * B * (3 * 112 * 112 * 4) + 2 * B * 196 * 8 + L * B * 36 * 8
+                                           + (2 * 2 * B * 196 + L * B * 36) * 768 * 2,
+                                  "flops": 2.0 * 192 * 768 * (2 * 2 * B * 196 + L * B * 36)},
         "dino_fwd+center": {"bytes": (nc + 2) * B * K * 2 + 8 * K},
         "dino_bwd": {"bytes": (2 * nc + 2) * B * K * 2},
         "ema": {"bytes": 12 * nparam},
@@ -241,6 +248,9 @@ def run_ours(args):
         gbps = alg[n]["bytes"] / ms / 1e6
         kernels[n] = {"ms": round(ms, 5), "alg_bytes": alg[n]["bytes"], "GBps": round(gbps, 1),
                       "frac_hbm": round(gbps / pk["hbm"], 4)}
+        if "flops" in alg[n]:
+            kernels[n]["TFLOPs"] = round(alg[n]["flops"] / ms / 1e9, 1)
+            kernels[n]["frac_tc"] = round(alg[n]["flops"] / ms / 1e9 / pk["tc"], 4)
     dom = max(kernels, key=lambda n: kernels[n]["ms"])
     line = {
         "metric": METRIC, "value": round(faces / (ms_step / 1e3), 1), "unit": "faces/s", "n_gpus": world,
@@ -254,13 +264,14 @@ def run_ours(args):
                    "parallelism": f"dp{world}"},
         "e2e": {"value": round(faces / (ms_e2e / args.steps / 1e3), 1), "unit": "faces/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 5)},
-        "gpu_launches": 13,
+        "gpu_launches": 15,   # 2 landmark, 3 weight prep, 2 gather-embed, 3 dino fwd, 1 centre, 1 dino bwd, 1 ema (+2 events)
         "clocks": clocks,
         "roofline": {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["GBps"], "peak": pk["hbm"], "unit": "GB/s",
                      "frac": kernels[dom]["frac_hbm"], "traffic": None, "peak_source": pk["src"]},
         "kernels": kernels,
     }
-    line["cpu_baseline"] = cpu_baseline(sample_faces=args.cpu_faces)
+    if not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(sample_faces=args.cpu_faces)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -285,13 +296,15 @@ def cpu_step_time(sample_faces, threads, reps=1):
     shapes = vit_b_param_shapes()
     q = [torch.randn(*sh, generator=g) for sh in shapes]
     k = [p.clone() for p in q]
+    ws, bs, wt, bt = q[1], q[2], k[1], k[2]     # patch_to_embedding of student / teacher
     best_face, best_ema = float("inf"), float("inf")
     for _ in range(reps + 1):
         t0 = time.perf_counter()
         th_g = O.landmark_post(raw_g, torch.randn(2 * Bs, 196, 2) * 5)
-        O.extract_tokens(img_g, th_g)
+        tok_g = O.extract_tokens(img_g, th_g)
+        O.patch_embed(tok_g, ws, bs); O.patch_embed(tok_g, wt, bt)
         th_l = O.landmark_post(raw_l, torch.randn(L * Bs, 196, 2) * 5, torch.randint(0, 196, (L * Bs, 36, 1)))
-        O.extract_tokens(img_l, th_l)
+        O.patch_embed(O.extract_tokens(img_l, th_l), ws, bs)
         O.dino_loss_and_grad(s, t, center, L + 2, 0.04)
         O.dino_center_update(center, t)
         t1 = time.perf_counter()
@@ -346,6 +359,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-faces", type=int, default=256, help="faces in the bounded CPU sample (256 = the full step)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

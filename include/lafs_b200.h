@@ -175,14 +175,16 @@ LAFS_API int lafs_head_grad_logits(const void* e_hat, const void* w_hat, const i
  *      replaces extract_patches_pytorch_gridsample + rearrange + patch_to_embedding
  *      (ViT_face.py:1615-1656, lafs_train.py:538, ViT_face.py:760-761) for 112x112 faces.
  * lafs_embed_weight_prep: nn.Linear(192, dim).weight fp32 [dim,192] (feature (i*8+j)*3+c)
- *      -> bf16 [dim,192] in the kernel's K order (c*64 + j*8 + i).  Stack two models by
+ *      -> bf16 [dim,192] in the kernel's K order (c*64 + j*8 + i); bias (may be NULL = 0) is
+ *      copied to bias_out (may be NULL) in the same launch.  Stack two models by
  *      writing them back to back ([2*dim,192]) to project the same patches with student and
  *      teacher weights (the two global SSL views, lafs_train.py:577-581).
  * lafs_gather_embed_fwd: out_m [Bv, n, dim] (out_dtype bf16, or fp32 for verification) =
  *      tokens(imgs, theta) @ W_m^T + bias_m for m < n_models; bias [n_models*dim] fp32;
  *      n <= 208, dim % 128 == 0.  Tokens and weights are rounded to bf16, accumulation is fp32.
  */
-LAFS_API int lafs_embed_weight_prep(const float* weight, int dim, void* out_bf16, lafs_stream_t stream);
+LAFS_API int lafs_embed_weight_prep(const float* weight, const float* bias, int dim, void* out_bf16, float* bias_out,
+                                    lafs_stream_t stream);
 LAFS_API int lafs_gather_embed_fwd(const float* imgs, const float* theta, const void* w_perm_bf16, const float* bias,
                                    void* out0, void* out1, int out_dtype, int Bv, int H, int W, int n, int dim,
                                    int n_models, lafs_stream_t stream);

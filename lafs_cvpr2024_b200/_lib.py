@@ -34,7 +34,7 @@ SIGNATURES = {
     "lafs_landmark_post_bwd": (_i, [_p, _p, _p, _i, _i, _f, _p]),
     "lafs_gather_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "lafs_gather_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
-    "lafs_embed_weight_prep": (_i, [_p, _i, _p, _p]),
+    "lafs_embed_weight_prep": (_i, [_p, _p, _i, _p, _p, _p]),
     "lafs_gather_embed_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "lafs_normalize_rows": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "lafs_head_workspace_bytes": (_z, [_i, _i, _i]),

@@ -64,137 +64,130 @@ struct Rows {
   uint4 s[NCROPS][U];
 };
 
-template <typename T, int U>
-__device__ __forceinline__ void load_row(uint4 (&dst)[U], const T* __restrict__ base, size_t row, int K,
-                                         const int (&col)[U], const bool (&ok)[U]) {
-#pragma unroll
-  for (int u = 0; u < U; ++u)
-    dst[u] = ok[u] ? ld_stream_u4(base + row * (size_t)K + col[u]) : make_uint4(0, 0, 0, 0);
-}
-
-template <typename T, int NCROPS, int U>
+// RAGGED: the last K-slice is partially filled (K % (32*VEC) != 0); lanes past K are masked.
+// The common case (K = 65536) compiles without any per-element predication.
+template <typename T, int NCROPS, bool RAGGED>
 __global__ void __launch_bounds__(kDinoThreads, 2)
 dino_fwd_partial(const T* __restrict__ student, const T* __restrict__ teacher,
                  const float* __restrict__ center, int B, int K, float a_s, float a_t,
                  int nslices, int ngroups, float* __restrict__ part, float* __restrict__ colsum_part) {
   constexpr int VEC = VecOf<T>::VEC;
-  constexpr int NC = U * VEC;
+  constexpr int NC = VEC;
   constexpr int REC = rec_floats(NCROPS);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int slice = blockIdx.x, group = blockIdx.y;
   const int b_lo = (int)(((long long)B * group) / ngroups);
   const int b_hi = (int)(((long long)B * (group + 1)) / ngroups);
 
-  int col[U];
-  bool ok[U];
+  const int col = slice * (32 * VEC) + lane * VEC;
+  const bool ok = !RAGGED || col < K;            // K % VEC == 0 is checked by the host
+  const int colc = ok ? col : 0;                 // masked lanes read a valid address and ignore it
   float cen[NC], csum[NC];
 #pragma unroll
-  for (int u = 0; u < U; ++u) {
-    col[u] = (slice * U + u) * (32 * VEC) + lane * VEC;
-    ok[u] = col[u] < K;  // K % VEC == 0 is checked by the host
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      cen[u * VEC + j] = ok[u] ? __ldg(center + col[u] + j) * a_t : 0.f;
-      csum[u * VEC + j] = 0.f;
-    }
+  for (int j = 0; j < VEC; ++j) {
+    cen[j] = __ldg(center + colc + j) * a_t;
+    csum[j] = 0.f;
   }
 
   // Register-rotating software pipeline: `rows` always holds the not-yet-consumed segments of
   // the current sample; as soon as a row has been unpacked its registers are re-filled with the
   // same row of the warp's next sample, so ncrops+2 128-bit loads stay in flight per lane.
-  Rows<T, NCROPS, U> rows;
+  // Row pointers are advanced by a constant byte stride instead of being recomputed.
   int b = b_lo + warp;
+  // address of (row r, this lane's columns) = base + off + r*row_bytes: one IMAD.WIDE per load,
+  // `off` advanced by a constant stride per sample
+  const unsigned row_bytes = (unsigned)((size_t)K * sizeof(T));
+  const size_t step = (size_t)kDinoWarps * row_bytes;
+  size_t off = (size_t)b * row_bytes + (size_t)colc * sizeof(T);
+  const char* tbase = reinterpret_cast<const char*>(teacher);
+  const char* sbase = reinterpret_cast<const char*>(student);
+  auto t_ptr = [&](int iq) { return tbase + (off + (size_t)((unsigned)(iq * B)) * row_bytes); };
+  auto s_ptr = [&](int v) { return sbase + (off + (size_t)((unsigned)(v * B)) * row_bytes); };
+  uint4 rt[2], rs[NCROPS];
   if (b < b_hi) {
 #pragma unroll
-    for (int iq = 0; iq < 2; ++iq) load_row<T, U>(rows.t[iq], teacher, (size_t)iq * B + b, K, col, ok);
+    for (int iq = 0; iq < 2; ++iq) rt[iq] = ld_stream_u4(t_ptr(iq));
 #pragma unroll
-    for (int v = 0; v < NCROPS; ++v) load_row<T, U>(rows.s[v], student, (size_t)v * B + b, K, col, ok);
+    for (int v = 0; v < NCROPS; ++v) rs[v] = ld_stream_u4(s_ptr(v));
   }
+  off += step;   // `off` now addresses the warp's NEXT sample
   for (; b < b_hi; b += kDinoWarps) {
-    const int bn = b + kDinoWarps;
-    const bool has_next = bn < b_hi;
+    const bool has_next = b + kDinoWarps < b_hi;
 
-    float rec[REC];
+    // partial record of this (sample, slice); lane 0 stores each entry as soon as it is final
+    float* dst = part + ((size_t)b * nslices + slice) * REC;
+    float zpart[2];
     float e[2][NC];  // teacher: first x (log2-domain logits), then exp2(x - max)
     // ---- teacher rows ------------------------------------------------------------------
 #pragma unroll
     for (int iq = 0; iq < 2; ++iq) {
+      float tv[VEC];
+      unpack<T>(rt[iq], tv);
+      if (has_next) rt[iq] = ld_stream_u4(t_ptr(iq));
       float mx = -INFINITY;
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        float tv[VEC];
-        unpack<T>(rows.t[iq][u], tv);
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-          const int c = u * VEC + j;
-          csum[c] += tv[j];
-          const float x = ok[u] ? fmaf(tv[j], a_t, -cen[c]) : -INFINITY;
-          e[iq][c] = x;
-          mx = fmaxf(mx, x);
-        }
+      for (int j = 0; j < VEC; ++j) {
+        if (!RAGGED || ok) csum[j] += tv[j];
+        float x = fmaf(tv[j], a_t, -cen[j]);
+        if (RAGGED && !ok) x = -INFINITY;
+        e[iq][j] = x;
+        mx = fmaxf(mx, x);
       }
-      if (has_next) load_row<T, U>(rows.t[iq], teacher, (size_t)iq * B + bn, K, col, ok);
       mx = warp_max_redux(mx);
       float z = 0.f;
 #pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        e[iq][c] = ex2(e[iq][c] - mx);
-        z += e[iq][c];
+      for (int j = 0; j < NC; ++j) {
+        e[iq][j] = ex2(e[iq][j] - mx);
+        z += e[iq][j];
       }
-      rec[3 * iq + 0] = mx;
-      rec[3 * iq + 1] = z;
+      if (lane == 0) dst[3 * iq] = mx;
+      zpart[iq] = z;
     }
     // ---- student rows ------------------------------------------------------------------
     float S[NC];
-#pragma unroll
-    for (int c = 0; c < NC; ++c) S[c] = 0.f;
     float a0 = 0.f, a1 = 0.f;
 #pragma unroll
     for (int v = 0; v < NCROPS; ++v) {
       float sv[NC];
-      float mx = -INFINITY;
+      unpack<T>(rs[v], sv);
+      if (has_next) rs[v] = ld_stream_u4(s_ptr(v));
+      float mx = sv[0];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        unpack<T>(rows.s[v][u], sv + u * VEC);
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) mx = fmaxf(mx, ok[u] ? sv[u * VEC + j] : -INFINITY);
-      }
-      if (has_next) load_row<T, U>(rows.s[v], student, (size_t)v * B + bn, K, col, ok);
+      for (int j = 1; j < VEC; ++j) mx = fmaxf(mx, sv[j]);
+      if (RAGGED && !ok) mx = -INFINITY;
       mx = warp_max_redux(mx) * a_s;  // a_s > 0: max commutes with the scaling
       float sum = 0.f;
 #pragma unroll
-      for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-          const int c = u * VEC + j;
-          sum += ok[u] ? ex2(fmaf(sv[c], a_s, -mx)) : 0.f;
-          S[c] += sv[c];
-        }
+      for (int j = 0; j < VEC; ++j) {
+        sum += ex2(fmaf(sv[j], a_s, -mx));
+        S[j] = v == 0 ? sv[j] : S[j] + sv[j];
+      }
+      if (RAGGED && !ok) sum = 0.f;
       // the two self-view products are removed from the S-dot below
       if (v == 0) {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) a0 = fmaf(e[0][c], -sv[c], a0);
+        for (int j = 0; j < NC; ++j) a0 = fmaf(e[0][j], -sv[j], a0);
       }
       if (v == 1) {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) a1 = fmaf(e[1][c], -sv[c], a1);
+        for (int j = 0; j < NC; ++j) a1 = fmaf(e[1][j], -sv[j], a1);
       }
-      rec[6 + 2 * v] = mx;
-      rec[7 + 2 * v] = warp_sum(sum);
+      sum = warp_sum(sum);
+      if (lane == 0) *reinterpret_cast<float2*>(dst + 6 + 2 * v) = make_float2(mx, sum);
     }
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      a0 = fmaf(e[0][c], S[c], a0);
-      a1 = fmaf(e[1][c], S[c], a1);
+    for (int j = 0; j < NC; ++j) {   // masked lanes: e == 0, so their (arbitrary) S does not count
+      a0 = fmaf(e[0][j], S[j], a0);
+      a1 = fmaf(e[1][j], S[j], a1);
     }
     // ---- warp reduction of the additive statistics ---------------------------------------
-    rec[1] = warp_sum(rec[1]); rec[2] = warp_sum(a0);
-    rec[4] = warp_sum(rec[4]); rec[5] = warp_sum(a1);
+    zpart[0] = warp_sum(zpart[0]); a0 = warp_sum(a0);
+    zpart[1] = warp_sum(zpart[1]); a1 = warp_sum(a1);
     if (lane == 0) {
-      float* dst = part + ((size_t)b * nslices + slice) * REC;  // REC is even -> 8-byte aligned
-#pragma unroll
-      for (int i = 0; i < REC; i += 2) *reinterpret_cast<float2*>(dst + i) = make_float2(rec[i], rec[i + 1]);
+      dst[1] = zpart[0]; dst[2] = a0;
+      dst[4] = zpart[1]; dst[5] = a1;
     }
+    off += step;
   }
 
   // ---- column sums of this CTA's samples: reduce the 8 warps through shared memory ---------
@@ -207,8 +200,7 @@ dino_fwd_partial(const T* __restrict__ student, const T* __restrict__ teacher,
 #pragma unroll
     for (int w = 0; w < kDinoWarps; ++w) acc += sm[w][i];
     const int c = i >> 5, l = i & 31;
-    const int u = c / VEC, j = c % VEC;
-    const int column = (slice * U + u) * (32 * VEC) + l * VEC + j;
+    const int column = slice * (32 * VEC) + l * VEC + c;
     if (column < K) colsum_part[(size_t)group * K + column] = acc;
   }
 }
@@ -425,9 +417,14 @@ static int launch_fwd(const void* student, const void* teacher, const float* cen
   float* colsum_part = reinterpret_cast<float*>(ws + p.off_colsum);
   float* sample_loss = reinterpret_cast<float*>(ws + p.off_sample);
   dim3 grid(p.nslices, p.ngroups);
-  dino_fwd_partial<T, NCROPS, 1><<<grid, kDinoThreads, 0, st>>>(
-      (const T*)student, (const T*)teacher, center, B, K, inv_ts * kLog2e, inv_tt * kLog2e,
-      p.nslices, p.ngroups, part, colsum_part);
+  if (K % p.cols_per_slice == 0)
+    dino_fwd_partial<T, NCROPS, false><<<grid, kDinoThreads, 0, st>>>(
+        (const T*)student, (const T*)teacher, center, B, K, inv_ts * kLog2e, inv_tt * kLog2e,
+        p.nslices, p.ngroups, part, colsum_part);
+  else
+    dino_fwd_partial<T, NCROPS, true><<<grid, kDinoThreads, 0, st>>>(
+        (const T*)student, (const T*)teacher, center, B, K, inv_ts * kLog2e, inv_tt * kLog2e,
+        p.nslices, p.ngroups, part, colsum_part);
   dino_rows_finalize<NCROPS><<<(B + kDinoWarps - 1) / kDinoWarps, kDinoThreads, 0, st>>>(
       part, B, p.nslices, inv_ts, row_stats, sample_loss);
   const float inv_norm = 1.f / ((float)(2 * NCROPS - 2) * (float)B);

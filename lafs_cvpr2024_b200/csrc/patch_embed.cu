@@ -288,8 +288,10 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
 }
 
 // W fp32 [dim, 192] (feature f = (i*8+j)*3 + c) -> bf16 [dim, 192] with K order c*64 + j*8 + i
-__global__ void embed_weight_prep_kernel(const float* __restrict__ w, int dim, __nv_bfloat16* __restrict__ out) {
+__global__ void embed_weight_prep_kernel(const float* __restrict__ w, const float* __restrict__ bias, int dim,
+                                        __nv_bfloat16* __restrict__ out, float* __restrict__ bias_out) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < dim && bias_out != nullptr) bias_out[idx] = bias != nullptr ? bias[idx] : 0.f;
   if (idx >= dim * pe::kFeat) return;
   const int d = idx / pe::kFeat, k = idx - d * pe::kFeat;
   const int c = k >> 6, j = (k >> 3) & 7, i = k & 7;
@@ -300,10 +302,11 @@ __global__ void embed_weight_prep_kernel(const float* __restrict__ w, int dim, _
 
 using namespace lafs;
 
-extern "C" int lafs_embed_weight_prep(const float* weight, int dim, void* out_bf16, lafs_stream_t stream) {
+extern "C" int lafs_embed_weight_prep(const float* weight, const float* bias, int dim, void* out_bf16, float* bias_out,
+                                      lafs_stream_t stream) {
   LAFS_REQUIRE(weight && out_bf16 && dim > 0, LAFS_ERR_ARG, "lafs_embed_weight_prep: bad argument");
   const int total = dim * pe::kFeat;
-  embed_weight_prep_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(weight, dim, (__nv_bfloat16*)out_bf16);
+  embed_weight_prep_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(weight, bias, dim, (__nv_bfloat16*)out_bf16, bias_out);
   return check_launch("lafs_embed_weight_prep");
 }
 

@@ -139,9 +139,10 @@ class PatchEmbedWeights:
     def refresh(self):
         for i, (w, b) in enumerate(self.linears):
             wd = w.detach().float().contiguous()
-            _lib.call("lafs_embed_weight_prep", wd.data_ptr(), self.dim,
-                      self.w_perm.data_ptr() + i * self.dim * 192 * 2, _lib.stream())
-            self.bias[i * self.dim:(i + 1) * self.dim].copy_(b.detach().float() if b is not None else 0)
+            bd = None if b is None else b.detach().float().contiguous()
+            _lib.call("lafs_embed_weight_prep", wd.data_ptr(), _lib.ptr(bd), self.dim,
+                      self.w_perm.data_ptr() + i * self.dim * 192 * 2,
+                      self.bias.data_ptr() + i * self.dim * 4, _lib.stream())
 
 
 @torch.no_grad()

@@ -15,7 +15,7 @@ import torch
 from . import _lib
 from .dino_loss import DINOLoss
 from .ema import EmaPlan
-from .patches import extract_tokens, landmark_post
+from .patches import PatchEmbedWeights, extract_tokens, gather_embed, landmark_post
 
 
 class SSLHotPath:
@@ -23,8 +23,15 @@ class SSLHotPath:
     current CUDA stream.  All inputs are CUDA tensors; nothing here touches the host."""
 
     def __init__(self, out_dim, n_local, teacher_params, student_params, nepochs=41,
-                 warmup_teacher_temp=0.04, teacher_temp=0.07, warmup_teacher_temp_epochs=30):
+                 warmup_teacher_temp=0.04, teacher_temp=0.07, warmup_teacher_temp_epochs=30,
+                 student_embed=None, teacher_embed=None):
+        """student_embed / teacher_embed: (weight [dim,192], bias [dim]) of the two
+        patch_to_embedding layers (ViT_face.py:619); enables the fused gather->embed path."""
         self.n_local = n_local
+        self.embed_global = self.embed_local = None
+        if student_embed is not None:
+            self.embed_global = PatchEmbedWeights([student_embed, teacher_embed])   # 2 models, 1 gather
+            self.embed_local = PatchEmbedWeights([student_embed])
         self.loss = DINOLoss(out_dim, n_local + 2, warmup_teacher_temp, teacher_temp,
                              warmup_teacher_temp_epochs, nepochs).cuda()
         self.ema = EmaPlan(list(teacher_params), list(student_params))
@@ -37,6 +44,18 @@ class SSLHotPath:
         theta_l = landmark_post(raw_l, noise_l, idx_l)
         tok_l = extract_tokens(img_l, theta_l)
         return theta_g, tok_g, theta_l, tok_l
+
+    def landmarks_and_embeddings(self, raw_g, noise_g, img_g, raw_l, noise_l, idx_l, img_l):
+        """Fused form: landmark tail, then gather -> patch_to_embedding on the tensor cores.
+        Returns (student_global, teacher_global, student_local) embedded tokens (bf16); the
+        patch mosaics / token tensors of the reference are never materialised."""
+        self.embed_global.refresh()        # weights moved by the optimizer / EMA since last step
+        self.embed_local.refresh()
+        theta_g = landmark_post(raw_g, noise_g)
+        s_g, t_g = gather_embed(img_g, theta_g, self.embed_global)
+        theta_l = landmark_post(raw_l, noise_l, idx_l)
+        (s_l,) = gather_embed(img_l, theta_l, self.embed_local)
+        return s_g, t_g, s_l
 
     def loss_and_grad(self, student_out, teacher_out, epoch):
         s = student_out.detach().requires_grad_(True)
