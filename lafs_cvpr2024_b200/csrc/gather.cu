@@ -232,7 +232,7 @@ static int gather_check(const float* imgs, const float* theta, int Bv, int C, in
                         int coord_mode, const char* who, int* r_out) {
   using namespace lafs;
   LAFS_REQUIRE(imgs && theta, LAFS_ERR_ARG, "%s: null pointer", who);
-  LAFS_REQUIRE(Bv >= 0 && n > 0 && H > 0 && W > 0, LAFS_ERR_ARG, "%s: bad sizes Bv=%d n=%d H=%d W=%d", who, Bv, n, H, W);
+  LAFS_REQUIRE(Bv > 0 && n > 0 && H > 0 && W > 0, LAFS_ERR_ARG, "%s: bad sizes Bv=%d n=%d H=%d W=%d", who, Bv, n, H, W);
   LAFS_REQUIRE(C >= 1 && C <= kMaxC, LAFS_ERR_ARG, "%s: C=%d outside [1,%d]", who, C, kMaxC);
   LAFS_REQUIRE(layout == LAFS_LAYOUT_MOSAIC || layout == LAFS_LAYOUT_TOKENS, LAFS_ERR_ARG, "%s: layout=%d", who, layout);
   LAFS_REQUIRE(coord_mode == LAFS_COORD_DIV || coord_mode == LAFS_COORD_RECIP, LAFS_ERR_ARG, "%s: coord_mode=%d", who, coord_mode);
@@ -246,6 +246,7 @@ static int gather_check(const float* imgs, const float* theta, int Bv, int C, in
 extern "C" int lafs_gather_fwd(const float* imgs, const float* theta, float* out, int Bv, int C, int H, int W,
                                int n, int layout, int coord_mode, lafs_stream_t stream) {
   using namespace lafs;
+  if (Bv == 0) return LAFS_OK;   // empty batch: nothing to do (pointers may be null)
   int r;
   int rc = gather_check(imgs, theta, Bv, C, H, W, n, layout, coord_mode, "lafs_gather_fwd", &r);
   if (rc) return rc;
@@ -265,6 +266,7 @@ extern "C" int lafs_gather_bwd(const float* imgs, const float* theta, const floa
                                float* grad_theta, int Bv, int C, int H, int W, int n, int layout,
                                int coord_mode, lafs_stream_t stream) {
   using namespace lafs;
+  if (Bv == 0) return LAFS_OK;
   int r;
   int rc = gather_check(imgs, theta, Bv, C, H, W, n, layout, coord_mode, "lafs_gather_bwd", &r);
   if (rc) return rc;
@@ -284,6 +286,7 @@ extern "C" int lafs_landmark_post(const float* raw, const float* noise, const in
                                   float* theta_out, float* minmax_out, int B, int n, int keep, float scale,
                                   lafs_stream_t stream) {
   using namespace lafs;
+  if (B == 0) return LAFS_OK;
   LAFS_REQUIRE(raw && theta_out, LAFS_ERR_ARG, "lafs_landmark_post: null pointer");
   LAFS_REQUIRE(B >= 0 && n > 0, LAFS_ERR_ARG, "lafs_landmark_post: B=%d n=%d", B, n);
   LAFS_REQUIRE(extract_id == nullptr || keep > 0, LAFS_ERR_ARG, "lafs_landmark_post: keep=%d with extract_id", keep);

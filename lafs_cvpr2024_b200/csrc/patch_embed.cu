@@ -314,6 +314,7 @@ extern "C" int lafs_gather_embed_fwd(const float* imgs, const float* theta, cons
                                      void* out0, void* out1, int out_dtype, int Bv, int H, int W, int n, int dim,
                                      int n_models, lafs_stream_t stream) {
   void* out0_bf16 = out0; void* out1_bf16 = out1;
+  if (Bv == 0) return LAFS_OK;
   LAFS_REQUIRE(imgs && theta && w_perm_bf16 && bias && out0_bf16, LAFS_ERR_ARG, "lafs_gather_embed_fwd: null pointer");
   LAFS_REQUIRE(out_dtype == LAFS_BF16 || out_dtype == LAFS_F32, LAFS_ERR_ARG, "lafs_gather_embed_fwd: out_dtype=%d (bf16 or fp32)", out_dtype);
   LAFS_REQUIRE(H == pe::kH && W == pe::kW, LAFS_ERR_ARG, "lafs_gather_embed_fwd: fused path is built for 112x112 faces, got %dx%d", H, W);

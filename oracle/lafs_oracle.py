@@ -80,12 +80,12 @@ def extract_patches(imgs, landmarks, num_landm=None, patch=PATCH, recip_mul=Fals
     n = landmarks.shape[1] if num_landm is None else num_landm
     landmarks = landmarks[:, :n]
     half = patch / 2
-    ar = torch.arange(-half, half, dtype=torch.float32)
+    ar = torch.arange(-half, half, dtype=torch.float32, device=landmarks.device)
     # sampling_grid[a][b] = (a-4, b-4)  (ViT_face.py:1637-1640)
     sg = torch.stack(torch.meshgrid(ar, ar, indexing="ij"), dim=-1)  # [8,8,2]
     pts = sg[None, None] + landmarks[:, :, None, None, :]  # [B,n,8,8,2]
     if recip_mul:
-        grid = pts * torch.tensor(1.0 / (H * 0.5), dtype=torch.float32) - 1
+        grid = pts * torch.tensor(1.0 / (H * 0.5), dtype=torch.float32, device=pts.device) - 1
     else:
         grid = pts / (H * 0.5) - 1
     out = F.grid_sample(imgs, grid.reshape(B, n * patch, patch, 2), align_corners=False)
