@@ -150,8 +150,13 @@ LAFS_API int lafs_gather_bwd(const float* imgs, const float* theta, const float*
  * lafs_head_loss  -> row_lse2 [B] (log2-domain lse, kept for backward) and the mean loss.
  * lafs_head_logits-> the full fp32 logits [B, C_local] (row stride ldc) for API parity with
  *                    CosFace.forward.
- * lafs_head_grad_logits -> (softmax - target)*gscale as bf16 [B, C_local] (row stride ldg),
- *                    recomputing the logits on the tensor cores.
+ * lafs_head_grad_logits -> G = (softmax - target) * d z/d cos * gscale * (*grad_out) as bf16
+ *                    [B, C_local] (row stride ldg, a multiple of 8), recomputing the logits on the
+ *                    tensor cores; gscale = s / B_global, grad_out = device scalar upstream gradient.
+ * lafs_head_bwd_embed  -> grad_e_hat [B,D] fp32 = G . W_hat (split-K GEMM; sharded heads all-reduce
+ *                    it over ranks before the Jacobian).  workspace: lafs_head_bwd_workspace_bytes.
+ * lafs_head_bwd_weight -> grad_w [C_local,D] fp32 = normalize-backward(G^T . E_hat).
+ * lafs_normalize_bwd   -> out = (g - x_hat <x_hat, g>) * inv_norm per row (F.normalize backward).
  */
 LAFS_API int lafs_normalize_rows(const void* x, int dtype, int R, int D, void* out_bf16, float* inv_norm,
                                  lafs_stream_t stream);
@@ -167,8 +172,16 @@ LAFS_API int lafs_head_logits(const void* e_hat, const void* w_hat, const int64_
                               float* logits, long long ldc, lafs_stream_t stream);
 LAFS_API int lafs_head_grad_logits(const void* e_hat, const void* w_hat, const int64_t* label_a, const int64_t* label_b,
                                    float lam, int B, int C_local, int D, int class_lo, float s, float m, int kind,
-                                   const float* row_lse2, float gscale, void* grad_bf16, long long ldg,
-                                   lafs_stream_t stream);
+                                   const float* row_lse2, const float* grad_out, float gscale, void* grad_bf16,
+                                   long long ldg, lafs_stream_t stream);
+LAFS_API size_t lafs_head_bwd_workspace_bytes(int B, int C_local, int D);
+LAFS_API int lafs_head_bwd_embed(const void* grad_bf16, long long ldg, const void* w_hat, int B, int C_local, int D,
+                                 float* grad_e_hat, void* workspace, size_t workspace_bytes, lafs_stream_t stream);
+LAFS_API int lafs_head_bwd_weight(const void* grad_bf16, long long ldg, const void* e_hat, const void* w_hat,
+                                  const float* inv_norm_w, int B, int C_local, int D, float* grad_w,
+                                  lafs_stream_t stream);
+LAFS_API int lafs_normalize_bwd(const float* g, const void* x_hat_bf16, const float* inv_norm, int R, int D, float* out,
+                                lafs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * (1b) Fused landmark gather -> patch embedding on tensor cores

@@ -42,7 +42,11 @@ SIGNATURES = {
     "lafs_head_merge": (_i, [_p, _i, _i, _p, _p]),
     "lafs_head_loss": (_i, [_p, _p, _p, _f, _i, _p, _p, _p]),
     "lafs_head_logits": (_i, [_p, _p, _p, _p, _f, _i, _i, _i, _i, _f, _f, _i, _p, C.c_longlong, _p]),
-    "lafs_head_grad_logits": (_i, [_p, _p, _p, _p, _f, _i, _i, _i, _i, _f, _f, _i, _p, _f, _p, C.c_longlong, _p]),
+    "lafs_head_grad_logits": (_i, [_p, _p, _p, _p, _f, _i, _i, _i, _i, _f, _f, _i, _p, _p, _f, _p, C.c_longlong, _p]),
+    "lafs_head_bwd_workspace_bytes": (_z, [_i, _i, _i]),
+    "lafs_head_bwd_embed": (_i, [_p, C.c_longlong, _p, _i, _i, _i, _p, _p, _z, _p]),
+    "lafs_head_bwd_weight": (_i, [_p, C.c_longlong, _p, _p, _p, _i, _i, _i, _p, _p]),
+    "lafs_normalize_bwd": (_i, [_p, _p, _p, _i, _i, _p, _p]),
 }
 
 _lib = None

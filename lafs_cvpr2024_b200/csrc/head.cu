@@ -42,7 +42,8 @@ struct HeadParams {
   const float* row_lse2;             // GRAD: [B] log2-domain lse of the full row
   __nv_bfloat16* grad;               // GRAD: [B][ldg] bf16  (softmax - target) * gscale
   long long ldg;
-  float gscale;
+  float gscale;                      // s / B_global
+  const float* grad_out;             // device scalar: upstream gradient of the loss
 };
 
 // margin-adjusted, s-scaled logit (natural units) of a class whose target weight is t (0..1)
@@ -53,6 +54,14 @@ __device__ __forceinline__ float margin_logit(float cosv, float t, const HeadPar
   float phi = cosv * p.cos_m - sine * p.sin_m;
   phi = cosv > p.th ? phi : cosv - p.mm;
   return p.s * phi;  // ArcFace (hard labels only)
+}
+
+// d(margin_logit)/d(cos) / s for the target class (1 for CosFace and for non-target classes)
+__device__ __forceinline__ float margin_dcos(float cosv, const HeadParams& p) {
+  if (p.kind == 0) return 1.f;
+  if (!(cosv > p.th)) return 1.f;
+  const float sine = sqrtf(fminf(fmaxf(1.f - cosv * cosv, 1e-12f), 1.f));
+  return p.cos_m + cosv * p.sin_m / sine;
 }
 
 template <int BN, int MODE>
@@ -155,7 +164,8 @@ head_gemm_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
     const float k2 = kLog2eH;                // natural logit -> log2 domain
     float m_run = -INFINITY, l_run = 0.f, tgt_a = 0.f, tgt_b = 0.f;
     float lse2 = 0.f;
-    if (MODE == HEAD_GRAD && row_ok) lse2 = p.row_lse2[b];
+    float gscale = 0.f;
+    if (MODE == HEAD_GRAD && row_ok) { lse2 = p.row_lse2[b]; gscale = p.gscale * __ldg(p.grad_out); }
     int it = 0;
     for (int chunk = range; chunk < p.nchunks; chunk += p.nranges, ++it) {
       const int buf = it & 1;
@@ -211,9 +221,9 @@ head_gemm_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
             for (int j = 0; j < 32; ++j) {
               const int c = cbase + j;
               float g = ex2(fmaf(z[j], k2, -lse2));
-              if (has_a && c == (int)la) g -= ta;
+              if (has_a && c == (int)la) g = (g - ta) * margin_dcos(__uint_as_float(raw[j]), p);
               if (has_b && c == (int)lb) g -= tb;
-              if (c < p.C_local) dst[j] = __float2bfloat16_rn(g * p.gscale);
+              if (c < p.C_local) dst[j] = __float2bfloat16_rn(g * gscale);
             }
           }
         }
@@ -455,13 +465,13 @@ extern "C" int lafs_head_loss(const float* row_stats, const int64_t* label_a, co
 
 extern "C" int lafs_head_grad_logits(const void* e_hat, const void* w_hat, const int64_t* label_a, const int64_t* label_b,
                                      float lam, int B, int C_local, int D, int class_lo, float s, float m, int kind,
-                                     const float* row_lse2, float gscale, void* grad_bf16, long long ldg,
-                                     lafs_stream_t stream) {
+                                     const float* row_lse2, const float* grad_out, float gscale, void* grad_bf16,
+                                     long long ldg, lafs_stream_t stream) {
   HeadParams p; HeadLaunch hl; CUtensorMap te, tw;
   int rc = head_common(e_hat, w_hat, label_a, label_b, lam, B, C_local, D, class_lo, s, m, kind, &p, &hl, &te, &tw, "lafs_head_grad_logits");
   if (rc) return rc;
-  LAFS_REQUIRE(row_lse2 && grad_bf16 && ldg >= C_local, LAFS_ERR_ARG, "lafs_head_grad_logits: bad argument");
-  p.row_lse2 = row_lse2; p.grad = (__nv_bfloat16*)grad_bf16; p.ldg = ldg; p.gscale = gscale;
+  LAFS_REQUIRE(row_lse2 && grad_out && grad_bf16 && ldg >= C_local, LAFS_ERR_ARG, "lafs_head_grad_logits: bad argument");
+  p.row_lse2 = row_lse2; p.grad = (__nv_bfloat16*)grad_bf16; p.ldg = ldg; p.gscale = gscale; p.grad_out = grad_out;
   cudaStream_t st = (cudaStream_t)stream;
   return hl.BN == 256 ? launch_head<256, HEAD_GRAD>(te, tw, p, hl, st) : launch_head<128, HEAD_GRAD>(te, tw, p, hl, st);
 }

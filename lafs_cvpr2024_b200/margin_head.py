@@ -61,6 +61,120 @@ def _prep(x, want_inv=False):
     return out, inv
 
 
+def _round8(n):
+    return (n + 7) // 8 * 8
+
+
+def _head_backward(G, ldg, e_hat, w_hat, inv_e, inv_w, B, C, D, sharded):
+    """dE [B,D], dW [C,D] (fp32) from the bf16 logit gradient G [B, ldg] via two tcgen05 GEMMs."""
+    dev = e_hat.device
+    nbytes = _lib.lib().lafs_head_bwd_workspace_bytes(B, C, D)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    de_hat = torch.empty(B, D, dtype=torch.float32, device=dev)
+    _lib.call("lafs_head_bwd_embed", G.data_ptr(), ldg, w_hat.data_ptr(), B, C, D, de_hat.data_ptr(),
+              ws.data_ptr(), nbytes, _lib.stream())
+    if sharded:
+        dist.all_reduce(de_hat)                      # sum over the class shards
+    de = torch.empty_like(de_hat)
+    _lib.call("lafs_normalize_bwd", de_hat.data_ptr(), e_hat.data_ptr(), inv_e.data_ptr(), B, D, de.data_ptr(),
+              _lib.stream())
+    dw = torch.empty(C, D, dtype=torch.float32, device=dev)
+    _lib.call("lafs_head_bwd_weight", G.data_ptr(), ldg, e_hat.data_ptr(), w_hat.data_ptr(), inv_w.data_ptr(),
+              B, C, D, dw.data_ptr(), _lib.stream())
+    return de, dw
+
+
+class _HeadLossFn(torch.autograd.Function):
+    """Fused margin head + softmax cross-entropy.  Nothing of size [B, C] is saved for backward:
+    the bf16 logit gradient is recomputed on the tensor cores from the saved row statistics."""
+
+    @staticmethod
+    def forward(ctx, input, weight, head, la, lb, lam):
+        B, D = input.shape
+        C = weight.shape[0]
+        e_hat, inv_e = _prep(input, want_inv=True)
+        w_hat, inv_w = _prep(weight, want_inv=True)
+        dev = input.device
+        stats = torch.empty(B, 4, dtype=torch.float32, device=dev)
+        nbytes = _lib.lib().lafs_head_workspace_bytes(B, C, D)
+        if nbytes == 0:
+            raise ValueError(f"unsupported head shape B={B} C={C} D={D}")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _lib.call("lafs_head_fwd", e_hat.data_ptr(), w_hat.data_ptr(), la.data_ptr(), _lib.ptr(lb), lam,
+                  B, C, D, head.class_lo, float(head.s), float(head.m), head.kind, stats.data_ptr(),
+                  ws.data_ptr(), nbytes, _lib.stream())
+        sharded = head.shard is not None and head.shard[1] > 1
+        if sharded:
+            parts = torch.empty(head.shard[1], B, 4, dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(parts, stats)
+            stats = torch.empty_like(stats)
+            _lib.call("lafs_head_merge", parts.data_ptr(), head.shard[1], B, stats.data_ptr(), _lib.stream())
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        lse2 = torch.empty(B, dtype=torch.float32, device=dev)
+        _lib.call("lafs_head_loss", stats.data_ptr(), la.data_ptr(), _lib.ptr(lb), lam, B, lse2.data_ptr(),
+                  loss.data_ptr(), _lib.stream())
+        ctx.save_for_backward(e_hat, w_hat, inv_e, inv_w, la, lb if lb is not None else la, lse2)
+        ctx.cfg = (head.class_lo, float(head.s), float(head.m), head.kind, lam, lb is not None, sharded,
+                   input.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        e_hat, w_hat, inv_e, inv_w, la, lb, lse2 = ctx.saved_tensors
+        class_lo, s, m, kind, lam, has_b, sharded, in_dtype = ctx.cfg
+        B, D = e_hat.shape
+        C = w_hat.shape[0]
+        ldg = _round8(C)
+        G = torch.empty(B, ldg, dtype=torch.bfloat16, device=e_hat.device)
+        g = grad_loss.detach().float().contiguous()
+        _lib.call("lafs_head_grad_logits", e_hat.data_ptr(), w_hat.data_ptr(), la.data_ptr(),
+                  lb.data_ptr() if has_b else None, lam, B, C, D, class_lo, s, m, kind, lse2.data_ptr(),
+                  g.data_ptr(), s / B, G.data_ptr(), ldg, _lib.stream())
+        de, dw = _head_backward(G, ldg, e_hat, w_hat, inv_e, inv_w, B, C, D, sharded)
+        return de.to(in_dtype), dw, None, None, None, None
+
+
+class _HeadLogitsFn(torch.autograd.Function):
+    """CosFace.forward parity path: full fp32 logits out, gradients through the same GEMMs."""
+
+    @staticmethod
+    def forward(ctx, input, weight, head, la, lb, lam):
+        B, D = input.shape
+        C = weight.shape[0]
+        e_hat, inv_e = _prep(input, want_inv=True)
+        w_hat, inv_w = _prep(weight, want_inv=True)
+        out = torch.empty(B, C, dtype=torch.float32, device=input.device)
+        _lib.call("lafs_head_logits", e_hat.data_ptr(), w_hat.data_ptr(), la.data_ptr(), _lib.ptr(lb), lam,
+                  B, C, D, head.class_lo, float(head.s), float(head.m), head.kind, out.data_ptr(), C, _lib.stream())
+        ctx.save_for_backward(e_hat, w_hat, inv_e, inv_w, la)
+        ctx.cfg = (float(head.s), float(head.m), head.kind, head.class_lo, input.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_logits):
+        e_hat, w_hat, inv_e, inv_w, la = ctx.saved_tensors
+        s, m, kind, class_lo, in_dtype = ctx.cfg
+        B, D = e_hat.shape
+        C = w_hat.shape[0]
+        ldg = _round8(C)
+        G = torch.zeros(B, ldg, dtype=torch.bfloat16, device=e_hat.device)
+        gz = grad_logits.detach().float() * s                      # d z / d cos = s (margin is a shift)
+        if kind == KIND_ARCFACE:                                   # target column: s * d phi / d cos
+            loc = la - class_lo
+            own = (loc >= 0) & (loc < C)
+            rows = torch.nonzero(own).flatten()
+            if rows.numel():
+                cols = loc[rows]
+                cos_t = (e_hat[rows].float() * w_hat[cols].float()).sum(1)
+                th = math.cos(math.pi - m)
+                sine = torch.sqrt((1 - cos_t * cos_t).clamp(1e-12, 1))
+                dphi = torch.where(cos_t > th, math.cos(m) + cos_t * math.sin(m) / sine, torch.ones_like(cos_t))
+                gz[rows, cols] = gz[rows, cols] * dphi
+        G[:, :C] = gz.to(torch.bfloat16)
+        de, dw = _head_backward(G, ldg, e_hat, w_hat, inv_e, inv_w, B, C, D, False)
+        return de.to(in_dtype), dw, None, None, None, None
+
+
 class _MarginHead(nn.Module):
     kind = KIND_COSFACE
 
@@ -101,13 +215,10 @@ class _MarginHead(nn.Module):
     def forward(self, input, label):
         """Full logits s*(cos - m*target) for the local classes (all classes when unsharded)."""
         la, lb, lam = self._labels(label, None, 1.0)
-        e_hat, w_hat = self._operands(input)
-        B, C = input.shape[0], self.weight.shape[0]
-        out = torch.empty(B, C, dtype=torch.float32, device=input.device)
-        _lib.call("lafs_head_logits", e_hat.data_ptr(), w_hat.data_ptr(), la.data_ptr(), _lib.ptr(lb), lam,
-                  B, C, self.in_features, self.class_lo, float(self.s), float(self.m), self.kind,
-                  out.data_ptr(), C, _lib.stream())
-        return out
+        _lib.require_cuda(input, self.weight)
+        if input.dim() != 2 or input.shape[1] != self.in_features:
+            raise ValueError(f"input must be [B, {self.in_features}], got {tuple(input.shape)}")
+        return _HeadLogitsFn.apply(input, self.weight, self, la, lb, lam)
 
     def forward_stats(self, input, label, label_b=None, lam=1.0):
         """Per-row (max2, sum-exp, z_a, z_b) over this rank's classes; [B,4] fp32."""
@@ -124,10 +235,19 @@ class _MarginHead(nn.Module):
                   stats.data_ptr(), ws.data_ptr(), nbytes, _lib.stream())
         return stats, (la, lb, lam, e_hat, w_hat)
 
-    @torch.no_grad()
     def forward_loss(self, input, label, label_b=None, lam=1.0):
-        """Fused head + cross-entropy (mean over the batch every rank sees).  Forward only in
-        this revision; returns (loss, row_lse2)."""
+        """Fused head + cross-entropy, differentiable w.r.t. input and weight: the mean (over the
+        batch every rank sees) of CrossEntropyLoss / SoftTargetCrossEntropy applied to
+        CosFace.forward's logits (train_largescale.py:815-820), without materialising them."""
+        la, lb, lam = self._labels(label, label_b, lam)
+        _lib.require_cuda(input, self.weight)
+        if input.dim() != 2 or input.shape[1] != self.in_features:
+            raise ValueError(f"input must be [B, {self.in_features}], got {tuple(input.shape)}")
+        return _HeadLossFn.apply(input, self.weight, self, la, lb, lam)
+
+    @torch.no_grad()
+    def forward_loss_stats(self, input, label, label_b=None, lam=1.0):
+        """(loss, row_lse2) without autograd (evaluation / tests)."""
         stats, (la, lb, lam, _, _) = self.forward_stats(input, label, label_b, lam)
         B = input.shape[0]
         if self.shard is not None and self.shard[1] > 1:

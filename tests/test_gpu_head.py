@@ -46,15 +46,15 @@ def test_cosface_golden_logits_and_loss(P, golden):
     ref = T(g["logits_hard"])
     assert logits.shape == ref.shape
     assert (logits - ref).abs().max() <= 1e-3 * ref.abs().max() * 8   # bf16 operands: ~2^-9 * 64
-    loss, _ = h.forward_loss(x.cuda(), lab.cuda())
+    loss, _ = h.forward_loss_stats(x.cuda(), lab.cuda())
     assert abs(float(loss) - float(g["loss_hard"])) <= 5e-3 * abs(float(g["loss_hard"]))
     # soft (mixup) targets through the dense [B, C] reference API and through the two-label form
     soft = O.mixup_target(lab, w.shape[0], float(g["lam"]))
     logits_s = h(x.cuda(), soft.cuda()).cpu()
     assert (logits_s - T(g["logits_soft"])).abs().max() <= 8e-3 * ref.abs().max()
-    loss_s, _ = h.forward_loss(x.cuda(), lab.cuda(), T(g["label_b"]).cuda(), float(g["lam"]))
+    loss_s, _ = h.forward_loss_stats(x.cuda(), lab.cuda(), T(g["label_b"]).cuda(), float(g["lam"]))
     assert abs(float(loss_s) - float(g["loss_soft"])) <= 5e-3 * abs(float(g["loss_soft"]))
-    loss_d, _ = h.forward_loss(x.cuda(), soft.cuda())
+    loss_d, _ = h.forward_loss_stats(x.cuda(), soft.cuda())
     assert abs(float(loss_d) - float(loss_s)) <= 1e-5 * abs(float(loss_s))
 
 
@@ -73,7 +73,7 @@ def test_head_vs_oracle_on_same_bf16_operands(P, B, C, D, kind):
     logits = h(x.cuda(), lab.cuda()).cpu()
     scale = ref_logits.abs().max()
     assert (logits - ref_logits).abs().max() <= 1e-3 * scale, float((logits - ref_logits).abs().max())
-    loss, lse2 = h.forward_loss(x.cuda(), lab.cuda())
+    loss, lse2 = h.forward_loss_stats(x.cuda(), lab.cuda())
     assert abs(float(loss) - float(ref_loss)) <= 1e-3 * abs(float(ref_loss)), (float(loss), float(ref_loss))
     ref_lse = torch.logsumexp(ref_logits, 1)
     assert (lse2.cpu() * np.log(2.0) - ref_lse).abs().max() <= 1e-3 * ref_lse.abs().max()
@@ -87,7 +87,7 @@ def test_head_mixup_soft_labels_vs_oracle(P):
     lam = 0.37
     h = make_head(P, P.CosFace, w)
     ref_loss, ref_logits, _, _ = oracle_on_bf16_operands(x, w, lab, "cosface", label_b=lab.flip(0), lam=lam)
-    loss, _ = h.forward_loss(x.cuda(), lab.cuda(), lab.flip(0).cuda(), lam)
+    loss, _ = h.forward_loss_stats(x.cuda(), lab.cuda(), lab.flip(0).cuda(), lam)
     assert abs(float(loss) - float(ref_loss)) <= 1e-3 * abs(float(ref_loss))
     dense = O.mixup_target(lab, C, lam)
     logits = h(x.cuda(), dense.cuda()).cpu()
@@ -111,7 +111,7 @@ def test_sharded_stats_merge_equals_unsharded(P):
     x, w = torch.randn(B, D), torch.randn(C, D)
     lab = torch.randint(0, C, (B,))
     full = make_head(P, P.CosFace, w)
-    loss_full, lse_full = full.forward_loss(x.cuda(), lab.cuda())
+    loss_full, lse_full = full.forward_loss_stats(x.cuda(), lab.cuda())
     from lafs_cvpr2024_b200 import _lib
     parts = []
     for r, (lo, hi) in enumerate(P.shard_bounds(C, R)):
@@ -129,3 +129,56 @@ def test_sharded_stats_merge_equals_unsharded(P):
     _lib.call("lafs_head_loss", merged.data_ptr(), la.data_ptr(), None, 1.0, B, lse2.data_ptr(), loss.data_ptr(), _lib.stream())
     assert abs(float(loss) - float(loss_full)) <= 1e-5 * abs(float(loss_full))
     torch.testing.assert_close(lse2, lse_full, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("B,C,D", [(8, 1000, 64), (130, 777, 128), (512, 5000, 512), (64, 3001, 768), (300, 20011, 512)])
+@pytest.mark.parametrize("kind", ["cosface", "arcface"])
+def test_head_backward_vs_oracle(P, B, C, D, kind):
+    """dE, dW of the fused loss against autograd on the oracle (fp32, same bf16-rounded operands)."""
+    torch.manual_seed(B + C + D + 1)
+    x = torch.randn(B, D)
+    w = torch.randn(C, D) * 0.05
+    lab = torch.randint(0, C, (B,))
+    cls = P.CosFace if kind == "cosface" else P.ArcFace
+    h = make_head(P, cls, w)
+    ref_loss, _, ref_gx, ref_gw = O.head_loss_and_grads(x, w, lab, kind)
+    xg = x.cuda().requires_grad_(True)
+    loss = h.forward_loss(xg, lab.cuda())
+    loss.backward()
+    assert abs(float(loss) - float(ref_loss)) <= 5e-3 * abs(float(ref_loss))
+    gx, gw = xg.grad.cpu(), h.weight.grad.cpu()
+    # bf16 operands + bf16 logit gradient: compare in the max-norm-relative sense (SURVEY H4)
+    assert (gx - ref_gx).abs().max() <= 2e-2 * ref_gx.abs().max(), float((gx - ref_gx).abs().max() / ref_gx.abs().max())
+    assert (gw - ref_gw).abs().max() <= 2e-2 * ref_gw.abs().max(), float((gw - ref_gw).abs().max() / ref_gw.abs().max())
+    # direction check: cosine similarity of the full gradients
+    cs = torch.nn.functional.cosine_similarity(gw.flatten(), ref_gw.flatten(), dim=0)
+    assert cs > 0.9995, float(cs)
+
+
+def test_head_backward_soft_labels_and_grad_out(P):
+    torch.manual_seed(11)
+    B, C, D = 96, 2048, 256
+    x, w = torch.randn(B, D), torch.randn(C, D) * 0.1
+    lab = torch.randint(0, C, (B,))
+    lam = 0.3
+    h = make_head(P, P.CosFace, w)
+    ref_loss, _, ref_gx, ref_gw = O.head_loss_and_grads(x, w, lab, "cosface", label_b=lab.flip(0), lam=lam, grad_out=3.0)
+    xg = x.cuda().requires_grad_(True)
+    loss = h.forward_loss(xg, lab.cuda(), lab.flip(0).cuda(), lam)
+    (loss * 3.0).backward()
+    gx, gw = xg.grad.cpu(), h.weight.grad.cpu()
+    assert (gx - ref_gx).abs().max() <= 2e-2 * ref_gx.abs().max()
+    assert (gw - ref_gw).abs().max() <= 2e-2 * ref_gw.abs().max()
+
+
+def test_cosface_forward_logits_backward_golden(P, golden):
+    """Drop-in use: logits = head(x, label); CrossEntropyLoss(logits, label).backward()  (reference grads)."""
+    g = golden("cosface")
+    x, w, lab = T(g["x"]), T(g["weight"]), T(g["label"])
+    h = make_head(P, P.CosFace, w)
+    xg = x.cuda().requires_grad_(True)
+    logits = h(xg, lab.cuda())
+    torch.nn.CrossEntropyLoss()(logits, lab.cuda()).backward()
+    ref_gx, ref_gw = T(g["grad_x_hard"]), T(g["grad_w_hard"])
+    assert (xg.grad.cpu() - ref_gx).abs().max() <= 2e-2 * ref_gx.abs().max()
+    assert (h.weight.grad.cpu() - ref_gw).abs().max() <= 2e-2 * ref_gw.abs().max()
