@@ -22,6 +22,24 @@ int check_launch(const char* what) {
   }
   return LAFS_OK;
 }
+int bind_device_of(const void* device_ptr) {
+  if (device_ptr == nullptr) return LAFS_OK;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, device_ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return LAFS_OK;   // not a CUDA pointer we can classify: keep the thread's current device
+  }
+  if (a.type != cudaMemoryTypeDevice && a.type != cudaMemoryTypeManaged) return LAFS_OK;
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess || cur != a.device) {
+    if (cudaSetDevice(a.device) != cudaSuccess) {
+      set_last_error("cudaSetDevice(%d): %s", a.device, cudaGetErrorString(cudaGetLastError()));
+      return LAFS_ERR_CUDA;
+    }
+  }
+  cudaFree(0);  // force the primary context current on this thread (driver entry points need it)
+  return LAFS_OK;
+}
 }  // namespace lafs
 
 extern "C" int lafs_version(void) { return 100; }

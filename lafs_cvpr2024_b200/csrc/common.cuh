@@ -16,6 +16,10 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 // ---- error plumbing (no exceptions cross the C ABI) --------------------------------------
 void set_last_error(const char* fmt, ...);
 int check_launch(const char* what);  // cudaGetLastError -> 0 or negative code, records message
+// Makes the device that owns `device_ptr` current for THIS library's runtime on the calling thread.
+// The library links its own (static) CUDA runtime, whose per-thread device defaults to 0; PyTorch's
+// autograd worker threads set their device lazily, so every entry point binds explicitly.
+int bind_device_of(const void* device_ptr);
 
 #define LAFS_REQUIRE(cond, code, ...)                 \
   do {                                                \

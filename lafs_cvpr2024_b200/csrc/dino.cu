@@ -474,6 +474,7 @@ extern "C" int lafs_dino_fwd(const void* student, const void* teacher, const flo
                              int ncrops, float inv_student_temp, float inv_teacher_temp, int dtype,
                              float* loss_out, float* row_stats, float* colsum_out, void* workspace,
                              size_t workspace_bytes, lafs_stream_t stream) {
+  if (int brc = lafs::bind_device_of(student)) return brc;
   using namespace lafs;
   int rc = dino_check(student, teacher, center, B, K, ncrops, dtype, "lafs_dino_fwd");
   if (rc) return rc;
@@ -503,6 +504,7 @@ extern "C" int lafs_dino_bwd(const void* student, const void* teacher, const flo
                              const float* row_stats, const float* grad_out, int B, int K, int ncrops,
                              float inv_student_temp, float inv_teacher_temp, int dtype, void* grad_student,
                              lafs_stream_t stream) {
+  if (int brc = lafs::bind_device_of(student)) return brc;
   using namespace lafs;
   int rc = dino_check(student, teacher, center, B, K, ncrops, dtype, "lafs_dino_bwd");
   if (rc) return rc;
@@ -526,6 +528,7 @@ extern "C" int lafs_dino_bwd(const void* student, const void* teacher, const flo
 
 extern "C" int lafs_center_ema(const float* center, const float* colsum, float count, float momentum,
                                float one_minus_momentum, int K, float* center_out, lafs_stream_t stream) {
+  if (int brc = lafs::bind_device_of(center)) return brc;
   using namespace lafs;
   LAFS_REQUIRE(center && colsum && center_out && K > 0, LAFS_ERR_ARG, "lafs_center_ema: bad argument");
   center_ema_kernel<<<(K + 255) / 256, 256, 0, (cudaStream_t)stream>>>(center, colsum, count, momentum,
@@ -535,6 +538,7 @@ extern "C" int lafs_center_ema(const float* center, const float* colsum, float c
 
 extern "C" int lafs_colsum(const void* x, int rows, int K, int dtype, float* out, void* workspace,
                            size_t workspace_bytes, lafs_stream_t stream) {
+  if (int brc = lafs::bind_device_of(x)) return brc;
   using namespace lafs;
   LAFS_REQUIRE(x && out && workspace && rows > 0 && K > 0, LAFS_ERR_ARG, "lafs_colsum: bad argument");
   LAFS_REQUIRE(dtype >= 0 && dtype <= 2, LAFS_ERR_ARG, "lafs_colsum: dtype=%d", dtype);

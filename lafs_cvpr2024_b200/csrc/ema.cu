@@ -67,6 +67,7 @@ ema_multi_kernel(const EmaChunk* __restrict__ table, float m, float om) {
 
 extern "C" int lafs_ema_multi(const void* table, int nchunks, float m, float one_minus_m,
                               lafs_stream_t stream) {
+  if (int brc = lafs::bind_device_of(table)) return brc;
   using namespace lafs;
   if (nchunks == 0) return LAFS_OK;
   LAFS_REQUIRE(table != nullptr && nchunks > 0, LAFS_ERR_ARG, "lafs_ema_multi: null table or nchunks<0");

@@ -245,6 +245,7 @@ static int gather_check(const float* imgs, const float* theta, int Bv, int C, in
 
 extern "C" int lafs_gather_fwd(const float* imgs, const float* theta, float* out, int Bv, int C, int H, int W,
                                int n, int layout, int coord_mode, lafs_stream_t stream) {
+  if (int brc = lafs::bind_device_of(imgs)) return brc;
   using namespace lafs;
   if (Bv == 0) return LAFS_OK;   // empty batch: nothing to do (pointers may be null)
   int r;
@@ -265,6 +266,7 @@ extern "C" int lafs_gather_fwd(const float* imgs, const float* theta, float* out
 extern "C" int lafs_gather_bwd(const float* imgs, const float* theta, const float* grad_out, float* grad_imgs,
                                float* grad_theta, int Bv, int C, int H, int W, int n, int layout,
                                int coord_mode, lafs_stream_t stream) {
+  if (int brc = lafs::bind_device_of(imgs)) return brc;
   using namespace lafs;
   if (Bv == 0) return LAFS_OK;
   int r;
@@ -285,6 +287,7 @@ extern "C" int lafs_gather_bwd(const float* imgs, const float* theta, const floa
 extern "C" int lafs_landmark_post(const float* raw, const float* noise, const int64_t* extract_id,
                                   float* theta_out, float* minmax_out, int B, int n, int keep, float scale,
                                   lafs_stream_t stream) {
+  if (int brc = lafs::bind_device_of(raw)) return brc;
   using namespace lafs;
   if (B == 0) return LAFS_OK;
   LAFS_REQUIRE(raw && theta_out, LAFS_ERR_ARG, "lafs_landmark_post: null pointer");
@@ -298,6 +301,7 @@ extern "C" int lafs_landmark_post(const float* raw, const float* noise, const in
 
 extern "C" int lafs_landmark_post_bwd(const float* raw, const float* grad_theta, float* grad_raw, int B, int n,
                                       float scale, lafs_stream_t stream) {
+  if (int brc = lafs::bind_device_of(raw)) return brc;
   using namespace lafs;
   LAFS_REQUIRE(raw && grad_theta && grad_raw, LAFS_ERR_ARG, "lafs_landmark_post_bwd: null pointer");
   LAFS_REQUIRE(B >= 0 && n > 0, LAFS_ERR_ARG, "lafs_landmark_post_bwd: B=%d n=%d", B, n);

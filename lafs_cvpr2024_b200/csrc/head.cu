@@ -404,6 +404,7 @@ using namespace lafs;
 
 extern "C" int lafs_normalize_rows(const void* x, int dtype, int R, int D, void* out_bf16, float* inv_norm,
                                    lafs_stream_t stream) {
+  if (int brc = lafs::bind_device_of(x)) return brc;
   LAFS_REQUIRE(x && out_bf16 && R >= 0 && D > 0, LAFS_ERR_ARG, "lafs_normalize_rows: bad argument");
   LAFS_REQUIRE(dtype >= 0 && dtype <= 2, LAFS_ERR_ARG, "lafs_normalize_rows: dtype=%d", dtype);
   if (R == 0) return LAFS_OK;
@@ -424,6 +425,7 @@ extern "C" size_t lafs_head_workspace_bytes(int B, int C_local, int D) {
 extern "C" int lafs_head_fwd(const void* e_hat, const void* w_hat, const int64_t* label_a, const int64_t* label_b,
                              float lam, int B, int C_local, int D, int class_lo, float s, float m, int kind,
                              float* row_stats, void* workspace, size_t workspace_bytes, lafs_stream_t stream) {
+  if (int brc = lafs::bind_device_of(e_hat)) return brc;
   HeadParams p; HeadLaunch hl; CUtensorMap te, tw;
   int rc = head_common(e_hat, w_hat, label_a, label_b, lam, B, C_local, D, class_lo, s, m, kind, &p, &hl, &te, &tw, "lafs_head_fwd");
   if (rc) return rc;
@@ -441,6 +443,7 @@ extern "C" int lafs_head_fwd(const void* e_hat, const void* w_hat, const int64_t
 extern "C" int lafs_head_logits(const void* e_hat, const void* w_hat, const int64_t* label_a, const int64_t* label_b,
                                 float lam, int B, int C_local, int D, int class_lo, float s, float m, int kind,
                                 float* logits, long long ldc, lafs_stream_t stream) {
+  if (int brc = lafs::bind_device_of(e_hat)) return brc;
   HeadParams p; HeadLaunch hl; CUtensorMap te, tw;
   int rc = head_common(e_hat, w_hat, label_a, label_b, lam, B, C_local, D, class_lo, s, m, kind, &p, &hl, &te, &tw, "lafs_head_logits");
   if (rc) return rc;
@@ -451,6 +454,7 @@ extern "C" int lafs_head_logits(const void* e_hat, const void* w_hat, const int6
 }
 
 extern "C" int lafs_head_merge(const float* parts, int nparts, int B, float* row_stats, lafs_stream_t stream) {
+  if (int brc = lafs::bind_device_of(parts)) return brc;
   LAFS_REQUIRE(parts && row_stats && nparts > 0 && B > 0, LAFS_ERR_ARG, "lafs_head_merge: bad argument");
   head_merge_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(parts, B, nparts, (long long)B * 4, 4, row_stats);
   return check_launch("lafs_head_merge");
@@ -458,6 +462,7 @@ extern "C" int lafs_head_merge(const float* parts, int nparts, int B, float* row
 
 extern "C" int lafs_head_loss(const float* row_stats, const int64_t* label_a, const int64_t* label_b, float lam, int B,
                               float* row_lse2, float* loss_out, lafs_stream_t stream) {
+  if (int brc = lafs::bind_device_of(row_stats)) return brc;
   LAFS_REQUIRE(row_stats && label_a && row_lse2 && loss_out && B > 0, LAFS_ERR_ARG, "lafs_head_loss: bad argument");
   head_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(row_stats, label_a, label_b, lam, B, row_lse2, loss_out);
   return check_launch("lafs_head_loss");
@@ -467,6 +472,7 @@ extern "C" int lafs_head_grad_logits(const void* e_hat, const void* w_hat, const
                                      float lam, int B, int C_local, int D, int class_lo, float s, float m, int kind,
                                      const float* row_lse2, const float* grad_out, float gscale, void* grad_bf16,
                                      long long ldg, lafs_stream_t stream) {
+  if (int brc = lafs::bind_device_of(e_hat)) return brc;
   HeadParams p; HeadLaunch hl; CUtensorMap te, tw;
   int rc = head_common(e_hat, w_hat, label_a, label_b, lam, B, C_local, D, class_lo, s, m, kind, &p, &hl, &te, &tw, "lafs_head_grad_logits");
   if (rc) return rc;

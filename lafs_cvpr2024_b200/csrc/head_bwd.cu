@@ -269,6 +269,7 @@ extern "C" size_t lafs_head_bwd_workspace_bytes(int B, int C_local, int D) {
  * splits into grad_e_hat [B,D] fp32 (no Jacobian: sharded heads all-reduce it first). */
 extern "C" int lafs_head_bwd_embed(const void* grad_bf16, long long ldg, const void* w_hat, int B, int C_local, int D,
                                    float* grad_e_hat, void* workspace, size_t workspace_bytes, lafs_stream_t stream) {
+  if (int brc = lafs::bind_device_of(grad_bf16)) return brc;
   LAFS_REQUIRE(grad_bf16 && w_hat && workspace && grad_e_hat, LAFS_ERR_ARG, "lafs_head_bwd_embed: null pointer");
   LAFS_REQUIRE(B > 0 && C_local > 0 && D > 0 && D % 64 == 0 && D <= 768, LAFS_ERR_ARG, "lafs_head_bwd_embed: B=%d C=%d D=%d", B, C_local, D);
   LAFS_REQUIRE(ldg % 8 == 0 && ldg >= C_local, LAFS_ERR_ARG, "lafs_head_bwd_embed: ldg=%lld must be a multiple of 8 and >= C_local", ldg);
@@ -299,6 +300,7 @@ extern "C" int lafs_head_bwd_embed(const void* grad_bf16, long long ldg, const v
 extern "C" int lafs_head_bwd_weight(const void* grad_bf16, long long ldg, const void* e_hat, const void* w_hat,
                                     const float* inv_norm_w, int B, int C_local, int D, float* grad_w,
                                     lafs_stream_t stream) {
+  if (int brc = lafs::bind_device_of(grad_bf16)) return brc;
   LAFS_REQUIRE(grad_bf16 && e_hat && w_hat && inv_norm_w && grad_w, LAFS_ERR_ARG, "lafs_head_bwd_weight: null pointer");
   LAFS_REQUIRE(B > 0 && C_local > 0 && D > 0 && D % 64 == 0 && D <= 768, LAFS_ERR_ARG, "lafs_head_bwd_weight: B=%d C=%d D=%d", B, C_local, D);
   LAFS_REQUIRE(ldg % 8 == 0 && ldg >= C_local, LAFS_ERR_ARG, "lafs_head_bwd_weight: ldg=%lld must be a multiple of 8 and >= C_local", ldg);
@@ -322,6 +324,7 @@ extern "C" int lafs_head_bwd_weight(const void* grad_bf16, long long ldg, const 
 /* out[r,:] = (g[r,:] - x_hat[r,:] <x_hat[r,:], g[r,:]>) * inv_norm[r]   (F.normalize backward); out may alias g */
 extern "C" int lafs_normalize_bwd(const float* g, const void* x_hat_bf16, const float* inv_norm, int R, int D, float* out,
                                   lafs_stream_t stream) {
+  if (int brc = lafs::bind_device_of(g)) return brc;
   LAFS_REQUIRE(g && x_hat_bf16 && inv_norm && out && R >= 0 && D > 0 && D <= 768, LAFS_ERR_ARG, "lafs_normalize_bwd: bad argument");
   if (R == 0) return LAFS_OK;
   normalize_bwd_kernel<<<(R + 7) / 8, 256, 0, (cudaStream_t)stream>>>(g, 1, 0, (const __nv_bfloat16*)x_hat_bf16, inv_norm, R, D, out);

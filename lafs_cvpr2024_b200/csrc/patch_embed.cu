@@ -304,6 +304,7 @@ using namespace lafs;
 
 extern "C" int lafs_embed_weight_prep(const float* weight, const float* bias, int dim, void* out_bf16, float* bias_out,
                                       lafs_stream_t stream) {
+  if (int brc = lafs::bind_device_of(weight)) return brc;
   LAFS_REQUIRE(weight && out_bf16 && dim > 0, LAFS_ERR_ARG, "lafs_embed_weight_prep: bad argument");
   const int total = dim * pe::kFeat;
   embed_weight_prep_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(weight, bias, dim, (__nv_bfloat16*)out_bf16, bias_out);
@@ -313,6 +314,7 @@ extern "C" int lafs_embed_weight_prep(const float* weight, const float* bias, in
 extern "C" int lafs_gather_embed_fwd(const float* imgs, const float* theta, const void* w_perm_bf16, const float* bias,
                                      void* out0, void* out1, int out_dtype, int Bv, int H, int W, int n, int dim,
                                      int n_models, lafs_stream_t stream) {
+  if (int brc = lafs::bind_device_of(imgs)) return brc;
   void* out0_bf16 = out0; void* out1_bf16 = out1;
   if (Bv == 0) return LAFS_OK;
   LAFS_REQUIRE(imgs && theta && w_perm_bf16 && bias && out0_bf16, LAFS_ERR_ARG, "lafs_gather_embed_fwd: null pointer");
