@@ -286,12 +286,13 @@ extern "C" int lafs_head_bwd_embed(const void* grad_bf16, long long ldg, const v
   p.m_tiles = (B + 127) / 128; p.n_tiles = (D + 255) / 256; p.splits = splits;
   p.kblocks_total = (C_local + 63) / 64;
   p.kblocks_per_split = (p.kblocks_total + splits - 1) / splits;
+  p.splits = (p.kblocks_total + p.kblocks_per_split - 1) / p.kblocks_per_split;   // no empty K ranges
   p.out = (float*)workspace; p.ldo = D; p.split_stride = (long long)B * D;
   cudaStream_t st = (cudaStream_t)stream;
   rc = launch_gemm<false>(ta, tb, p, st);
   if (rc) return rc;
   const long long n = (long long)B * D;
-  split_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const float*)workspace, splits, n, n, grad_e_hat);
+  split_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const float*)workspace, p.splits, n, n, grad_e_hat);
   return check_launch("lafs_head_bwd_embed");
 }
 

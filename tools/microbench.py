@@ -108,8 +108,15 @@ def main():
             prep = lambda: _lib.call("lafs_normalize_rows", h.weight.data_ptr(), 0, C, D, w_hat.data_ptr(), None, _lib.stream())
             mp, bp = timeit(prep)
             fl = 2.0 * B * C * D
+            xg = x.clone().requires_grad_(True)
+            def fb():
+                xg.grad = None; h.weight.grad = None
+                h.forward_loss(xg, lab).backward()
+            mfb, _ = timeit(fb, warmup=3, iters=10)
             res[f"head_fwd_B{B}_C{C}_D{D}"] = {"ms": mf, "TFLOPs": fl / mf / 1e9, "frac_tc": fl / mf / 1e9 / tc,
-                                               "w_prep_ms": mp, "w_prep_GBps": C * D * 6 / mp / 1e6}
+                                               "w_prep_ms": mp, "w_prep_GBps": C * D * 6 / mp / 1e6,
+                                               "fwd_bwd_step_ms": mfb, "fwd_bwd_TFLOPs_6BCD": 3 * fl / mfb / 1e9,
+                                               "fwd_bwd_faces_per_s": B / mfb * 1e3}
             del h, w_hat
     print(json.dumps(res, indent=1))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

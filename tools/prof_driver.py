@@ -37,6 +37,14 @@ elif mode == "head":
     lab = torch.randint(0, C, (B,), device="cuda")
     for _ in range(reps):
         h.forward_loss(x, lab)
+elif mode == "head_bwd":
+    B, C, D = 512, 93431, 512
+    h = P.CosFace(D, C, None).cuda()
+    x = torch.randn(B, D, device="cuda").requires_grad_(True)
+    lab = torch.randint(0, C, (B,), device="cuda")
+    for _ in range(reps):
+        x.grad = None; h.weight.grad = None
+        h.forward_loss(x, lab).backward()
 elif mode == "ema":
     q = [torch.randn(30000, 768, device="cuda"), torch.randn(65536, 256, device="cuda")] + [torch.randn(2112, 768, device="cuda") for _ in range(12)]
     k = [a.clone() for a in q]
