@@ -136,6 +136,7 @@ def run_ours(args):
     import lafs_cvpr2024_b200 as P
     from lafs_cvpr2024_b200 import _lib
     from lafs_cvpr2024_b200.ssl_step import SSLHotPath
+    torch.backends.cuda.matmul.allow_tf32 = False
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -225,6 +226,11 @@ def run_ours(args):
         e2e_step(i, None)
     ms_e2e, _ = timed(e2e_step, args.steps)
 
+    # ---- secondary: class-sharded margin head (BASELINE configs[2], configs[3]) -----------------
+    del st, path, dev_in, stage
+    torch.cuda.empty_cache()
+    head = bench_head(P, world, rank, dev, dist, args)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -270,11 +276,60 @@ def run_ours(args):
                      "frac": kernels[dom]["frac_hbm"], "traffic": None, "peak_source": pk["src"]},
         "kernels": kernels,
     }
+    for name, h in head.items():
+        h["frac_tc"] = round(h["TFLOPs_6BCD"] / pk["tc"], 4)
+    line["head"] = head
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(sample_faces=args.cpu_faces)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_head(P, world, rank, dev, dist, args):
+    """Finetune margin head, classes sharded over the N ranks with torch.chunk's rule; every rank
+    sees the global batch (post all-gather embeddings).  One step = weight/embedding
+    normalisation + fused GEMM/softmax-CE forward + statistics exchange + recompute-G backward
+    (dE all-reduced over shards, dW local).  Strong scaling in N (fixed global batch)."""
+    out = {}
+    cfgs = [("cosface_ms1mv3", P.CosFace, 512, 93431, 512), ("arcface_webface4m", P.ArcFace, 1024, 205990, 512)]
+    for name, cls, B, C, D in cfgs:
+        torch.manual_seed(7)
+        h = cls(D, C, None, shard=(rank, world) if world > 1 else None).to(dev)
+        x = torch.randn(B, D, device=dev, requires_grad=True)
+        lab = torch.randint(0, C, (B,), device=dev)
+
+        def step():
+            x.grad = None
+            h.weight.grad = None
+            loss = h.forward_loss(x, lab)
+            loss.backward()
+            return loss
+
+        for _ in range(3):
+            step()
+        iters = max(5, min(args.steps, 20))
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            step()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / iters], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        out[name] = {"B_global": B, "classes": C, "D": D, "shards": world, "ms_fwd_bwd": round(ms, 4),
+                     "faces_per_s": round(B / ms * 1e3, 1), "TFLOPs_6BCD": round(6.0 * B * C * D / ms / 1e9 / world, 1),
+                     "note": "TFLOPs per GPU on the 6*B*C*D/R count; the step also recomputes the logits once (8*B*C*D issued)"}
+        del h, x
+        torch.cuda.empty_cache()
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -355,7 +410,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-faces", type=int, default=256, help="faces in the bounded CPU sample (256 = the full step)")

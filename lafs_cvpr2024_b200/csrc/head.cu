@@ -210,20 +210,44 @@ head_gemm_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
         } else if (MODE == HEAD_LOGITS) {
           if (row_ok) {
             float* dst = p.logits + (long long)b * p.ldc + cbase;
+            if (!tail && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (cbase + j < p.C_local) dst[j] = z[j];
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(dst + j) = make_float4(z[j], z[j + 1], z[j + 2], z[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (cbase + j < p.C_local) dst[j] = z[j];
+            }
           }
-        } else {  // HEAD_GRAD: (softmax - target) * gscale, bf16
+        } else {  // HEAD_GRAD: (softmax - target) * dz/dcos * gscale, bf16; 64 contiguous bytes per row
           if (row_ok) {
-            __nv_bfloat16* dst = p.grad + (long long)b * p.ldg + cbase;
+            float gv[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int c = cbase + j;
-              float g = ex2(fmaf(z[j], k2, -lse2));
-              if (has_a && c == (int)la) g = (g - ta) * margin_dcos(__uint_as_float(raw[j]), p);
-              if (has_b && c == (int)lb) g -= tb;
-              if (c < p.C_local) dst[j] = __float2bfloat16_rn(g * gscale);
+            for (int j = 0; j < 32; ++j) gv[j] = ex2(fmaf(z[j], k2, -lse2));
+            if (has_a || has_b) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int c = cbase + j;
+                if (has_a && c == (int)la) gv[j] = (gv[j] - ta) * margin_dcos(__uint_as_float(raw[j]), p);
+                if (has_b && c == (int)lb) gv[j] -= tb;
+              }
+            }
+            __nv_bfloat16* dst = p.grad + (long long)b * p.ldg + cbase;   // ldg % 8 == 0: 16-byte aligned
+            if (!tail) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 pk;
+                pk.x = Half2Ops<__nv_bfloat16>::pack(gv[j] * gscale, gv[j + 1] * gscale);
+                pk.y = Half2Ops<__nv_bfloat16>::pack(gv[j + 2] * gscale, gv[j + 3] * gscale);
+                pk.z = Half2Ops<__nv_bfloat16>::pack(gv[j + 4] * gscale, gv[j + 5] * gscale);
+                pk.w = Half2Ops<__nv_bfloat16>::pack(gv[j + 6] * gscale, gv[j + 7] * gscale);
+                *reinterpret_cast<uint4*>(dst + j) = pk;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (cbase + j < p.C_local) dst[j] = __float2bfloat16_rn(gv[j] * gscale);
             }
           }
         }

@@ -182,33 +182,58 @@ gemm_bwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   }
 }
 
-// out[r, :] = (sum_s part[s][r, :] - x_hat[r, :] * <x_hat[r, :], sum_s part[s][r, :]>) * inv_norm[r]
-// one warp per row; x_hat bf16 [R, D].  part may alias out when splits == 1.
+// out[r, :] = (g[r, :] - x_hat[r, :] * <x_hat[r, :], g[r, :]>) * inv_norm[r]   (F.normalize backward)
+// one warp per row, 128-bit accesses, all loads of a row issued before the reduction.
+// D % 64 == 0, D <= 768: a lane holds up to three (float4 x 2) groups.  out may alias g.
 __global__ void __launch_bounds__(256)
-normalize_bwd_kernel(const float* __restrict__ part, int splits, long long split_stride, const __nv_bfloat16* __restrict__ x_hat,
+normalize_bwd_kernel(const float* __restrict__ g, const __nv_bfloat16* __restrict__ x_hat,
                      const float* __restrict__ inv_norm, int R, int D, float* __restrict__ out) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + warp;
   if (r >= R) return;
-  float dot = 0.f;
-  // D <= 768: each lane holds up to 24 values
-  float g[24];
+  const float* grow = g + (size_t)r * D;
+  const __nv_bfloat16* xrow = x_hat + (size_t)r * D;
+  float4 gv[3][2];
+  uint4 xv[3];
+  // group q covers columns q*256 + lane*8 .. +7
 #pragma unroll
-  for (int i = 0; i < 24; ++i) {
-    const int c = lane + i * 32;
-    float acc = 0.f;
+  for (int q = 0; q < 3; ++q) {
+    const int c = q * 256 + lane * 8;
     if (c < D) {
-      for (int s = 0; s < splits; ++s) acc += part[(size_t)s * split_stride + (size_t)r * D + c];
-      dot = fmaf(acc, __bfloat162float(x_hat[(size_t)r * D + c]), dot);
+      gv[q][0] = *reinterpret_cast<const float4*>(grow + c);
+      gv[q][1] = *reinterpret_cast<const float4*>(grow + c + 4);
+      xv[q] = *reinterpret_cast<const uint4*>(xrow + c);
     }
-    g[i] = acc;
+  }
+  float dot = 0.f;
+  float xf[3][8];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const int c = q * 256 + lane * 8;
+    if (c < D) {
+      xf[q][0] = Half2Ops<__nv_bfloat16>::lo(xv[q].x); xf[q][1] = Half2Ops<__nv_bfloat16>::hi(xv[q].x);
+      xf[q][2] = Half2Ops<__nv_bfloat16>::lo(xv[q].y); xf[q][3] = Half2Ops<__nv_bfloat16>::hi(xv[q].y);
+      xf[q][4] = Half2Ops<__nv_bfloat16>::lo(xv[q].z); xf[q][5] = Half2Ops<__nv_bfloat16>::hi(xv[q].z);
+      xf[q][6] = Half2Ops<__nv_bfloat16>::lo(xv[q].w); xf[q][7] = Half2Ops<__nv_bfloat16>::hi(xv[q].w);
+      dot += gv[q][0].x * xf[q][0] + gv[q][0].y * xf[q][1] + gv[q][0].z * xf[q][2] + gv[q][0].w * xf[q][3] +
+             gv[q][1].x * xf[q][4] + gv[q][1].y * xf[q][5] + gv[q][1].z * xf[q][6] + gv[q][1].w * xf[q][7];
+    }
   }
   dot = warp_sum(dot);
   const float inv = inv_norm[r];
+  float* orow = out + (size_t)r * D;
 #pragma unroll
-  for (int i = 0; i < 24; ++i) {
-    const int c = lane + i * 32;
-    if (c < D) out[(size_t)r * D + c] = (g[i] - __bfloat162float(x_hat[(size_t)r * D + c]) * dot) * inv;
+  for (int q = 0; q < 3; ++q) {
+    const int c = q * 256 + lane * 8;
+    if (c < D) {
+      float4 o0, o1;
+      o0.x = (gv[q][0].x - xf[q][0] * dot) * inv; o0.y = (gv[q][0].y - xf[q][1] * dot) * inv;
+      o0.z = (gv[q][0].z - xf[q][2] * dot) * inv; o0.w = (gv[q][0].w - xf[q][3] * dot) * inv;
+      o1.x = (gv[q][1].x - xf[q][4] * dot) * inv; o1.y = (gv[q][1].y - xf[q][5] * dot) * inv;
+      o1.z = (gv[q][1].z - xf[q][6] * dot) * inv; o1.w = (gv[q][1].w - xf[q][7] * dot) * inv;
+      *reinterpret_cast<float4*>(orow + c) = o0;
+      *reinterpret_cast<float4*>(orow + c + 4) = o1;
+    }
   }
 }
 
@@ -318,7 +343,7 @@ extern "C" int lafs_head_bwd_weight(const void* grad_bf16, long long ldg, const 
   cudaStream_t st = (cudaStream_t)stream;
   rc = launch_gemm<true>(ta, tb, p, st);
   if (rc) return rc;
-  normalize_bwd_kernel<<<(C_local + 7) / 8, 256, 0, st>>>(grad_w, 1, 0, (const __nv_bfloat16*)w_hat, inv_norm_w, C_local, D, grad_w);
+  normalize_bwd_kernel<<<(C_local + 7) / 8, 256, 0, st>>>(grad_w, (const __nv_bfloat16*)w_hat, inv_norm_w, C_local, D, grad_w);
   return check_launch("lafs_head_bwd_weight");
 }
 
@@ -328,6 +353,7 @@ extern "C" int lafs_normalize_bwd(const float* g, const void* x_hat_bf16, const 
   if (int brc = lafs::bind_device_of(g)) return brc;
   LAFS_REQUIRE(g && x_hat_bf16 && inv_norm && out && R >= 0 && D > 0 && D <= 768, LAFS_ERR_ARG, "lafs_normalize_bwd: bad argument");
   if (R == 0) return LAFS_OK;
-  normalize_bwd_kernel<<<(R + 7) / 8, 256, 0, (cudaStream_t)stream>>>(g, 1, 0, (const __nv_bfloat16*)x_hat_bf16, inv_norm, R, D, out);
+  LAFS_REQUIRE(D % 8 == 0, LAFS_ERR_ARG, "lafs_normalize_bwd: D=%d must be a multiple of 8", D);
+  normalize_bwd_kernel<<<(R + 7) / 8, 256, 0, (cudaStream_t)stream>>>(g, (const __nv_bfloat16*)x_hat_bf16, inv_norm, R, D, out);
   return check_launch("lafs_normalize_bwd");
 }

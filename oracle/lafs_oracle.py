@@ -273,3 +273,17 @@ def label_to_shard(label, num_classes, world):
     step = -(-num_classes // world)
     label = np.asarray(label, dtype=np.int64)
     return label // step, label % step
+
+
+def softmax_stats(logits):
+    """Per-row (max, sum-exp) of a logit block -- the record a class shard contributes."""
+    m = logits.max(dim=1)[0]
+    return m, torch.exp(logits - m[:, None]).sum(1)
+
+
+def merge_softmax_stats(ms, ls):
+    """Merges per-shard (max, sum-exp) records into the full-row log-sum-exp: the exchange the
+    class-parallel head performs instead of moving logits."""
+    m = torch.stack(ms).max(0)[0]
+    l = sum(li * torch.exp(mi - m) for mi, li in zip(ms, ls))
+    return m + torch.log(l)

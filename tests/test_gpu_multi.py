@@ -1,0 +1,64 @@
+"""Multi-GPU (>= 2 devices, NCCL): class-sharded margin head and the DINO centre all-reduce
+against the single-GPU result.  Skipped on a 1-GPU box; run with `gpurun --gpus 2`."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import lafs_cvpr2024_b200 as P
+        torch.manual_seed(0)
+        B, C, D = 192, 10007, 512
+        x, w = torch.randn(B, D), torch.randn(C, D) * 0.05
+        lab = torch.randint(0, C, (B,))
+        lo, hi = P.shard_bounds(C, world)[rank]
+        h = P.CosFace(D, C, None, shard=(rank, world)).cuda()
+        with torch.no_grad():
+            h.weight.copy_(w[lo:hi])
+        xg = x.cuda().requires_grad_(True)
+        loss = h.forward_loss(xg, lab.cuda())
+        loss.backward()
+        # single-GPU unsharded result on the same device
+        full = P.CosFace(D, C, None).cuda()
+        with torch.no_grad():
+            full.weight.copy_(w)
+        xf = x.cuda().requires_grad_(True)
+        lf = full.forward_loss(xf, lab.cuda())
+        lf.backward()
+        assert abs(float(loss) - float(lf)) <= 1e-5 * abs(float(lf)), (float(loss), float(lf))
+        assert (xg.grad - xf.grad).abs().max() <= 2e-3 * xf.grad.abs().max()
+        assert (h.weight.grad - full.weight.grad[lo:hi]).abs().max() <= 2e-3 * full.weight.grad.abs().max()
+        # DINO centre: every rank ends with the same centre = EMA of the global teacher mean
+        K = 4096
+        g = torch.Generator().manual_seed(10 + rank)
+        t = torch.randn(8, K, generator=g).cuda()
+        s = torch.randn(16, K, generator=g).cuda()
+        crit = P.DINOLoss(K, 4, 0.04, 0.07, 30, 41).cuda()
+        crit(s, t, 0)
+        allt = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        ref = torch.cat(allt).sum(0, keepdim=True) / (8 * world) * (1 - 0.9)
+        torch.testing.assert_close(crit.center, ref, rtol=1e-5, atol=1e-6)
+        ret[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_sharded_head_and_center_two_gpus():
+    world = 2
+    port = 29800 + (os.getpid() % 100)
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+        assert dict(ret) == {0: "ok", 1: "ok"}
