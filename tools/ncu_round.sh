@@ -1,0 +1,22 @@
+#!/bin/bash
+# Profiling pass for a round (run under gpurun, ONE GPU).  Writes everything to gpurun_out/.
+#   1. launch list of the bench command (per-launch device time, cold-cache & serialised)
+#   2. one `--set full` capture of each hot kernel
+set -u
+mkdir -p gpurun_out
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_bench.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/launches_bench.log 2>&1
+cap() {  # name regex driver-mode skip
+  ncu --set full --clock-control none --import-source on -k regex:$2 -s $4 -c 1 -o gpurun_out/$1 \
+      python tools/prof_driver.py $3 3 > gpurun_out/$1.log 2>&1
+}
+cap ema ema_multi_kernel ema 1
+cap dino_fwd dino_fwd_partial dino 1
+cap dino_bwd dino_bwd_kernel dino 1
+cap pe_global gather_embed_kernel pe_global 1
+cap pe_local gather_embed_kernel pe_local 1
+cap head_fwd "head_gemm_kernel<256,.0>" head_bwd 1
+cap head_grad "head_gemm_kernel<256,.2>" head_bwd 1
+cap head_dw "gemm_bwd_kernel<1>" head_bwd 1
+cap head_de "gemm_bwd_kernel<0>" head_bwd 1
+ls -la gpurun_out/*.ncu-rep

@@ -1,0 +1,48 @@
+"""Condenses gpurun_out/*.ncu-rep into profiles/<round>_ncu_summary.csv (run in the build container)."""
+import csv
+import glob
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+        "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_bytes.sum", "sm__cycles_elapsed.max"]
+
+
+def main(tag):
+    out_rows = []
+    for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "*.ncu-rep"))):
+        r = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True)
+        rows = list(csv.reader(r.stdout.splitlines()))
+        if len(rows) < 3:
+            continue
+        hdr, units = rows[0], rows[1]
+        for vals in rows[2:]:
+            d = dict(zip(hdr, vals))
+            u = dict(zip(hdr, units))
+            rec = {"report": os.path.basename(rep), "kernel": d.get("Kernel Name", "")[:80]}
+            for w in WANT:
+                if w in d:
+                    rec[w + (" [" + u[w] + "]" if u.get(w) else "")] = d[w]
+            out_rows.append(rec)
+    keys = []
+    for r in out_rows:
+        for k in r:
+            if k not in keys:
+                keys.append(k)
+    path = os.path.join(ROOT, "profiles", f"{tag}_ncu_summary.csv")
+    with open(path, "w", newline="") as f:
+        w = csv.DictWriter(f, fieldnames=keys)
+        w.writeheader()
+        w.writerows(out_rows)
+    print(path, len(out_rows), "kernels")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1] if len(sys.argv) > 1 else "r01")
