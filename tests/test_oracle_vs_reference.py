@@ -1,0 +1,63 @@
+"""Build container only (needs /root/reference): the oracle restatement against the LIVE
+reference on fresh random inputs -- complements the committed golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lafs_oracle as O
+
+pytestmark = pytest.mark.reference
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from oracle import ref_harness
+    return ref_harness.load()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_extract_patches_bit_exact(ref, seed):
+    g = torch.Generator().manual_seed(seed)
+    B = 3
+    imgs = torch.randn(B, 3, 112, 112, generator=g)
+    for n in (196, 36, 49):
+        th = torch.rand(B, n, 2, generator=g) * 111 + torch.randn(B, n, 2, generator=g) * 5
+        out = ref.VF.extract_patches_pytorch_gridsample(imgs, th, torch.tensor([8, 8]), n)
+        assert torch.equal(out, O.extract_patches(imgs, th, n))
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_dino_loss_matches(ref, seed):
+    g = torch.Generator().manual_seed(seed)
+    B, K, nc = 5, 2048, 10
+    dl = ref.L.DINOLoss(K, nc, 0.04, 0.07, 30, 41)
+    dl.center = torch.randn(1, K, generator=g) * 0.2
+    c0 = dl.center.clone()
+    s = torch.randn(nc * B, K, generator=g) * 2
+    t = torch.randn(2 * B, K, generator=g) * 2
+    for epoch in (0, 12, 40):
+        dl.center = c0.clone()
+        loss = dl(s, t, epoch)
+        temp = float(O.teacher_temp_schedule(0.04, 0.07, 30, 41)[epoch])
+        assert torch.equal(loss, O.dino_loss(s, t, c0, nc, temp))
+        assert torch.equal(dl.center, O.dino_center_update(c0, t))
+
+
+def test_cosface_and_mixup_match(ref):
+    import contextlib
+    import io
+    torch.manual_seed(3)
+    B, D, C = 16, 48, 333
+    with contextlib.redirect_stdout(io.StringIO()):
+        head = ref.VF.CosFace(D, C, None)
+    x = torch.randn(B, D)
+    lab = torch.randint(0, C, (B,))
+    assert torch.equal(head(x, lab), O.cosface_logits(x, head.weight.detach(), lab))
+    soft = ref.mixup.mixup_target(lab, C, lam=0.7, smoothing=0.0, device="cpu")
+    assert torch.equal(soft, O.mixup_target(lab, C, 0.7))
+    assert torch.equal(head(x, soft), O.cosface_logits(x, head.weight.detach(), soft))
+
+
+def test_cosine_scheduler_matches(ref):
+    a = ref.dutils.cosine_scheduler(0.996, 1, 41, 123)
+    assert np.array_equal(a, O.cosine_scheduler(0.996, 1, 41, 123))
