@@ -36,6 +36,7 @@ typedef void* lafs_stream_t; /* cudaStream_t */
 #define LAFS_F32 0
 #define LAFS_BF16 1
 #define LAFS_F16 2
+#define LAFS_U8 3 /* images only: lafs_gather_embed_fwd */
 
 LAFS_API int lafs_version(void);
 LAFS_API const char* lafs_last_error_string(void);
@@ -195,12 +196,16 @@ LAFS_API int lafs_normalize_bwd(const float* g, const void* x_hat_bf16, const fl
  * lafs_gather_embed_fwd: out_m [Bv, n, dim] (out_dtype bf16, or fp32 for verification) =
  *      tokens(imgs, theta) @ W_m^T + bias_m for m < n_models; bias [n_models*dim] fp32;
  *      n <= 208, dim % 128 == 0.  Tokens and weights are rounded to bf16, accumulation is fp32.
+ *      imgs is fp32 (in_dtype LAFS_F32: the reference's normalised tensors) or uint8 (LAFS_U8:
+ *      the decoded pixels; the reference's ToTensor + Normalize (lafs_train.py:800-803) is applied
+ *      in the kernel as in_scale*u8 + in_shift, e.g. 2/255 and -1, and the zero padding of
+ *      grid_sample stays a zero in normalised space).
  */
 LAFS_API int lafs_embed_weight_prep(const float* weight, const float* bias, int dim, void* out_bf16, float* bias_out,
                                     lafs_stream_t stream);
-LAFS_API int lafs_gather_embed_fwd(const float* imgs, const float* theta, const void* w_perm_bf16, const float* bias,
-                                   void* out0, void* out1, int out_dtype, int Bv, int H, int W, int n, int dim,
-                                   int n_models, lafs_stream_t stream);
+LAFS_API int lafs_gather_embed_fwd(const void* imgs, int in_dtype, float in_scale, float in_shift, const float* theta,
+                                   const void* w_perm_bf16, const float* bias, void* out0, void* out1, int out_dtype,
+                                   int Bv, int H, int W, int n, int dim, int n_models, lafs_stream_t stream);
 
 #ifdef __cplusplus
 }

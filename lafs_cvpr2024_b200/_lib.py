@@ -12,7 +12,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblafs_b200.so")
 
-F32, BF16, F16 = 0, 1, 2
+F32, BF16, F16, U8 = 0, 1, 2, 3
 LAYOUT_MOSAIC, LAYOUT_TOKENS = 0, 1
 COORD_DIV, COORD_RECIP = 0, 1
 EMA_CHUNK = 16384
@@ -35,7 +35,7 @@ SIGNATURES = {
     "lafs_gather_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "lafs_gather_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "lafs_embed_weight_prep": (_i, [_p, _p, _i, _p, _p, _p]),
-    "lafs_gather_embed_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "lafs_gather_embed_fwd": (_i, [_p, _i, _f, _f, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "lafs_normalize_rows": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "lafs_head_workspace_bytes": (_z, [_i, _i, _i]),
     "lafs_head_fwd": (_i, [_p, _p, _p, _p, _f, _i, _i, _i, _i, _f, _f, _i, _p, _p, _z, _p]),

@@ -36,7 +36,7 @@ enum : int {
   LAFS_ERR_WORKSPACE = -3  // workspace too small
 };
 
-enum : int { LAFS_F32 = 0, LAFS_BF16 = 1, LAFS_F16 = 2 };
+enum : int { LAFS_F32 = 0, LAFS_BF16 = 1, LAFS_F16 = 2, LAFS_U8 = 3 };
 
 // ---- device helpers ------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

@@ -6,13 +6,21 @@
 // embedded tokens of up to two models (student + teacher) that share the gathered patches.
 //
 // One persistent CTA per SM walks over faces.  Per face:
-//   plane producer : cp.async.bulk of the three 112x112 fp32 channel planes into a 2-slot ring
+//   plane producer : cp.async.bulk of the three 112x112 channel planes into a 2-slot ring
 //   gather warps   : bilinear 8x8 patches from the staged plane -> bf16 token tile in the UMMA
 //                    K-major/128B-swizzle layout (tokens x 192), K order = c*64 + j*8 + i
 //   W producer     : TMA of [128 x 64] bf16 weight chunks (weights pre-permuted to that K order)
 //   UMMA issuer    : D[128 dims x N tokens] += Wchunk[128 x 192] * Tok[N x 192]^T   (tokens on the
 //                    N side: N = 208 for 196 landmarks, 48 for 36 -- no 128-row padding waste)
 //   epilogue warps : TMEM -> +bias -> bf16 -> out[model][face, token, dim]
+//
+// Two input formats:
+//   fp32 planes (the reference's tensors).  100 KB of planes leave room for ONE token tile, so
+//     the gather of face f+1 waits for the UMMAs of face f.
+//   uint8 planes (what the data loader decodes; ToTensor + Normalize = a*u8 + b is applied to the
+//     interpolated value, zero padding becomes the raw value -b/a).  25 KB of planes leave room
+//     for TWO token tiles: gather(f+1) overlaps UMMA/epilogue(f), and HBM/PCIe image bytes drop 4x.
+//
 // The bf16 path does not need the reference's fp32 coordinate round trip: sample
 // positions are theta + (idx - 4.5) directly; the error (<1e-5 px) is far below bf16 rounding.
 // The stand-alone fp32 gather (gather.cu) keeps the exact sequence for the 1e-5 parity clause.
@@ -24,13 +32,13 @@ using namespace umma;
 
 namespace pe {
 constexpr int kH = 112, kW = 112, kC = 3;
-constexpr int kPlaneBytes = kH * kW * 4;           // 50,176
 constexpr int kFeat = 192;                         // 3 * 8 * 8
 constexpr int kMaxTok = 208;                       // largest UMMA N (196 landmarks -> N_pad 208)
 constexpr int kTokRows = 200;                      // token rows owned per chunk (25 x 8); a UMMA with
                                                    // N_pad = 208 also reads 8 rows of the NEXT region:
                                                    // harmless garbage columns that are never stored
 constexpr int kTokChunkBytes = kTokRows * 128;     // one 64-feature chunk: 25,600 B (25 x 1024)
+constexpr int kTokTileBytes = 3 * kTokChunkBytes;  // 76,800 B
 constexpr int kWStageBytes = 128 * 128;            // [128 dims x 64 k] bf16
 constexpr int kWStages = 3;
 constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quarter
@@ -40,21 +48,30 @@ constexpr int kGatherThreads = kGatherWarps * 32;
 constexpr int kWarpPlane = 0, kWarpW = 1, kWarpMma = 2, kWarpEpi0 = 4, kWarpGather0 = kWarpEpi0 + kEpiWarps;
 constexpr int kThreads = (kWarpGather0 + kGatherWarps) * 32;   // 20 warps
 
-constexpr int kOffPlanes = 0;
-constexpr int kOffTok = 2 * kPlaneBytes;                       // 100,352 (1024-aligned: 98 x 1024)
-constexpr int kOffW = kOffTok + 3 * kTokChunkBytes;            // 180,224
-constexpr int kOffBar = kOffW + kWStages * kWStageBytes;       // 212,992
-constexpr int kSmemBytes = kOffBar + 256 + 1024;               // + barriers + alignment slack
-static_assert(kOffTok % 1024 == 0 && kOffW % 1024 == 0, "UMMA tiles need 1024-byte alignment");
+template <typename InT>
+struct Layout {
+  static constexpr int kPlaneBytes = kH * kW * (int)sizeof(InT);          // 50,176 (fp32) / 12,544 (u8)
+  static constexpr int kPlaneSlot = (kPlaneBytes + 1023) / 1024 * 1024;   // keeps later regions 1024-aligned
+  static constexpr int kTokBufs = sizeof(InT) == 1 ? 2 : 1;
+  static constexpr int kOffPlanes = 0;
+  static constexpr int kOffTok = 2 * kPlaneSlot;
+  static constexpr int kOffW = kOffTok + kTokBufs * kTokTileBytes;
+  static constexpr int kOffBar = kOffW + kWStages * kWStageBytes;
+  static constexpr int kSmemBytes = kOffBar + 256 + 1024;                 // + barriers + alignment slack
+  static_assert(kOffTok % 1024 == 0 && kOffW % 1024 == 0, "UMMA tiles need 1024-byte alignment");
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+};
 }  // namespace pe
 
 struct EmbedParams {
-  const float* imgs;        // [Bv, 3, 112, 112]
+  const void* imgs;         // [Bv, 3, 112, 112] fp32 or uint8
   const float* theta;       // [Bv, n, 2]
   const float* bias;        // [n_models * dim]
   void* out[2];             // per model: [Bv, n, dim] bf16 or fp32
   int Bv, n, n_pad, dim, n_models;
   int mchunks;              // n_models * dim / 128
+  float in_scale, in_shift; // normalised pixel = in_scale * raw + in_shift   (1, 0 for fp32 input)
+  float pad_raw;            // raw value of a zero-padded (out-of-image) pixel = -in_shift / in_scale
 };
 
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -66,34 +83,39 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
 __device__ __forceinline__ void store_out(float* p, float v) { *p = v; }
 __device__ __forceinline__ void store_out(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
+__device__ __forceinline__ float raw_pixel(const float* plane, int idx) { return plane[idx]; }
+__device__ __forceinline__ float raw_pixel(const uint8_t* plane, int idx) { return (float)plane[idx]; }
+
 // DIM > 0: compile-time embedding width (store offsets become immediates); DIM == 0: runtime p.dim
-template <typename OutT, int DIM>
+template <typename InT, typename OutT, int DIM>
 __global__ void __launch_bounds__(pe::kThreads, 1)
 gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParams p) {
   using namespace pe;
+  using L = Layout<InT>;
+  constexpr int NTB = L::kTokBufs;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* s_planes = smem + kOffPlanes;
-  uint8_t* s_tok = smem + kOffTok;
-  uint8_t* s_w = smem + kOffW;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint8_t* s_planes = smem + L::kOffPlanes;
+  uint8_t* s_tok = smem + L::kOffTok;
+  uint8_t* s_w = smem + L::kOffW;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
   uint64_t* plane_full = bars;            // 2
   uint64_t* plane_empty = bars + 2;       // 2
-  uint64_t* tok_full = bars + 4;          // 3
-  uint64_t* tok_empty = bars + 7;         // 1
-  uint64_t* w_full = bars + 8;            // kWStages (<= 4)
-  uint64_t* w_empty = bars + 12;          // kWStages
-  uint64_t* acc_full = bars + 16;         // 2
-  uint64_t* acc_empty = bars + 18;        // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* tok_full = bars + 4;          // NTB * 3
+  uint64_t* tok_empty = bars + 10;        // NTB
+  uint64_t* w_full = bars + 12;           // kWStages (<= 4)
+  uint64_t* w_empty = bars + 16;          // kWStages
+  uint64_t* acc_full = bars + 20;         // 2
+  uint64_t* acc_empty = bars + 22;        // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tmap_w);
     for (int i = 0; i < 2; ++i) { mbar_init(plane_full + i, 1); mbar_init(plane_empty + i, kGatherWarps); }
-    for (int i = 0; i < 3; ++i) mbar_init(tok_full + i, kGatherWarps);
-    mbar_init(tok_empty, 1);
+    for (int i = 0; i < NTB * 3; ++i) mbar_init(tok_full + i, kGatherWarps);
+    for (int i = 0; i < NTB; ++i) mbar_init(tok_empty + i, 1);
     for (int i = 0; i < kWStages; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, kEpiWarps); }
     fence_mbar_init();
@@ -109,14 +131,15 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
   if (warp == kWarpPlane) {
     // ===================== image plane producer =====================
     if (lane == 0) {
+      const InT* imgs = reinterpret_cast<const InT*>(p.imgs);
       uint32_t cnt = 0;
       for (int fi = 0; fi < nfaces_mine; ++fi) {
         const int f = blockIdx.x + fi * gridDim.x;
         for (int c = 0; c < kC; ++c, ++cnt) {
           const int slot = cnt & 1;
           mbar_wait(plane_empty + slot, ((cnt >> 1) & 1) ^ 1);
-          mbar_arrive_expect_tx(plane_full + slot, kPlaneBytes);
-          bulk_load(s_planes + slot * kPlaneBytes, p.imgs + ((size_t)f * kC + c) * (kH * kW), kPlaneBytes,
+          mbar_arrive_expect_tx(plane_full + slot, L::kPlaneBytes);
+          bulk_load(s_planes + slot * L::kPlaneSlot, imgs + ((size_t)f * kC + c) * (kH * kW), L::kPlaneBytes,
                     plane_full + slot);
         }
       }
@@ -140,18 +163,20 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
       const uint32_t idesc = make_idesc_bf16(128, p.n_pad);
       uint32_t wcnt = 0, acnt = 0;
       for (int fi = 0; fi < nfaces_mine; ++fi) {
+        const int tb = fi % NTB;
+        const uint32_t tuse = (uint32_t)(fi / NTB);
         for (int mc = 0; mc < p.mchunks; ++mc, ++acnt) {
           const int buf = acnt & 1;
           mbar_wait(acc_empty + buf, ((acnt >> 1) & 1) ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
           for (int c = 0; c < kC; ++c, ++wcnt) {
-            if (mc == 0) { mbar_wait(tok_full + c, fi & 1); }
+            if (mc == 0) { mbar_wait(tok_full + tb * 3 + c, tuse & 1); }
             const int st = wcnt % kWStages;
             mbar_wait(w_full + st, (wcnt / kWStages) & 1);
             tc_fence_after();
             const uint64_t da = make_desc_k_sw128(smem_u32(s_w + st * kWStageBytes));
-            const uint64_t db = make_desc_k_sw128(smem_u32(s_tok + c * kTokChunkBytes));
+            const uint64_t db = make_desc_k_sw128(smem_u32(s_tok + tb * kTokTileBytes + c * kTokChunkBytes));
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
               mma_f16_ss(d_tmem, desc_advance_k(da, kk * 16), desc_advance_k(db, kk * 16), idesc, (c | kk) != 0);
@@ -159,7 +184,7 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
           }
           mma_commit(acc_full + buf);
         }
-        mma_commit(tok_empty);   // all UMMAs reading this face's tokens have completed
+        mma_commit(tok_empty + tb);   // all UMMAs reading this face's token tile have completed
       }
     }
   } else if (warp >= kWarpEpi0 && warp < kWarpEpi0 + kEpiWarps) {
@@ -211,16 +236,19 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
   } else if (warp >= kWarpGather0) {
     // ===================== gather warps =====================
     const int gt = threadIdx.x - kWarpGather0 * 32;        // 0..255
+    const float a_in = p.in_scale, b_in = p.in_shift, pad = p.pad_raw;
     uint32_t pcnt = 0;
     for (int fi = 0; fi < nfaces_mine; ++fi) {
       const int f = blockIdx.x + fi * gridDim.x;
+      const int tb = fi % NTB;
+      const uint32_t tuse = (uint32_t)(fi / NTB);
       const float* th = p.theta + (size_t)f * p.n * 2;
-      mbar_wait(tok_empty, (fi & 1) ^ 1);                  // previous face's UMMAs are done with the tile
+      mbar_wait(tok_empty + tb, (tuse & 1) ^ 1);           // the UMMAs of the face that used this tile are done
       for (int c = 0; c < kC; ++c, ++pcnt) {
         const int slot = pcnt & 1;
         mbar_wait(plane_full + slot, (pcnt >> 1) & 1);
-        const float* plane = reinterpret_cast<const float*>(s_planes + slot * kPlaneBytes);
-        uint8_t* tok = s_tok + c * kTokChunkBytes;
+        const InT* plane = reinterpret_cast<const InT*>(s_planes + slot * L::kPlaneSlot);
+        uint8_t* tok = s_tok + tb * kTokTileBytes + c * kTokChunkBytes;
         // item = (token t, half h): output columns j = 4h..4h+3, all 8 i  -> four 16-byte stores
         for (int item = gt; item < 2 * p.n; item += kGatherThreads) {
           const int t = item >> 1, h = item & 1;
@@ -237,17 +265,17 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
             float px[9];
             const int y = y0 + r;
             if (inside) {
-              const float* rowp = plane + y * kW + x0;
+              const int base = y * kW + x0;
 #pragma unroll
-              for (int q = 0; q < 9; ++q) px[q] = rowp[q];
+              for (int q = 0; q < 9; ++q) px[q] = raw_pixel(plane, base + q);
             } else {
               const bool yok = (y >= 0) && (y < kH);
-              const float* rowp = plane + min(max(y, 0), kH - 1) * kW;
+              const int rowb = min(max(y, 0), kH - 1) * kW;
 #pragma unroll
               for (int q = 0; q < 9; ++q) {
                 const int x = x0 + q;
-                const float v = rowp[min(max(x, 0), kW - 1)];
-                px[q] = (yok && x >= 0 && x < kW) ? v : 0.f;
+                const float v = raw_pixel(plane, rowb + min(max(x, 0), kW - 1));
+                px[q] = (yok && x >= 0 && x < kW) ? v : pad;
               }
             }
             float hcur[8];
@@ -258,7 +286,10 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
               uint4 pk;
               float o[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) o[i] = fmaf(wy, hcur[i] - hprev[i], hprev[i]);
+              for (int i = 0; i < 8; ++i) {
+                o[i] = fmaf(wy, hcur[i] - hprev[i], hprev[i]);
+                if (sizeof(InT) == 1) o[i] = fmaf(o[i], a_in, b_in);   // ToTensor + Normalize, after the lerp
+              }
               pk.x = Half2Ops<__nv_bfloat16>::pack(o[0], o[1]);
               pk.y = Half2Ops<__nv_bfloat16>::pack(o[2], o[3]);
               pk.z = Half2Ops<__nv_bfloat16>::pack(o[4], o[5]);
@@ -272,7 +303,7 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
         fence_proxy_async_smem();      // token stores -> visible to the UMMA (async proxy) reads
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(tok_full + c);
+          mbar_arrive(tok_full + tb * 3 + c);
           mbar_arrive(plane_empty + slot);
         }
       }
@@ -298,6 +329,20 @@ __global__ void embed_weight_prep_kernel(const float* __restrict__ w, const floa
   out[idx] = __float2bfloat16_rn(w[(size_t)d * pe::kFeat + (i * 8 + j) * 3 + c]);
 }
 
+template <typename InT>
+static int launch_embed(const CUtensorMap& tw, const EmbedParams& p, int out_dtype, int dim, cudaStream_t st) {
+  void (*kern)(const CUtensorMap, const EmbedParams);
+  if (out_dtype == LAFS_F32) kern = dim == 768 ? gather_embed_kernel<InT, float, 768> : gather_embed_kernel<InT, float, 0>;
+  else kern = dim == 768 ? gather_embed_kernel<InT, __nv_bfloat16, 768>
+            : dim == 384 ? gather_embed_kernel<InT, __nv_bfloat16, 384> : gather_embed_kernel<InT, __nv_bfloat16, 0>;
+  constexpr int smem = pe::Layout<InT>::kSmemBytes;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  LAFS_REQUIRE(e == cudaSuccess, LAFS_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  const int grid = p.Bv < kNumSMs ? p.Bv : kNumSMs;
+  kern<<<grid, pe::kThreads, smem, st>>>(tw, p);
+  return check_launch("lafs_gather_embed_fwd");
+}
+
 }  // namespace lafs
 
 using namespace lafs;
@@ -311,36 +356,31 @@ extern "C" int lafs_embed_weight_prep(const float* weight, const float* bias, in
   return check_launch("lafs_embed_weight_prep");
 }
 
-extern "C" int lafs_gather_embed_fwd(const float* imgs, const float* theta, const void* w_perm_bf16, const float* bias,
-                                     void* out0, void* out1, int out_dtype, int Bv, int H, int W, int n, int dim,
-                                     int n_models, lafs_stream_t stream) {
+extern "C" int lafs_gather_embed_fwd(const void* imgs, int in_dtype, float in_scale, float in_shift, const float* theta,
+                                     const void* w_perm_bf16, const float* bias, void* out0, void* out1, int out_dtype,
+                                     int Bv, int H, int W, int n, int dim, int n_models, lafs_stream_t stream) {
   if (int brc = lafs::bind_device_of(imgs)) return brc;
-  void* out0_bf16 = out0; void* out1_bf16 = out1;
   if (Bv == 0) return LAFS_OK;
-  LAFS_REQUIRE(imgs && theta && w_perm_bf16 && bias && out0_bf16, LAFS_ERR_ARG, "lafs_gather_embed_fwd: null pointer");
+  LAFS_REQUIRE(imgs && theta && w_perm_bf16 && bias && out0, LAFS_ERR_ARG, "lafs_gather_embed_fwd: null pointer");
+  LAFS_REQUIRE(in_dtype == LAFS_F32 || in_dtype == LAFS_U8, LAFS_ERR_ARG, "lafs_gather_embed_fwd: in_dtype=%d (fp32 or uint8)", in_dtype);
   LAFS_REQUIRE(out_dtype == LAFS_BF16 || out_dtype == LAFS_F32, LAFS_ERR_ARG, "lafs_gather_embed_fwd: out_dtype=%d (bf16 or fp32)", out_dtype);
   LAFS_REQUIRE(H == pe::kH && W == pe::kW, LAFS_ERR_ARG, "lafs_gather_embed_fwd: fused path is built for 112x112 faces, got %dx%d", H, W);
-  LAFS_REQUIRE(n_models == 1 || (n_models == 2 && out1_bf16), LAFS_ERR_ARG, "lafs_gather_embed_fwd: n_models=%d", n_models);
+  LAFS_REQUIRE(n_models == 1 || (n_models == 2 && out1), LAFS_ERR_ARG, "lafs_gather_embed_fwd: n_models=%d", n_models);
   LAFS_REQUIRE(n > 0 && n <= pe::kMaxTok, LAFS_ERR_ARG, "lafs_gather_embed_fwd: n=%d outside [1,%d]", n, pe::kMaxTok);
   LAFS_REQUIRE(dim > 0 && dim % 128 == 0, LAFS_ERR_ARG, "lafs_gather_embed_fwd: dim=%d must be a multiple of 128", dim);
   LAFS_REQUIRE(((uintptr_t)imgs & 15u) == 0 && ((uintptr_t)theta & 7u) == 0, LAFS_ERR_ARG, "lafs_gather_embed_fwd: misaligned input");
-  if (Bv == 0) return LAFS_OK;
   LAFS_REQUIRE(Bv > 0, LAFS_ERR_ARG, "lafs_gather_embed_fwd: Bv=%d", Bv);
+  LAFS_REQUIRE(in_dtype == LAFS_F32 || in_scale != 0.f, LAFS_ERR_ARG, "lafs_gather_embed_fwd: in_scale must be non-zero");
   CUtensorMap tw;
   int rc = TmaEncoder::bf16_2d_sw128(&tw, w_perm_bf16, (uint64_t)n_models * dim, pe::kFeat, pe::kFeat * 2, 128);
   if (rc) return rc;
   EmbedParams p{};
   p.imgs = imgs; p.theta = theta; p.bias = bias;
-  p.out[0] = out0_bf16; p.out[1] = out1_bf16;
+  p.out[0] = out0; p.out[1] = out1;
   p.Bv = Bv; p.n = n; p.n_pad = (n + 15) & ~15; p.dim = dim; p.n_models = n_models;
   p.mchunks = n_models * dim / 128;
-  void (*kern)(const CUtensorMap, const EmbedParams);
-  if (out_dtype == LAFS_F32) kern = dim == 768 ? gather_embed_kernel<float, 768> : gather_embed_kernel<float, 0>;
-  else kern = dim == 768 ? gather_embed_kernel<__nv_bfloat16, 768>
-            : dim == 384 ? gather_embed_kernel<__nv_bfloat16, 384> : gather_embed_kernel<__nv_bfloat16, 0>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pe::kSmemBytes);
-  LAFS_REQUIRE(e == cudaSuccess, LAFS_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  const int grid = Bv < kNumSMs ? Bv : kNumSMs;
-  kern<<<grid, pe::kThreads, pe::kSmemBytes, (cudaStream_t)stream>>>(tw, p);
-  return check_launch("lafs_gather_embed_fwd");
+  if (in_dtype == LAFS_U8) { p.in_scale = in_scale; p.in_shift = in_shift; p.pad_raw = -in_shift / in_scale; }
+  else { p.in_scale = 1.f; p.in_shift = 0.f; p.pad_raw = 0.f; }
+  cudaStream_t st = (cudaStream_t)stream;
+  return in_dtype == LAFS_U8 ? launch_embed<uint8_t>(tw, p, out_dtype, dim, st) : launch_embed<float>(tw, p, out_dtype, dim, st);
 }

@@ -146,12 +146,21 @@ class PatchEmbedWeights:
 
 
 @torch.no_grad()
-def gather_embed(imgs, landmarks, weights: PatchEmbedWeights, out_dtype=torch.bfloat16):
+def gather_embed(imgs, landmarks, weights: PatchEmbedWeights, out_dtype=torch.bfloat16, mean=0.5, std=0.5):
     """tokens(imgs, landmarks) @ W^T + b for every model in `weights`, without materialising the
     patches: list of [B, n, dim] tensors.  Forward only (the SSL landmark CNN is frozen and
-    the teacher has no gradient)."""
+    the teacher has no gradient).
+
+    imgs: fp32 [B,3,112,112] already normalised (the reference's tensors), or uint8 decoded pixels;
+    for uint8 the reference's ToTensor + Normalize(mean, std) (lafs_train.py:800-803) runs inside
+    the kernel, which quarters the image bytes moved over PCIe / read from HBM."""
     _lib.require_cuda(imgs, landmarks)
-    x = imgs.detach().float().contiguous()
+    if imgs.dtype == torch.uint8:
+        x = imgs.detach().contiguous()
+        in_dtype, scale, shift = _lib.U8, 1.0 / (255.0 * std), -mean / std
+    else:
+        x = imgs.detach().float().contiguous()
+        in_dtype, scale, shift = _lib.F32, 1.0, 0.0
     th = landmarks.detach().float().contiguous()
     Bv, Cc, H, W = x.shape
     if Cc != 3:
@@ -159,7 +168,8 @@ def gather_embed(imgs, landmarks, weights: PatchEmbedWeights, out_dtype=torch.bf
     n = th.shape[1]
     m = len(weights.linears)
     outs = [torch.empty(Bv, n, weights.dim, dtype=out_dtype, device=x.device) for _ in range(m)]
-    _lib.call("lafs_gather_embed_fwd", x.data_ptr(), th.data_ptr(), weights.w_perm.data_ptr(),
-              weights.bias.data_ptr(), outs[0].data_ptr(), outs[1].data_ptr() if m > 1 else None,
-              _lib.dtype_code(outs[0]), Bv, H, W, n, weights.dim, m, _lib.stream())
+    _lib.call("lafs_gather_embed_fwd", x.data_ptr(), in_dtype, scale, shift, th.data_ptr(),
+              weights.w_perm.data_ptr(), weights.bias.data_ptr(), outs[0].data_ptr(),
+              outs[1].data_ptr() if m > 1 else None, _lib.dtype_code(outs[0]), Bv, H, W, n, weights.dim, m,
+              _lib.stream())
     return outs

@@ -71,3 +71,25 @@ def test_patch_embed_golden(P, golden):
     ref = T(g["embedded"])                        # reference fp32 patch_to_embedding output
     err = (o[:, :, :64].cpu() - ref).abs().max()
     assert err <= 1e-2 * ref.abs().max(), float(err)   # bf16 operands vs the fp32 reference
+
+
+@pytest.mark.parametrize("n", [196, 36])
+def test_uint8_images_normalised_in_kernel(P, n):
+    """uint8 transport: ToTensor + Normalize(0.5, 0.5) fused into the gather == the reference's
+    fp32 pipeline (lafs_train.py:800-803) followed by extract + patch_to_embedding."""
+    torch.manual_seed(n)
+    B, dim = 301, 768
+    u8 = torch.randint(0, 256, (B, 3, 112, 112), dtype=torch.uint8)
+    th = torch.rand(B, n, 2) * 111 + torch.randn(B, n, 2) * 5
+    th[0, 0] = torch.tensor([-3.0, 113.0]); th[0, 1] = torch.tensor([400.0, 5.0])
+    s, t = torch.nn.Linear(192, dim), torch.nn.Linear(192, dim)
+    wts = P.PatchEmbedWeights([(s.weight.cuda(), s.bias.cuda()), (t.weight.cuda(), t.bias.cuda())])
+    o_s, o_t = P.gather_embed(u8.cuda(), th.cuda(), wts, out_dtype=torch.float32)
+    imgs_f = (u8.float() / 255 - 0.5) / 0.5
+    for b in (0, 1, 150, 300):
+        for o, lin in ((o_s, s), (o_t, t)):
+            ref = O.gather_embed(imgs_f[b:b + 1], th[b:b + 1], lin.weight.detach(), lin.bias.detach(), round_bf16=True)
+            check(o[b:b + 1], ref, fp32=True)
+    # same numbers as the fp32-input kernel up to bf16 token rounding flips
+    o_f, _ = P.gather_embed(imgs_f.cuda(), th.cuda(), wts, out_dtype=torch.float32)
+    assert (o_f - o_s).abs().max() <= 1e-3 * o_f.abs().max()

@@ -84,6 +84,13 @@ def main():
     th_l = torch.rand(1024, 36, 2, device="cuda") * 111
     mg2, _ = timeit(lambda: P.gather_embed(imgs, th, w2))
     ml1, _ = timeit(lambda: P.gather_embed(imgs_l, th_l, w1))
+    u8g = torch.randint(0, 256, (512, 3, 112, 112), dtype=torch.uint8, device="cuda")
+    u8l = torch.randint(0, 256, (1024, 3, 112, 112), dtype=torch.uint8, device="cuda")
+    mg2u, _ = timeit(lambda: P.gather_embed(u8g, th, w2))
+    ml1u, _ = timeit(lambda: P.gather_embed(u8l, th_l, w1))
+    res["gather_embed_u8_global"] = {"ms": mg2u, "GBps": (by_g0 := 512 * (3 * 112 * 112 + 196 * 8) + 2 * 512 * 196 * 768 * 2) / mg2u / 1e6}
+    res["gather_embed_u8_local"] = {"ms": ml1u, "GBps": (1024 * (3 * 112 * 112 + 36 * 8) + 1024 * 36 * 768 * 2) / ml1u / 1e6}
+    del u8g, u8l
     by_g = 512 * (3 * 112 * 112 * 4 + 196 * 8) + 2 * 512 * 196 * 768 * 2
     fl_g = 2.0 * 192 * 768 * 2 * 512 * 196
     by_l = 1024 * (3 * 112 * 112 * 4 + 36 * 8) + 1024 * 36 * 768 * 2
