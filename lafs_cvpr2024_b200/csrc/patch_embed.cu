@@ -24,6 +24,7 @@
 // The bf16 path does not need the reference's fp32 coordinate round trip: sample
 // positions are theta + (idx - 4.5) directly; the error (<1e-5 px) is far below bf16 rounding.
 // The stand-alone fp32 gather (gather.cu) keeps the exact sequence for the 1e-5 parity clause.
+#include <stdlib.h>
 #include "umma.cuh"
 #include "../../include/lafs_b200.h"
 
@@ -42,6 +43,7 @@ constexpr int kTokTileBytes = 3 * kTokChunkBytes;  // 76,800 B
 constexpr int kWStageBytes = 128 * 128;            // [128 dims x 64 k] bf16
 constexpr int kWStages = 3;
 constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quarter
+constexpr int kScratchBytes = 0;
 constexpr int kGatherWarps = 8;
 constexpr int kGatherThreads = kGatherWarps * 32;
 // warp roles
@@ -56,7 +58,8 @@ struct Layout {
   static constexpr int kOffPlanes = 0;
   static constexpr int kOffTok = 2 * kPlaneSlot;
   static constexpr int kOffW = kOffTok + kTokBufs * kTokTileBytes;
-  static constexpr int kOffBar = kOffW + kWStages * kWStageBytes;
+  static constexpr int kOffScratch = kOffW + kWStages * kWStageBytes;
+  static constexpr int kOffBar = kOffScratch + kEpiWarps * kScratchBytes;
   static constexpr int kSmemBytes = kOffBar + 256 + 1024;                 // + barriers + alignment slack
   static_assert(kOffTok % 1024 == 0 && kOffW % 1024 == 0, "UMMA tiles need 1024-byte alignment");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
@@ -72,6 +75,7 @@ struct EmbedParams {
   int mchunks;              // n_models * dim / 128
   float in_scale, in_shift; // normalised pixel = in_scale * raw + in_shift   (1, 0 for fp32 input)
   float pad_raw;            // raw value of a zero-padded (out-of-image) pixel = -in_shift / in_scale
+  int debug;                // development ablations (env LAFS_PE_DEBUG): 1 = no stores, 2 = no gather math, 4 = no UMMA
 };
 
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -177,9 +181,11 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
             tc_fence_after();
             const uint64_t da = make_desc_k_sw128(smem_u32(s_w + st * kWStageBytes));
             const uint64_t db = make_desc_k_sw128(smem_u32(s_tok + tb * kTokTileBytes + c * kTokChunkBytes));
+            if (!(p.debug & 4)) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              mma_f16_ss(d_tmem, desc_advance_k(da, kk * 16), desc_advance_k(db, kk * 16), idesc, (c | kk) != 0);
+              for (int kk = 0; kk < 4; ++kk)
+                mma_f16_ss(d_tmem, desc_advance_k(da, kk * 16), desc_advance_k(db, kk * 16), idesc, (c | kk) != 0);
+            }
             mma_commit(w_empty + st);
           }
           mma_commit(acc_full + buf);
@@ -191,7 +197,10 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
     // ===================== epilogue =====================
     // lane = output feature (TMEM lane), registers = 32 consecutive tokens.  A warp-wide 2-byte
     // store covers 32 consecutive features of one token (64 contiguous bytes = 2 full sectors).
-    // The two warps of a lane quarter take alternate 32-token pieces.
+    // The two warps of a lane quarter take alternate 32-token pieces; the TMEM load of the next
+    // piece is in flight while the current one is converted and stored.
+    // (A shared-memory transpose to 16-byte stores was measured 25 % SLOWER: the extra STS/LDS
+    //  traffic competes with the gather warps for the MIO pipe.)
     const int quarter = warp & 3;
     const int half = (warp - kWarpEpi0) >> 2;
     const int dim = DIM > 0 ? DIM : p.dim;
@@ -207,17 +216,19 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
         mbar_wait(acc_full + buf, (acnt >> 1) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t)(buf * 256) + ((uint32_t)(quarter * 32) << 16);
-        for (int t0 = half * 32; t0 < p.n; t0 += 64) {
-          uint32_t v[32];
+        // n_pad is a multiple of 16; pieces are 32 columns, the last one may be a 16-column tail
+        auto issue_ld = [&](int t0, uint32_t (&v)[32]) {
           if (t0 + 32 <= p.n_pad) {
             tmem_ld_32x32b_x32(taddr + (uint32_t)t0, v);
-          } else {                                          // n_pad is a multiple of 16: 16-column tail
+          } else {
             uint32_t lo[16];
             tmem_ld_32x32b_x16(taddr + (uint32_t)t0, lo);
 #pragma unroll
             for (int j = 0; j < 16; ++j) { v[j] = lo[j]; v[16 + j] = 0u; }
           }
-          tmem_ld_wait();
+        };
+        auto emit = [&](int t0, const uint32_t (&v)[32]) {
+          if (p.debug & 1) return;
           OutT* q = dst + (size_t)t0 * dim;
           if (t0 + 32 <= p.n) {
 #pragma unroll
@@ -227,6 +238,21 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
             for (int j = 0; j < 32; ++j)
               if (t0 + j < p.n) store_out(q + (size_t)j * dim, __uint_as_float(v[j]) + bias);
           }
+        };
+        uint32_t va[32], vb[32];
+        int t0 = half * 32;
+        if (t0 < p.n) issue_ld(t0, va);
+        while (t0 < p.n) {
+          tmem_ld_wait();
+          const int t1 = t0 + 64;
+          if (t1 < p.n) issue_ld(t1, vb);
+          emit(t0, va);
+          if (t1 >= p.n) break;
+          tmem_ld_wait();
+          const int t2 = t1 + 64;
+          if (t2 < p.n) issue_ld(t2, va);
+          emit(t1, vb);
+          t0 = t2;
         }
         tc_fence_before();
         __syncwarp();
@@ -250,7 +276,7 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
         const InT* plane = reinterpret_cast<const InT*>(s_planes + slot * L::kPlaneSlot);
         uint8_t* tok = s_tok + tb * kTokTileBytes + c * kTokChunkBytes;
         // item = (token t, half h): output columns j = 4h..4h+3, all 8 i  -> four 16-byte stores
-        for (int item = gt; item < 2 * p.n; item += kGatherThreads) {
+        for (int item = gt; item < ((p.debug & 2) ? 0 : 2 * p.n); item += kGatherThreads) {
           const int t = item >> 1, h = item & 1;
           const float2 thv = __ldg(reinterpret_cast<const float2*>(th) + t);
           const float sx = thv.x - 4.5f, sy = thv.y - 4.5f + (float)(4 * h);
@@ -381,6 +407,7 @@ extern "C" int lafs_gather_embed_fwd(const void* imgs, int in_dtype, float in_sc
   p.mchunks = n_models * dim / 128;
   if (in_dtype == LAFS_U8) { p.in_scale = in_scale; p.in_shift = in_shift; p.pad_raw = -in_shift / in_scale; }
   else { p.in_scale = 1.f; p.in_shift = 0.f; p.pad_raw = 0.f; }
+  if (const char* dbg = getenv("LAFS_PE_DEBUG")) p.debug = atoi(dbg);
   cudaStream_t st = (cudaStream_t)stream;
   return in_dtype == LAFS_U8 ? launch_embed<uint8_t>(tw, p, out_dtype, dim, st) : launch_embed<float>(tw, p, out_dtype, dim, st);
 }
