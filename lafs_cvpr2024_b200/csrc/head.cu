@@ -270,13 +270,16 @@ head_gemm_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
   }
 }
 
-// merge `nparts` partial (max2, sumexp, tgt_a, tgt_b) records per row -> one record per row
-__global__ void head_merge_kernel(const float* __restrict__ part, int B, int nparts, long long part_stride,
-                                  long long row_stride, float* __restrict__ out) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+// merge `nparts` partial (max2, sumexp, tgt_a, tgt_b) records per row -> one record per row.
+// One warp per row, lanes stride over the parts, butterfly merge.
+__global__ void __launch_bounds__(256)
+head_merge_kernel(const float* __restrict__ part, int B, int nparts, long long part_stride,
+                  long long row_stride, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (b >= B) return;
   float m = -INFINITY, l = 0.f, ta = 0.f, tb = 0.f;
-  for (int r = 0; r < nparts; ++r) {
+  for (int r = lane; r < nparts; r += 32) {
     const float4 v = *reinterpret_cast<const float4*>(part + (size_t)r * part_stride + (size_t)b * row_stride);
     if (v.x == -INFINITY) continue;     // CTA saw no valid class for this row
     const float mn = fmaxf(m, v.x);
@@ -285,7 +288,11 @@ __global__ void head_merge_kernel(const float* __restrict__ part, int B, int npa
     ta += v.z;
     tb += v.w;
   }
-  *reinterpret_cast<float4*>(out + (size_t)b * 4) = make_float4(m, l, ta, tb);
+  const float mw = warp_max(m);
+  l = warp_sum(m == -INFINITY ? 0.f : l * ex2(m - mw));
+  ta = warp_sum(ta);
+  tb = warp_sum(tb);
+  if (lane == 0) *reinterpret_cast<float4*>(out + (size_t)b * 4) = make_float4(mw, l, ta, tb);
 }
 
 // per-row loss from merged statistics: lse(z) - (ta_w*z_a + tb_w*z_b); mean over rows.
@@ -460,7 +467,7 @@ extern "C" int lafs_head_fwd(const void* e_hat, const void* w_hat, const int64_t
   cudaStream_t st = (cudaStream_t)stream;
   rc = hl.BN == 256 ? launch_head<256, HEAD_STATS>(te, tw, p, hl, st) : launch_head<128, HEAD_STATS>(te, tw, p, hl, st);
   if (rc) return rc;
-  head_merge_kernel<<<(B + 127) / 128, 128, 0, st>>>(p.part, B, hl.nranges, 4, (long long)hl.nranges * 4, row_stats);
+  head_merge_kernel<<<(B + 7) / 8, 256, 0, st>>>(p.part, B, hl.nranges, 4, (long long)hl.nranges * 4, row_stats);
   return check_launch("lafs_head_fwd/merge");
 }
 
@@ -480,7 +487,7 @@ extern "C" int lafs_head_logits(const void* e_hat, const void* w_hat, const int6
 extern "C" int lafs_head_merge(const float* parts, int nparts, int B, float* row_stats, lafs_stream_t stream) {
   if (int brc = lafs::bind_device_of(parts)) return brc;
   LAFS_REQUIRE(parts && row_stats && nparts > 0 && B > 0, LAFS_ERR_ARG, "lafs_head_merge: bad argument");
-  head_merge_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(parts, B, nparts, (long long)B * 4, 4, row_stats);
+  head_merge_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(parts, B, nparts, (long long)B * 4, 4, row_stats);
   return check_launch("lafs_head_merge");
 }
 

@@ -1,0 +1,289 @@
+"""Part-fViT and landmark-CNN wrappers with the reference's constructor / forward surface and
+state-dict keys, routed through the sm_100a kernels for the hot-path pieces.
+
+    ViT_face_landmark_patch8(...)        face_pre_pro/ViT_face.py:560-795
+    face_landmark_4simmin_glo_loc(...)   face_pre_pro/ViT_face.py:1218-1409
+
+What runs where
+  * landmark tail (joint min-max, noise, re-sampling)            -> lafs_landmark_post   (kernel)
+  * patch extraction / token layout                              -> lafs_gather_fwd/_bwd (kernel)
+  * extraction + patch_to_embedding without gradients            -> lafs_gather_embed_fwd (tcgen05)
+  * margin head `self.loss`                                      -> CosFace / ArcFace    (tcgen05)
+  * transformer blocks, LayerNorm, MobileNetV3 landmark trunk    -> stock PyTorch, as in the
+    reference (outside the hot path); the trunk class is taken from the
+    reference checkout (`face_pre_pro.mobilenet.MobileNetV3_backbone`) or injected via `stn=`.
+
+Checkpoint compatibility: parameter / buffer names equal the reference's (`pos_embedding`,
+`patch_to_embedding.{weight,bias}`, `cls_token`, `transformer.layers.{i}.{0,1}.fn.…`,
+`mlp_head.0.*`, `loss.weight`, `stn.*`, `output_layer.1.*`, `global_token.1.*`, `mask_token`).
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from .margin_head import ArcFace, CosFace
+from .patches import PatchEmbedWeights, extract_tokens, gather_embed, landmark_post
+
+MIN_NUM_PATCHES = 15  # ViT_face.py:21
+
+
+def _default_trunk():
+    try:
+        from face_pre_pro.mobilenet import MobileNetV3_backbone  # the reference's own trunk
+    except Exception as e:  # pragma: no cover - depends on the checkout
+        raise RuntimeError(
+            "the MobileNetV3 landmark trunk is outside the hot path and is not re-implemented here: run "
+            "inside the reference checkout (face_pre_pro.mobilenet importable) or pass stn=<module "
+            "mapping [B,3,112,112] -> [B,160,h,w]>") from e
+    return MobileNetV3_backbone(mode="large")
+
+
+class DropPath(nn.Module):
+    """Per-sample stochastic depth."""
+
+    def __init__(self, p=0.0):
+        super().__init__()
+        self.drop_prob = p
+
+    def forward(self, x):
+        if self.drop_prob == 0.0 or not self.training:
+            return x
+        keep = 1.0 - self.drop_prob
+        mask = x.new_empty((x.shape[0],) + (1,) * (x.dim() - 1)).bernoulli_(keep)
+        return x * mask / keep
+
+
+class Residual_droppath(nn.Module):
+    def __init__(self, fn, drop_path_rate=0.1):
+        super().__init__()
+        self.fn = fn
+        self.drop_path = DropPath(drop_path_rate) if drop_path_rate > 0.0 else nn.Identity()
+
+    def forward(self, x, **kw):
+        return self.drop_path(self.fn(x, **kw)) + x
+
+
+class PreNorm(nn.Module):
+    def __init__(self, dim, fn):
+        super().__init__()
+        self.norm = nn.LayerNorm(dim)
+        self.fn = fn
+
+    def forward(self, x, **kw):
+        return self.fn(self.norm(x), **kw)
+
+
+class FeedForward(nn.Module):
+    def __init__(self, dim, hidden_dim, dropout=0.0):
+        super().__init__()
+        self.net = nn.Sequential(nn.Linear(dim, hidden_dim), nn.GELU(), nn.Dropout(dropout),
+                                 nn.Linear(hidden_dim, dim), nn.Dropout(dropout))
+
+    def forward(self, x):
+        return self.net(x)
+
+
+class Attention(nn.Module):
+    """Multi-head attention with the reference's quirks: heads*dim_head need not equal
+    dim and the logits are scaled by dim**-0.5, not dim_head**-0.5."""
+
+    def __init__(self, dim, heads=8, dim_head=64, dropout=0.0):
+        super().__init__()
+        inner = dim_head * heads
+        self.heads = heads
+        self.scale = dim ** -0.5
+        self.to_qkv = nn.Linear(dim, inner * 3, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner, dim), nn.Dropout(dropout))
+
+    def forward(self, x, mask=None):
+        b, n, _ = x.shape
+        q, k, v = (t.view(b, n, self.heads, -1).transpose(1, 2) for t in self.to_qkv(x).chunk(3, dim=-1))
+        attn_mask = None
+        if mask is not None:
+            m = F.pad(mask.flatten(1), (1, 0), value=True)
+            attn_mask = (m[:, None, :] * m[:, :, None])[:, None]
+        out = F.scaled_dot_product_attention(q, k, v, attn_mask=attn_mask, scale=self.scale)
+        return self.to_out(out.transpose(1, 2).reshape(b, n, -1))
+
+
+class Transformer(nn.Module):
+    def __init__(self, dim, depth, heads, dim_head, mlp_dim, dropout):
+        super().__init__()
+        self.layers = nn.ModuleList([
+            nn.ModuleList([Residual_droppath(PreNorm(dim, Attention(dim, heads, dim_head, dropout))),
+                           Residual_droppath(PreNorm(dim, FeedForward(dim, mlp_dim, dropout)))])
+            for _ in range(depth)])
+
+    def forward(self, x, mask=None):
+        for attn, ff in self.layers:
+            x = ff(attn(x, mask=mask))
+        return x
+
+
+def _tokens_and_embedding(imgs, theta, linear, training_path):
+    """patch tokens -> patch_to_embedding.  With gradients: differentiable fp32 gather kernel +
+    the nn.Linear; without: the fused tcgen05 gather->embed kernel (no token tensor in HBM)."""
+    if training_path:
+        tok = extract_tokens(imgs, theta)
+        return linear(tok.to(linear.weight.dtype))
+    w = PatchEmbedWeights([(linear.weight, linear.bias)])
+    (emb,) = gather_embed(imgs, theta, w, out_dtype=torch.bfloat16)
+    return emb.to(linear.weight.dtype)
+
+
+class ViT_face_landmark_patch8(nn.Module):
+    def __init__(self, *, loss_type, GPU_ID, num_class, image_size, patch_size, dim, depth, heads, mlp_dim,
+                 pool='cls', num_patches=None, channels=3, dim_head=64, dropout=0., emb_dropout=0., fp16=True,
+                 with_land=False, use_standcoord=False, Random_prob=False, shuffle=False, stn=None):
+        super().__init__()
+        if num_patches is None:
+            num_patches = (image_size // patch_size) ** 2
+        patch_dim = channels * patch_size ** 2
+        assert num_patches > MIN_NUM_PATCHES, f'your number of patches ({num_patches}) is way too small for attention to be effective (at least 16). Try decreasing your patch size'
+        assert pool in {'cls', 'mean'}, 'pool type must be either cls (cls token) or mean (mean pooling)'
+        if patch_size != 8:
+            raise ValueError("the sm_100a gather kernels implement the reference's 8x8 patches")
+        if use_standcoord:
+            raise NotImplementedError("use_standcoord (fixed grid, unused by LAFS pretrain/finetune) is not built")
+        self.patch_size = patch_size
+        self.fp16 = fp16
+        self.num_patches = num_patches
+        self.row_num = int(math.sqrt(num_patches))
+        self.with_land = with_land
+        if with_land:
+            self.stn = stn if stn is not None else _default_trunk()
+            self.output_layer = nn.Sequential(nn.Dropout(p=0.5), nn.Linear(160, self.row_num * self.row_num * 2))
+        self.patch_shape = torch.tensor([patch_size, patch_size])
+        self.theta = 0
+        self.pos_embedding = nn.Parameter(torch.randn(1, num_patches + 1, dim))
+        self.patch_to_embedding = nn.Linear(patch_dim, dim)
+        self.cls_token = nn.Parameter(torch.randn(1, 1, dim))
+        self.dropout = nn.Dropout(emb_dropout)
+        self.transformer = Transformer(dim, depth, heads, dim_head, mlp_dim, dropout)
+        self.pool = pool
+        self.to_latent = nn.Identity()
+        self.mlp_head = nn.Sequential(nn.LayerNorm(dim))
+        self.loss_type = loss_type
+        self.GPU_ID = GPU_ID
+        self.Random_prob = Random_prob
+        self.shuffle = shuffle
+        if loss_type == 'CosFace':
+            self.loss = CosFace(in_features=dim, out_features=num_class, device_id=GPU_ID, m=0.4)
+        elif loss_type == 'ArcFace':
+            self.loss = ArcFace(in_features=dim, out_features=num_class, device_id=GPU_ID)
+        elif loss_type != 'None':
+            raise ValueError(f"loss_type {loss_type!r}: the reference defines only CosFace (ArcFace is provided "
+                             "here; Softmax / SFace are undefined in the reference as well)")
+
+    def landmarks(self, x):
+        """[B,n,2] landmark coordinates of a face batch (ViT_face.py:680-706), differentiable."""
+        feat = self.stn(x).mean(dim=(-2, -1))
+        theta = landmark_post(self.output_layer(feat))
+        self.theta = theta
+        return theta
+
+    def forward(self, x, label=None, mask=None, visualize=False, save_token=False, opt=None, keep_num=None,
+                glo_diff=False):
+        theta = None
+        if x.dim() == 4:
+            if not self.with_land:
+                raise ValueError("4-D image input needs with_land=True (token input is 3-D [B, n, 192])")
+            _lib.require_cuda(x)
+            theta = self.landmarks(x.float())
+            num_land = (x.shape[-2] // self.patch_size) ** 2
+            need_grad = torch.is_grad_enabled() and (theta.requires_grad or x.requires_grad
+                                                     or self.patch_to_embedding.weight.requires_grad)
+            x = _tokens_and_embedding(x.float(), theta[:, :num_land], self.patch_to_embedding, need_grad)
+        else:
+            x = self.patch_to_embedding(x)                       # SSL path: tokens prepared by the landmark CNN
+        b, n, _ = x.shape
+        x = torch.cat((self.cls_token.expand(b, -1, -1).to(x.dtype), x), dim=1)
+        x = x + self.pos_embedding[:, :(n + 1)].to(x.dtype)
+        x = self.dropout(x)
+        x = self.transformer(x, mask)
+        tokens = x[:, 1:] if save_token else None
+        x = x.mean(dim=1) if self.pool == 'mean' else x[:, 0]
+        emb = self.mlp_head(self.to_latent(x))
+        if save_token:
+            return emb, tokens, self.theta
+        if label is not None:
+            return self.loss(emb.float(), label), (emb if opt is not None else self.theta)
+        return (emb, theta) if visualize else emb
+
+    def forward_loss(self, x, label, label_b=None, lam=1.0):
+        """Fused finetune step tail: embedding -> margin head -> cross-entropy, no [B,C] logits."""
+        emb = self.forward(x)
+        return self.loss.forward_loss(emb.float(), label, label_b, lam)
+
+
+class face_landmark_4simmin_glo_loc(nn.Module):
+    def __init__(self, *, loss_type, GPU_ID, num_class, image_size, patch_size, dim, depth, heads, mlp_dim,
+                 pool='cls', num_patches=None, channels=3, dim_head=64, dropout=0., emb_dropout=0., fp16=True,
+                 stn=None):
+        super().__init__()
+        if num_patches is None:
+            num_patches = (image_size // patch_size) ** 2
+        patch_dim = channels * patch_size ** 2
+        assert num_patches > MIN_NUM_PATCHES, f'your number of patches ({num_patches}) is way too small for attention to be effective (at least 16). Try decreasing your patch size'
+        if patch_size != 8:
+            raise ValueError("the sm_100a gather kernels implement the reference's 8x8 patches")
+        self.patch_size = patch_size
+        self.fp16 = fp16
+        self.num_patches = num_patches
+        self.row_num = int(math.sqrt(num_patches))
+        self.stn = stn if stn is not None else _default_trunk()
+        self.dim = dim
+        self.output_layer = nn.Sequential(nn.Dropout(p=0.5), nn.Linear(160, self.row_num * self.row_num * 2))
+        self.global_token = nn.Sequential(nn.Dropout(p=0.5), nn.Linear(160, dim))
+        self.patch_shape = torch.tensor([patch_size, patch_size])
+        self.theta = 0
+        self.pos_embedding = nn.Parameter(torch.randn(1, num_patches + 1, dim))
+        self.patch_to_embedding = nn.Linear(patch_dim, dim)
+        self.cls_token = nn.Parameter(torch.randn(1, 1, dim))
+        self.dropout = nn.Dropout(emb_dropout)
+        self.loss_type = loss_type
+        self.GPU_ID = GPU_ID
+        self.num_features = dim
+        self.in_chans = channels
+        self.mask_token = nn.Parameter(torch.zeros(1, 1, dim))
+        nn.init.trunc_normal_(self.mask_token, std=.02, a=-.02, b=.02)
+
+    def landmarks(self, x, Random_prob=False, return_prob=False, ran_sample=False):
+        """theta as the reference computes it (ViT_face.py:1332-1380).  The noise and the re-sampled
+        indices are drawn on the CPU default generator in the reference's order."""
+        feat = self.stn(x).mean(dim=(-2, -1))
+        raw = self.output_layer(feat)
+        n = self.row_num * self.row_num
+        noise = idx = None
+        if Random_prob:
+            noise = (torch.randn(raw.shape[0], n, 2) * 5).to(raw.device)
+            if not return_prob:
+                keep = 36 if ran_sample else n
+                idx = torch.randint(0, n, (raw.shape[0], keep, 1)).to(raw.device)
+        return landmark_post(raw, noise, idx)
+
+    def forward(self, x, x_Aug=None, keep_num=None, patch_shape=None, Random_prob=False, return_prob=False,
+                ran_sample=False, random_coor=False, return_land=False):
+        _lib.require_cuda(x)
+        if random_coor:
+            num_land = 25 if ran_sample else self.row_num * self.row_num
+            theta = (torch.rand(x.shape[0], num_land, 2) * 111.0).to(x.device)
+        else:
+            theta = self.landmarks(x, Random_prob, return_prob, ran_sample)
+            self.theta = theta
+        if return_land:
+            return theta, x
+        src = x if x_Aug is None else x_Aug
+        n = theta.shape[1]
+        r = int(math.isqrt(n))
+        from .patches import extract_patches_pytorch_gridsample
+        return theta, extract_patches_pytorch_gridsample(src, theta, self.patch_shape, r * r)
+
+    def forward_tokens(self, x, x_Aug=None, Random_prob=False, return_prob=False, ran_sample=False):
+        """theta and the '(p1 p2 c)' token tensor [B,n,192] directly (fuses lafs_train.py:535-538)."""
+        theta = self.landmarks(x, Random_prob, return_prob, ran_sample)
+        self.theta = theta
+        return theta, extract_tokens(x if x_Aug is None else x_Aug, theta)

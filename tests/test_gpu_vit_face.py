@@ -1,0 +1,111 @@
+"""GPU: the Part-fViT / landmark-CNN wrappers (reference module surface) against the same
+composition built from the CPU oracle pieces.  The MobileNetV3 trunk is outside the hot path;
+a tiny stand-in trunk with the same output contract ([B,160,h,w]) is injected."""
+import copy
+
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle import lafs_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+class TinyTrunk(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.net = nn.Sequential(nn.Conv2d(3, 16, 7, stride=8, padding=3), nn.ReLU(), nn.Conv2d(16, 160, 3, stride=4, padding=1))
+
+    def forward(self, x):
+        return self.net(x)
+
+
+@pytest.fixture(scope="module")
+def P():
+    import lafs_cvpr2024_b200 as pkg
+    return pkg
+
+
+def oracle_forward(m, x, label=None):
+    """The wrapper's forward with every hot-path kernel replaced by its oracle function (CPU)."""
+    feat = m.stn(x).mean(dim=(-2, -1))
+    theta = O.landmark_post(m.output_layer(feat))
+    tok = O.extract_tokens(x, theta)
+    y = m.patch_to_embedding(tok)
+    b, n, _ = y.shape
+    y = torch.cat((m.cls_token.expand(b, -1, -1), y), 1) + m.pos_embedding[:, :n + 1]
+    emb = m.mlp_head(m.transformer(m.dropout(y))[:, 0])
+    if label is None:
+        return emb, theta
+    return O.cross_entropy(O.cosface_logits(emb, m.loss.weight, label), label), theta
+
+
+def make(P, **kw):
+    torch.manual_seed(0)
+    cfg = dict(loss_type="CosFace", GPU_ID=None, num_class=300, image_size=112, patch_size=8, dim=128, depth=2,
+               heads=3, mlp_dim=128, num_patches=196, with_land=True, stn=TinyTrunk())
+    cfg.update(kw)
+    return P.ViT_face_landmark_patch8(**cfg).eval()
+
+
+def test_finetune_forward_backward_matches_oracle_composition(P):
+    m = make(P)
+    ref = copy.deepcopy(m)
+    x = torch.rand(4, 3, 112, 112) * 2 - 1
+    lab = torch.tensor([0, 7, 299, 150])
+    loss_ref, theta_ref = oracle_forward(ref, x, lab)
+    loss_ref.backward()
+    mg = m.cuda()
+    logits, theta = mg(x.cuda(), lab.cuda())
+    assert logits.shape == (4, 300)
+    assert torch.equal(theta.detach().cpu(), theta_ref.detach())               # landmark tail bit-exact
+    loss = torch.nn.CrossEntropyLoss()(logits, lab.cuda())
+    loss.backward()
+    assert abs(float(loss) - float(loss_ref)) <= 5e-3 * abs(float(loss_ref))
+    for name in ("patch_to_embedding.weight", "output_layer.1.weight", "stn.net.0.weight", "loss.weight"):
+        g = dict(mg.named_parameters())[name].grad.cpu()
+        gr = dict(ref.named_parameters())[name].grad
+        assert (g - gr).abs().max() <= 3e-2 * gr.abs().max(), name
+    # fused loss entry point gives the same loss
+    mg.zero_grad()
+    l2 = mg.forward_loss(x.cuda(), lab.cuda())
+    assert abs(float(l2) - float(loss)) <= 1e-4 * abs(float(loss))
+
+
+def test_inference_uses_fused_path(P):
+    m = make(P, loss_type="None")
+    ref = copy.deepcopy(m)
+    x = torch.rand(3, 3, 112, 112) * 2 - 1
+    with torch.no_grad():
+        emb_ref, _ = oracle_forward(ref, x)
+        emb = m.cuda()(x.cuda())
+    assert (emb.cpu() - emb_ref).abs().max() <= 2e-2 * emb_ref.abs().max()     # bf16 patch embedding inside
+
+
+def test_landmark_cnn_wrapper_ssl_calls(P):
+    torch.manual_seed(1)
+    cnn = P.face_landmark_4simmin_glo_loc(loss_type="CosFace", GPU_ID=None, num_class=10, num_patches=196, image_size=112,
+                                          patch_size=8, dim=64, depth=1, heads=2, mlp_dim=64, stn=TinyTrunk()).eval()
+    ref = copy.deepcopy(cnn)
+    x = torch.rand(3, 3, 112, 112) * 2 - 1
+    xa = torch.rand(3, 3, 112, 112) * 2 - 1
+    g = cnn.cuda()
+    ps = torch.tensor([8, 8])
+    with torch.no_grad():
+        raw = ref.output_layer(ref.stn(x).mean(dim=(-2, -1)))
+        # global view (lafs_train.py:535): noise only
+        torch.manual_seed(5)
+        th, mos = g(x.cuda(), x_Aug=xa.cuda(), patch_shape=ps, Random_prob=True, return_prob=True)
+        torch.manual_seed(5)
+        th_ref = O.landmark_post(raw, torch.randn(3, 196, 2) * 5)
+        assert torch.equal(th.cpu(), th_ref) and torch.equal(mos.cpu(), O.extract_patches(xa, th_ref, 196))
+        # local view (lafs_train.py:565): noise + 36 re-sampled landmarks
+        torch.manual_seed(6)
+        th, mos = g(x.cuda(), x_Aug=xa.cuda(), patch_shape=ps, Random_prob=True, ran_sample=True)
+        torch.manual_seed(6)
+        noise = torch.randn(3, 196, 2) * 5
+        idx = torch.randint(0, 196, (3, 36, 1))
+        th_ref = O.landmark_post(raw, noise, idx)
+        assert mos.shape == (3, 3, 48, 48)
+        assert torch.equal(th.cpu(), th_ref) and torch.equal(mos.cpu(), O.extract_patches(xa, th_ref, 36))

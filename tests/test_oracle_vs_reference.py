@@ -61,3 +61,23 @@ def test_cosface_and_mixup_match(ref):
 def test_cosine_scheduler_matches(ref):
     a = ref.dutils.cosine_scheduler(0.996, 1, 41, 123)
     assert np.array_equal(a, O.cosine_scheduler(0.996, 1, 41, 123))
+
+
+def test_module_wrappers_keep_state_dict_keys(ref):
+    """Checkpoint contract: the drop-in modules expose the reference's parameter names
+    and shapes, so the reference's checkpoints load with strict=True."""
+    import contextlib
+    import io
+    import lafs_cvpr2024_b200 as P
+    kw = dict(loss_type="CosFace", GPU_ID=None, num_class=50, image_size=112, patch_size=8, dim=64, depth=2,
+              heads=3, mlp_dim=96, num_patches=196)
+    with contextlib.redirect_stdout(io.StringIO()):
+        r1 = ref.VF.ViT_face_landmark_patch8(with_land=True, **kw)
+        r2 = ref.VF.face_landmark_4simmin_glo_loc(**kw)
+        m1 = P.ViT_face_landmark_patch8(with_land=True, **kw)
+        m2 = P.face_landmark_4simmin_glo_loc(**kw)
+    for r, m in ((r1, m1), (r2, m2)):
+        rs, ms = r.state_dict(), m.state_dict()
+        assert set(rs) == set(ms), (sorted(set(rs) ^ set(ms))[:10])
+        assert all(rs[k].shape == ms[k].shape for k in rs)
+        m.load_state_dict(rs, strict=True)
