@@ -72,6 +72,8 @@ struct EmbedParams {
   const float* bias;        // [n_models * dim]
   void* out[2];             // per model: [Bv, n, dim] bf16 or fp32
   int Bv, n, n_pad, dim, n_models;
+  int gfaces;               // faces whose tokens share one tile / one pass over the weights (G*n <= 200)
+  int ngroups;              // ceil(Bv / gfaces)
   int mchunks;              // n_models * dim / 128
   float in_scale, in_shift; // normalised pixel = in_scale * raw + in_shift   (1, 0 for fp32 input)
   float pad_raw;            // raw value of a zero-padded (out-of-image) pixel = -in_shift / in_scale
@@ -89,6 +91,65 @@ __device__ __forceinline__ void store_out(__nv_bfloat16* p, float v) { *p = __fl
 
 __device__ __forceinline__ float raw_pixel(const float* plane, int idx) { return plane[idx]; }
 __device__ __forceinline__ float raw_pixel(const uint8_t* plane, int idx) { return (float)plane[idx]; }
+
+// Bilinear gather of one staged channel plane into one 64-feature chunk of the token tile.
+template <typename InT, int JB>
+__device__ __forceinline__ void gather_plane(const InT* __restrict__ plane, uint8_t* __restrict__ tok,
+                                             const float* __restrict__ th, int n, int row0, int gt, float a_in,
+                                             float b_in, float pad, int debug) {
+  using namespace pe;
+  constexpr int NB = 8 / JB;                               // items per token
+  for (int item = gt; item < ((debug & 2) ? 0 : NB * n); item += kGatherThreads) {
+    const int t = item / NB, h = item - t * NB;
+    const float2 thv = __ldg(reinterpret_cast<const float2*>(th) + t);
+    const float sx = thv.x - 4.5f, sy = thv.y - 4.5f + (float)(JB * h);
+    const float fxf = floorf(sx), fyf = floorf(sy);
+    const float wx = sx - fxf, wy = sy - fyf;
+    const int x0 = (int)fminf(fmaxf(fxf, -16.f), 128.f);
+    const int y0 = (int)fminf(fmaxf(fyf, -16.f), 128.f);
+    const bool inside = (x0 >= 0) && (x0 + 8 < kW) && (y0 >= 0) && (y0 + JB < kH);
+    float hprev[8];
+#pragma unroll
+    for (int r = 0; r < JB + 1; ++r) {
+      float px[9];
+      const int y = y0 + r;
+      if (inside) {
+        const int base = y * kW + x0;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) px[q] = raw_pixel(plane, base + q);
+      } else {
+        const bool yok = (y >= 0) && (y < kH);
+        const int rowb = min(max(y, 0), kH - 1) * kW;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+          const int x = x0 + q;
+          const float v = raw_pixel(plane, rowb + min(max(x, 0), kW - 1));
+          px[q] = (yok && x >= 0 && x < kW) ? v : pad;
+        }
+      }
+      float hcur[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) hcur[i] = fmaf(wx, px[i + 1] - px[i], px[i]);
+      if (r > 0) {
+        const int j = JB * h + r - 1;
+        uint4 pk;
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          o[i] = fmaf(wy, hcur[i] - hprev[i], hprev[i]);
+          if (sizeof(InT) == 1) o[i] = fmaf(o[i], a_in, b_in);   // ToTensor + Normalize, after the lerp
+        }
+        pk.x = Half2Ops<__nv_bfloat16>::pack(o[0], o[1]);
+        pk.y = Half2Ops<__nv_bfloat16>::pack(o[2], o[3]);
+        pk.z = Half2Ops<__nv_bfloat16>::pack(o[4], o[5]);
+        pk.w = Half2Ops<__nv_bfloat16>::pack(o[6], o[7]);
+        *reinterpret_cast<uint4*>(tok + sw128_offset(row0 + t, j * 8)) = pk;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) hprev[i] = hcur[i];
+    }
+  }
+}
 
 // DIM > 0: compile-time embedding width (store offsets become immediates); DIM == 0: runtime p.dim
 template <typename InT, typename OutT, int DIM>
@@ -130,21 +191,29 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int nfaces_mine = (p.Bv - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // work unit = a GROUP of p.gfaces consecutive faces (1 for 196 landmarks, 5 for 36): their tokens
+  // fill one tile, so every weight chunk fetched from L2 is used for all of them
+  const int ngroups_mine = (p.ngroups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto group_faces = [&](int g) { return min(p.gfaces, p.Bv - g * p.gfaces); };
+  auto group_ntok = [&](int g) { return group_faces(g) * p.n; };
 
   if (warp == kWarpPlane) {
     // ===================== image plane producer =====================
     if (lane == 0) {
       const InT* imgs = reinterpret_cast<const InT*>(p.imgs);
       uint32_t cnt = 0;
-      for (int fi = 0; fi < nfaces_mine; ++fi) {
-        const int f = blockIdx.x + fi * gridDim.x;
-        for (int c = 0; c < kC; ++c, ++cnt) {
-          const int slot = cnt & 1;
-          mbar_wait(plane_empty + slot, ((cnt >> 1) & 1) ^ 1);
-          mbar_arrive_expect_tx(plane_full + slot, L::kPlaneBytes);
-          bulk_load(s_planes + slot * L::kPlaneSlot, imgs + ((size_t)f * kC + c) * (kH * kW), L::kPlaneBytes,
-                    plane_full + slot);
+      for (int gi = 0; gi < ngroups_mine; ++gi) {
+        const int g = blockIdx.x + gi * gridDim.x;
+        const int nf = group_faces(g);
+        for (int ff = 0; ff < nf; ++ff) {
+          const int f = g * p.gfaces + ff;
+          for (int c = 0; c < kC; ++c, ++cnt) {
+            const int slot = cnt & 1;
+            mbar_wait(plane_empty + slot, ((cnt >> 1) & 1) ^ 1);
+            mbar_arrive_expect_tx(plane_full + slot, L::kPlaneBytes);
+            bulk_load(s_planes + slot * L::kPlaneSlot, imgs + ((size_t)f * kC + c) * (kH * kW), L::kPlaneBytes,
+                      plane_full + slot);
+          }
         }
       }
     }
@@ -152,7 +221,7 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
     // ===================== weight chunk producer =====================
     if (lane == 0) {
       uint32_t cnt = 0;
-      for (int fi = 0; fi < nfaces_mine; ++fi)
+      for (int gi = 0; gi < ngroups_mine; ++gi)
         for (int mc = 0; mc < p.mchunks; ++mc)
           for (int c = 0; c < kC; ++c, ++cnt) {
             const int st = cnt % kWStages;
@@ -164,11 +233,12 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
   } else if (warp == kWarpMma) {
     // ===================== UMMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, p.n_pad);
       uint32_t wcnt = 0, acnt = 0;
-      for (int fi = 0; fi < nfaces_mine; ++fi) {
+      for (int fi = 0; fi < ngroups_mine; ++fi) {
         const int tb = fi % NTB;
         const uint32_t tuse = (uint32_t)(fi / NTB);
+        const int npad_g = (group_ntok(blockIdx.x + fi * gridDim.x) + 15) & ~15;
+        const uint32_t idesc = make_idesc_bf16(128, npad_g);
         for (int mc = 0; mc < p.mchunks; ++mc, ++acnt) {
           const int buf = acnt & 1;
           mbar_wait(acc_empty + buf, ((acnt >> 1) & 1) ^ 1);
@@ -205,8 +275,10 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
     const int half = (warp - kWarpEpi0) >> 2;
     const int dim = DIM > 0 ? DIM : p.dim;
     uint32_t acnt = 0;
-    for (int fi = 0; fi < nfaces_mine; ++fi) {
-      const int f = blockIdx.x + fi * gridDim.x;
+    for (int fi = 0; fi < ngroups_mine; ++fi) {
+      const int g = blockIdx.x + fi * gridDim.x;
+      const int f = g * p.gfaces;                          // first face: the group's tokens are contiguous in `out`
+      const int ntok = group_ntok(g), npad = (ntok + 15) & ~15;
       for (int mc = 0; mc < p.mchunks; ++mc, ++acnt) {
         const int buf = acnt & 1;
         const int d = mc * 128 + quarter * 32 + lane;      // row of the stacked [n_models*dim] weight
@@ -218,7 +290,7 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
         const uint32_t taddr = tmem_base + (uint32_t)(buf * 256) + ((uint32_t)(quarter * 32) << 16);
         // n_pad is a multiple of 16; pieces are 32 columns, the last one may be a 16-column tail
         auto issue_ld = [&](int t0, uint32_t (&v)[32]) {
-          if (t0 + 32 <= p.n_pad) {
+          if (t0 + 32 <= npad) {
             tmem_ld_32x32b_x32(taddr + (uint32_t)t0, v);
           } else {
             uint32_t lo[16];
@@ -230,27 +302,27 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
         auto emit = [&](int t0, const uint32_t (&v)[32]) {
           if (p.debug & 1) return;
           OutT* q = dst + (size_t)t0 * dim;
-          if (t0 + 32 <= p.n) {
+          if (t0 + 32 <= ntok) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) store_out(q + (size_t)j * dim, __uint_as_float(v[j]) + bias);
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (t0 + j < p.n) store_out(q + (size_t)j * dim, __uint_as_float(v[j]) + bias);
+              if (t0 + j < ntok) store_out(q + (size_t)j * dim, __uint_as_float(v[j]) + bias);
           }
         };
         uint32_t va[32], vb[32];
         int t0 = half * 32;
-        if (t0 < p.n) issue_ld(t0, va);
-        while (t0 < p.n) {
+        if (t0 < ntok) issue_ld(t0, va);
+        while (t0 < ntok) {
           tmem_ld_wait();
           const int t1 = t0 + 64;
-          if (t1 < p.n) issue_ld(t1, vb);
+          if (t1 < ntok) issue_ld(t1, vb);
           emit(t0, va);
-          if (t1 >= p.n) break;
+          if (t1 >= ntok) break;
           tmem_ld_wait();
           const int t2 = t1 + 64;
-          if (t2 < p.n) issue_ld(t2, va);
+          if (t2 < ntok) issue_ld(t2, va);
           emit(t1, vb);
           t0 = t2;
         }
@@ -264,75 +336,34 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
     const int gt = threadIdx.x - kWarpGather0 * 32;        // 0..255
     const float a_in = p.in_scale, b_in = p.in_shift, pad = p.pad_raw;
     uint32_t pcnt = 0;
-    for (int fi = 0; fi < nfaces_mine; ++fi) {
-      const int f = blockIdx.x + fi * gridDim.x;
+    for (int fi = 0; fi < ngroups_mine; ++fi) {
+      const int g = blockIdx.x + fi * gridDim.x;
+      const int nf = group_faces(g);
       const int tb = fi % NTB;
       const uint32_t tuse = (uint32_t)(fi / NTB);
+      mbar_wait(tok_empty + tb, (tuse & 1) ^ 1);           // the UMMAs of the group that used this tile are done
+     for (int ff = 0; ff < nf; ++ff) {
+      const int f = g * p.gfaces + ff;
+      const int row0 = ff * p.n;                           // first token row of this face inside the tile
       const float* th = p.theta + (size_t)f * p.n * 2;
-      mbar_wait(tok_empty + tb, (tuse & 1) ^ 1);           // the UMMAs of the face that used this tile are done
       for (int c = 0; c < kC; ++c, ++pcnt) {
         const int slot = pcnt & 1;
         mbar_wait(plane_full + slot, (pcnt >> 1) & 1);
         const InT* plane = reinterpret_cast<const InT*>(s_planes + slot * L::kPlaneSlot);
         uint8_t* tok = s_tok + tb * kTokTileBytes + c * kTokChunkBytes;
-        // item = (token t, half h): output columns j = 4h..4h+3, all 8 i  -> four 16-byte stores
-        for (int item = gt; item < ((p.debug & 2) ? 0 : 2 * p.n); item += kGatherThreads) {
-          const int t = item >> 1, h = item & 1;
-          const float2 thv = __ldg(reinterpret_cast<const float2*>(th) + t);
-          const float sx = thv.x - 4.5f, sy = thv.y - 4.5f + (float)(4 * h);
-          const float fxf = floorf(sx), fyf = floorf(sy);
-          const float wx = sx - fxf, wy = sy - fyf;
-          const int x0 = (int)fminf(fmaxf(fxf, -16.f), 128.f);
-          const int y0 = (int)fminf(fmaxf(fyf, -16.f), 128.f);
-          const bool inside = (x0 >= 0) && (x0 + 8 < kW) && (y0 >= 0) && (y0 + 4 < kH);
-          float hprev[8];
-#pragma unroll
-          for (int r = 0; r < 5; ++r) {
-            float px[9];
-            const int y = y0 + r;
-            if (inside) {
-              const int base = y * kW + x0;
-#pragma unroll
-              for (int q = 0; q < 9; ++q) px[q] = raw_pixel(plane, base + q);
-            } else {
-              const bool yok = (y >= 0) && (y < kH);
-              const int rowb = min(max(y, 0), kH - 1) * kW;
-#pragma unroll
-              for (int q = 0; q < 9; ++q) {
-                const int x = x0 + q;
-                const float v = raw_pixel(plane, rowb + min(max(x, 0), kW - 1));
-                px[q] = (yok && x >= 0 && x < kW) ? v : pad;
-              }
-            }
-            float hcur[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) hcur[i] = fmaf(wx, px[i + 1] - px[i], px[i]);
-            if (r > 0) {
-              const int j = 4 * h + r - 1;
-              uint4 pk;
-              float o[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                o[i] = fmaf(wy, hcur[i] - hprev[i], hprev[i]);
-                if (sizeof(InT) == 1) o[i] = fmaf(o[i], a_in, b_in);   // ToTensor + Normalize, after the lerp
-              }
-              pk.x = Half2Ops<__nv_bfloat16>::pack(o[0], o[1]);
-              pk.y = Half2Ops<__nv_bfloat16>::pack(o[2], o[3]);
-              pk.z = Half2Ops<__nv_bfloat16>::pack(o[4], o[5]);
-              pk.w = Half2Ops<__nv_bfloat16>::pack(o[6], o[7]);
-              *reinterpret_cast<uint4*>(tok + sw128_offset(t, j * 8)) = pk;
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) hprev[i] = hcur[i];
-          }
-        }
+        // item = (token t, block h of JB output columns j): JB+1 pixel rows -> JB 16-byte stores.
+        // JB = 4 (two items per token) keeps row reuse high when there are many tokens; with few
+        // tokens per plane (36-landmark views) JB = 1 spreads the work over all gather threads.
+        if (p.n > 64) gather_plane<InT, 4>(plane, tok, th, p.n, row0, gt, a_in, b_in, pad, p.debug);
+        else          gather_plane<InT, 1>(plane, tok, th, p.n, row0, gt, a_in, b_in, pad, p.debug);
         fence_proxy_async_smem();      // token stores -> visible to the UMMA (async proxy) reads
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(tok_full + tb * 3 + c);
+          if (ff == nf - 1) mbar_arrive(tok_full + tb * 3 + c);   // chunk c complete for every face of the group
           mbar_arrive(plane_empty + slot);
         }
       }
+     }
     }
   }
 
@@ -364,7 +395,7 @@ static int launch_embed(const CUtensorMap& tw, const EmbedParams& p, int out_dty
   constexpr int smem = pe::Layout<InT>::kSmemBytes;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   LAFS_REQUIRE(e == cudaSuccess, LAFS_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  const int grid = p.Bv < kNumSMs ? p.Bv : kNumSMs;
+  const int grid = p.ngroups < kNumSMs ? p.ngroups : kNumSMs;
   kern<<<grid, pe::kThreads, smem, st>>>(tw, p);
   return check_launch("lafs_gather_embed_fwd");
 }
@@ -405,6 +436,22 @@ extern "C" int lafs_gather_embed_fwd(const void* imgs, int in_dtype, float in_sc
   p.out[0] = out0; p.out[1] = out1;
   p.Bv = Bv; p.n = n; p.n_pad = (n + 15) & ~15; p.dim = dim; p.n_models = n_models;
   p.mchunks = n_models * dim / 128;
+  // faces per group: as many as fit the tile, traded against load balance over the 148 CTAs.
+  // cost model per CTA: rounds * (one latency-bound pass over the weights ~ 6 face-equivalents + G faces)
+  {
+    int gmax = pe::kTokRows / n < 1 ? 1 : pe::kTokRows / n;
+    if (gmax > Bv) gmax = Bv;
+    int best_g = 1;
+    long long best_cost = -1;
+    for (int g = 1; g <= gmax; ++g) {
+      const int groups = (Bv + g - 1) / g;
+      const long long rounds = (groups + kNumSMs - 1) / kNumSMs;
+      const long long cost = rounds * (6 + g);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_g = g; }
+    }
+    p.gfaces = best_g;
+  }
+  p.ngroups = (Bv + p.gfaces - 1) / p.gfaces;
   if (in_dtype == LAFS_U8) { p.in_scale = in_scale; p.in_shift = in_shift; p.pad_raw = -in_shift / in_scale; }
   else { p.in_scale = 1.f; p.in_shift = 0.f; p.pad_raw = 0.f; }
   if (const char* dbg = getenv("LAFS_PE_DEBUG")) p.debug = atoi(dbg);
