@@ -91,7 +91,7 @@ LAFS_API int lafs_dino_bwd(const void* student, const void* teacher, const float
 LAFS_API int lafs_center_ema(const float* center, const float* colsum, float count, float momentum,
                     float one_minus_momentum, int K, float* center_out, lafs_stream_t stream);
 /* Column sum over `rows` rows of x [rows,K] (torch.sum(teacher_output, dim=0),
- * lafs_train.py:674) for update_center called on its own; workspace >= 16*K*4 bytes. */
+ * lafs_train.py:674) for update_center called on its own; workspace >= 32*K*4 bytes. */
 LAFS_API int lafs_colsum(const void* x, int rows, int K, int dtype, float* out, void* workspace,
                 size_t workspace_bytes, lafs_stream_t stream);
 

@@ -69,6 +69,10 @@ __device__ __forceinline__ float lg2(float x) {
   return y;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+}
+
 // streaming 128-bit accesses (data touched once: keep it out of L1)
 __device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
   uint4 r;

@@ -15,6 +15,7 @@
 //     maxima with one REDUX each, and produces per-(sample,slice) partial statistics;
 //   * partials are merged across slices by dino_rows_finalize (deterministic, no atomics).
 // All math in fp32, exponentials in the log2 domain (ex2.approx).
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/lafs_b200.h"
 
@@ -24,7 +25,7 @@ constexpr int kDinoThreads = 256;
 constexpr int kDinoWarps = kDinoThreads / 32;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
-constexpr int kMaxGroups = 16;
+constexpr int kMaxGroups = 32;
 
 template <typename T> struct VecOf { static constexpr int VEC = 16 / sizeof(T); };
 
@@ -75,7 +76,11 @@ dino_fwd_partial(const T* __restrict__ student, const T* __restrict__ teacher,
   constexpr int NC = VEC;
   constexpr int REC = rec_floats(NCROPS);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int slice = blockIdx.x, group = blockIdx.y;
+  // The 8 warps of a CTA own 8 ADJACENT slices and walk over the same samples at the same pace, so
+  // a CTA touches 8 x 512 B = 4 KB contiguous bytes of every row it reads (DRAM page locality: with
+  // one 512 B segment per row per CTA the same kernel ran at 40 % of the HBM rate).
+  const int slice = blockIdx.x * kDinoWarps + warp, group = blockIdx.y;
+  if (slice >= nslices) return;
   const int b_lo = (int)(((long long)B * group) / ngroups);
   const int b_hi = (int)(((long long)B * (group + 1)) / ngroups);
 
@@ -93,11 +98,11 @@ dino_fwd_partial(const T* __restrict__ student, const T* __restrict__ teacher,
   // the current sample; as soon as a row has been unpacked its registers are re-filled with the
   // same row of the warp's next sample, so ncrops+2 128-bit loads stay in flight per lane.
   // Row pointers are advanced by a constant byte stride instead of being recomputed.
-  int b = b_lo + warp;
+  int b = b_lo;
   // address of (row r, this lane's columns) = base + off + r*row_bytes: one IMAD.WIDE per load,
   // `off` advanced by a constant stride per sample
   const unsigned row_bytes = (unsigned)((size_t)K * sizeof(T));
-  const size_t step = (size_t)kDinoWarps * row_bytes;
+  const size_t step = (size_t)row_bytes;
   size_t off = (size_t)b * row_bytes + (size_t)colc * sizeof(T);
   const char* tbase = reinterpret_cast<const char*>(teacher);
   const char* sbase = reinterpret_cast<const char*>(student);
@@ -111,8 +116,15 @@ dino_fwd_partial(const T* __restrict__ student, const T* __restrict__ teacher,
     for (int v = 0; v < NCROPS; ++v) rs[v] = ld_stream_u4(s_ptr(v));
   }
   off += step;   // `off` now addresses the warp's NEXT sample
-  for (; b < b_hi; b += kDinoWarps) {
-    const bool has_next = b + kDinoWarps < b_hi;
+  for (; b < b_hi; ++b) {
+    const bool has_next = b + 1 < b_hi;
+    // the register pipeline covers one iteration of latency; pull the sample after next into L2
+    if (b + 2 < b_hi) {
+#pragma unroll
+      for (int iq = 0; iq < 2; ++iq) prefetch_l2(t_ptr(iq) + step);
+#pragma unroll
+      for (int v = 0; v < NCROPS; ++v) prefetch_l2(s_ptr(v) + step);
+    }
 
     // partial record of this (sample, slice); lane 0 stores each entry as soon as it is final
     float* dst = part + ((size_t)b * nslices + slice) * REC;
@@ -190,29 +202,24 @@ dino_fwd_partial(const T* __restrict__ student, const T* __restrict__ teacher,
     off += step;
   }
 
-  // ---- column sums of this CTA's samples: reduce the 8 warps through shared memory ---------
-  __shared__ float sm[kDinoWarps][32 * NC + 1];
+  // ---- column sums of this warp's samples (each warp owns its columns: no cross-warp reduction) ----
+  if (ok) {
+    float* dstc = colsum_part + (size_t)group * K + col;
 #pragma unroll
-  for (int c = 0; c < NC; ++c) sm[warp][c * 32 + lane] = csum[c];
-  __syncthreads();
-  for (int i = threadIdx.x; i < 32 * NC; i += kDinoThreads) {
-    float acc = 0.f;
-#pragma unroll
-    for (int w = 0; w < kDinoWarps; ++w) acc += sm[w][i];
-    const int c = i >> 5, l = i & 31;
-    const int column = slice * (32 * VEC) + l * VEC + c;
-    if (column < K) colsum_part[(size_t)group * K + column] = acc;
+    for (int j = 0; j < VEC; j += 4)
+      *reinterpret_cast<float4*>(dstc + j) = make_float4(csum[j], csum[j + 1], csum[j + 2], csum[j + 3]);
   }
 }
 
 // One warp per sample: merge the slice partials, emit row statistics and the sample's loss.
+constexpr int kFinalizeWarps = 2;   // small blocks: B/2 CTAs keep every SM busy on this latency-bound merge
 template <int NCROPS>
-__global__ void __launch_bounds__(kDinoThreads)
+__global__ void __launch_bounds__(kFinalizeWarps * 32)
 dino_rows_finalize(const float* __restrict__ part, int B, int nslices, float inv_ts,
                    float* __restrict__ row_stats, float* __restrict__ sample_loss) {
   constexpr int REC = rec_floats(NCROPS);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int b = blockIdx.x * kDinoWarps + warp;
+  const int b = blockIdx.x * kFinalizeWarps + warp;
   if (b >= B) return;
   float m[2 + NCROPS], z[2 + NCROPS], a[2];
 #pragma unroll
@@ -388,9 +395,10 @@ static DinoPlan make_plan(int B, int K, int ncrops, int elem_bytes) {
   const int cap = kNumSMs * 2;
   int best = 1;
   double best_eff = 0.0;
-  const int gmax = B / kDinoWarps < 1 ? 1 : (B / kDinoWarps > kMaxGroups ? kMaxGroups : B / kDinoWarps);
+  const int gmax = B < kMaxGroups ? B : kMaxGroups;
+  const int xctas = (p.nslices + kDinoWarps - 1) / kDinoWarps;
   for (int g = 1; g <= gmax; ++g) {
-    const long long n = (long long)p.nslices * g;
+    const long long n = (long long)xctas * g;
     const long long waves = (n + cap - 1) / cap;
     const double eff = (double)n / (double)(waves * cap);
     if (eff > best_eff + 1e-9 || (eff > best_eff - 0.02 && g > best)) {
@@ -399,6 +407,10 @@ static DinoPlan make_plan(int B, int K, int ncrops, int elem_bytes) {
     }
   }
   p.ngroups = best;
+  if (const char* e = getenv("LAFS_DINO_GROUPS")) {   // development override
+    const int g = atoi(e);
+    if (g >= 1 && g <= kMaxGroups && g <= B) p.ngroups = g;
+  }
   size_t o = 0;
   p.off_part = o;   o += (size_t)B * p.nslices * rec_floats(ncrops) * sizeof(float);
   o = (o + 255) & ~(size_t)255;
@@ -416,7 +428,7 @@ static int launch_fwd(const void* student, const void* teacher, const float* cen
   float* part = reinterpret_cast<float*>(ws + p.off_part);
   float* colsum_part = reinterpret_cast<float*>(ws + p.off_colsum);
   float* sample_loss = reinterpret_cast<float*>(ws + p.off_sample);
-  dim3 grid(p.nslices, p.ngroups);
+  dim3 grid((p.nslices + kDinoWarps - 1) / kDinoWarps, p.ngroups);
   if (K % p.cols_per_slice == 0)
     dino_fwd_partial<T, NCROPS, false><<<grid, kDinoThreads, 0, st>>>(
         (const T*)student, (const T*)teacher, center, B, K, inv_ts * kLog2e, inv_tt * kLog2e,
@@ -425,7 +437,7 @@ static int launch_fwd(const void* student, const void* teacher, const float* cen
     dino_fwd_partial<T, NCROPS, true><<<grid, kDinoThreads, 0, st>>>(
         (const T*)student, (const T*)teacher, center, B, K, inv_ts * kLog2e, inv_tt * kLog2e,
         p.nslices, p.ngroups, part, colsum_part);
-  dino_rows_finalize<NCROPS><<<(B + kDinoWarps - 1) / kDinoWarps, kDinoThreads, 0, st>>>(
+  dino_rows_finalize<NCROPS><<<(B + kFinalizeWarps - 1) / kFinalizeWarps, kFinalizeWarps * 32, 0, st>>>(
       part, B, p.nslices, inv_ts, row_stats, sample_loss);
   const float inv_norm = 1.f / ((float)(2 * NCROPS - 2) * (float)B);
   dino_tail<<<(K + kDinoThreads - 1) / kDinoThreads, kDinoThreads, 0, st>>>(

@@ -104,7 +104,7 @@ class DINOLoss(nn.Module):
         else:
             t = teacher_output.detach().contiguous()
             colsum = torch.empty(K, dtype=torch.float32, device=t.device)
-            nbytes = 16 * K * 4
+            nbytes = 32 * K * 4
             ws = _workspace(t.device, nbytes)
             _lib.call("lafs_colsum", t.data_ptr(), t.shape[0], K, _lib.dtype_code(t), colsum.data_ptr(),
                       ws.data_ptr(), nbytes, _lib.stream())
