@@ -37,7 +37,14 @@ int bind_device_of(const void* device_ptr) {
       return LAFS_ERR_CUDA;
     }
   }
-  cudaFree(0);  // force the primary context current on this thread (driver entry points need it)
+  // force the primary context current on this thread once (driver entry points such as the TMA
+  // descriptor encoder need it); never again, so that entry points stay legal inside a CUDA-graph
+  // stream capture (cudaFree invalidates a capture)
+  static thread_local int bound_device = -1;
+  if (bound_device != a.device) {
+    cudaFree(0);
+    bound_device = a.device;
+  }
   return LAFS_OK;
 }
 }  // namespace lafs

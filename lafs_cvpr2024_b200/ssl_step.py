@@ -65,3 +65,46 @@ class SSLHotPath:
 
     def ema_step(self, m):
         self.ema.step(m)
+
+
+class GraphedSSLStep:
+    """The whole hot-path step captured once into a CUDA graph and replayed with a single launch
+    (15 kernels -> 1 graph launch; the inputs live in static device buffers that the caller
+    refreshes, e.g. with copy_ from pinned host memory on a copy stream).
+
+    Static inputs : img_g, img_l (uint8 or fp32), raw_g, raw_l, noise_g, noise_l, idx_l,
+                    student_out, teacher_out.   Outputs: loss (0-dim), grad_student, the three
+    embedded-token tensors.  The DINO centre is kept in a static buffer and updated in place at the
+    end of the graph (the loss and its backward inside the graph still see the old centre, Q7)."""
+
+    def __init__(self, path: SSLHotPath, static_inputs: dict, epoch: int, momentum: float):
+        self.path, self.inp = path, static_inputs
+        self.center = path.loss.center.detach().clone().contiguous()
+        self.graph = torch.cuda.CUDAGraph()
+        self.out = {}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                 # warm-up outside capture (lazy init, workspaces)
+            for _ in range(2):
+                self._body(epoch, momentum)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(self.graph):
+            self._body(epoch, momentum)
+
+    def _body(self, epoch, momentum):
+        p, i = self.path, self.inp
+        p.loss.center = self.center
+        s_g, t_g, s_l = p.landmarks_and_embeddings(i["raw_g"], i["noise_g"], i["img_g"], i["raw_l"], i["noise_l"],
+                                                   i["idx_l"], i["img_l"])
+        s = i["student_out"].detach().requires_grad_(True)
+        loss = p.loss(s, i["teacher_out"], epoch)
+        (grad,) = torch.autograd.grad(loss, s)
+        self.center.copy_(p.loss.center)              # static centre buffer <- re-bound new centre
+        p.loss.center = self.center
+        p.ema_step(momentum)
+        self.out = {"loss": loss.detach(), "grad_student": grad, "s_g": s_g, "t_g": t_g, "s_l": s_l}
+
+    def replay(self):
+        self.graph.replay()
+        return self.out["loss"]
