@@ -38,6 +38,7 @@ class EmaPlan:
             for off in range(0, n, _lib.EMA_CHUNK):
                 recs.append((kp + 4 * off, qp + 4 * off, min(_lib.EMA_CHUNK, n - off)))
         self.nchunks = len(recs)
+        self._keep = (ks, qs)            # the table holds raw pointers: keep the tensors alive
         self.key = self.make_key(ks, qs)
         dev = ks[0].device if ks else torch.device("cuda")
         table = np.array(recs, dtype=_REC)
