@@ -51,10 +51,13 @@ LAFS_API int lafs_device_ok(void);
  * each describing a contiguous run of one fp32 tensor pair.  Arithmetic is
  *   k = fl(fl(k*m) + fl(q*one_minus_m))   -- three separately rounded fp32 operations,
  * bit-identical to the reference (m and 1-m are rounded to fp32 by the caller from the
- * float64 schedule value, as PyTorch does).
+ * float64 schedule value, as PyTorch does).  max_ctas <= 0: one CTA per chunk (fastest when the
+ * kernel runs alone); max_ctas > 0: that many persistent CTAs (e.g. 148 = one per SM) so that the
+ * kernel can run concurrently with another one on a second stream.
  */
 #define LAFS_EMA_CHUNK 16384
-LAFS_API int lafs_ema_multi(const void* table, int nchunks, float m, float one_minus_m, lafs_stream_t stream);
+LAFS_API int lafs_ema_multi(const void* table, int nchunks, float m, float one_minus_m, int max_ctas,
+                            lafs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * (2) DINO loss  --  replaces DINOLoss.forward / update_center  lafs_train.py:643-679

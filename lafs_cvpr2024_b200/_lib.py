@@ -24,7 +24,7 @@ SIGNATURES = {
     "lafs_version": (_i, []),
     "lafs_last_error_string": (C.c_char_p, []),
     "lafs_device_ok": (_i, []),
-    "lafs_ema_multi": (_i, [_p, _i, _f, _f, _p]),
+    "lafs_ema_multi": (_i, [_p, _i, _f, _f, _i, _p]),
     "lafs_dino_workspace_bytes": (_z, [_i, _i, _i]),
     "lafs_dino_fwd": (_i, [_p, _p, _p, _i, _i, _i, _f, _f, _i, _p, _p, _p, _p, _z, _p]),
     "lafs_dino_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _i, _p, _p]),

@@ -20,9 +20,12 @@ __device__ __forceinline__ float ema1(float k, float q, float m, float om) {
   return __fadd_rn(__fmul_rn(k, m), __fmul_rn(q, om));
 }
 
+// grid == nchunks: one chunk per CTA.  grid < nchunks: persistent CTAs stride over the chunks -- used
+// to co-schedule the EMA next to a kernel that leaves HBM bandwidth unused (one 256-thread CTA per SM).
 __global__ void __launch_bounds__(kEmaThreads)
-ema_multi_kernel(const EmaChunk* __restrict__ table, float m, float om) {
-  const EmaChunk c = table[blockIdx.x];
+ema_multi_kernel(const EmaChunk* __restrict__ table, int nchunks, float m, float om) {
+ for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+  const EmaChunk c = table[chunk];
   const int n = (int)c.n;
   float* __restrict__ k = c.k;
   const float* __restrict__ q = c.q;
@@ -61,17 +64,19 @@ ema_multi_kernel(const EmaChunk* __restrict__ table, float m, float om) {
   } else {
     for (int j = threadIdx.x; j < n; j += kEmaThreads) k[j] = ema1(k[j], q[j], m, om);
   }
+ }
 }
 
 }  // namespace lafs
 
-extern "C" int lafs_ema_multi(const void* table, int nchunks, float m, float one_minus_m,
+extern "C" int lafs_ema_multi(const void* table, int nchunks, float m, float one_minus_m, int max_ctas,
                               lafs_stream_t stream) {
   if (int brc = lafs::bind_device_of(table)) return brc;
   using namespace lafs;
   if (nchunks == 0) return LAFS_OK;
   LAFS_REQUIRE(table != nullptr && nchunks > 0, LAFS_ERR_ARG, "lafs_ema_multi: null table or nchunks<0");
-  ema_multi_kernel<<<nchunks, kEmaThreads, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const EmaChunk*>(table), m, one_minus_m);
+  const int grid = (max_ctas > 0 && max_ctas < nchunks) ? max_ctas : nchunks;
+  ema_multi_kernel<<<grid, kEmaThreads, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const EmaChunk*>(table), nchunks, m, one_minus_m);
   return check_launch("lafs_ema_multi");
 }

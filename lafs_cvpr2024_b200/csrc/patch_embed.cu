@@ -311,20 +311,13 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
               if (t0 + j < ntok) store_out(q + (size_t)j * dim, __uint_as_float(v[j]) + bias);
           }
         };
-        uint32_t va[32], vb[32];
-        int t0 = half * 32;
-        if (t0 < ntok) issue_ld(t0, va);
-        while (t0 < ntok) {
+        // (software-pipelining the TMEM loads over two register sets bought nothing and cost 24
+        //  registers per thread, which matter for co-residency with the EMA kernel)
+        for (int t0 = half * 32; t0 < ntok; t0 += 64) {
+          uint32_t v[32];
+          issue_ld(t0, v);
           tmem_ld_wait();
-          const int t1 = t0 + 64;
-          if (t1 < ntok) issue_ld(t1, vb);
-          emit(t0, va);
-          if (t1 >= ntok) break;
-          tmem_ld_wait();
-          const int t2 = t1 + 64;
-          if (t2 < ntok) issue_ld(t2, va);
-          emit(t1, vb);
-          t0 = t2;
+          emit(t0, v);
         }
         tc_fence_before();
         __syncwarp();

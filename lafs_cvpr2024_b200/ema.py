@@ -48,13 +48,14 @@ class EmaPlan:
     def make_key(ks, qs):
         return tuple((k.data_ptr(), q.data_ptr(), k.numel()) for k, q in zip(ks, qs))
 
-    def step(self, m):
+    def step(self, m, max_ctas=0):
+        """max_ctas > 0: persistent launch with that many CTAs (co-scheduling next to another kernel)."""
         if self.nchunks == 0:
             return
         m = float(m)
         # PyTorch rounds the python/numpy float64 scalars m and (1-m) to fp32 separately
         _lib.call("lafs_ema_multi", self.table.data_ptr(), self.nchunks,
-                  float(np.float32(m)), float(np.float32(1.0 - m)), _lib.stream())
+                  float(np.float32(m)), float(np.float32(1.0 - m)), int(max_ctas), _lib.stream())
 
 
 _plans = {}

@@ -45,12 +45,13 @@ class SSLHotPath:
         tok_l = extract_tokens(img_l, theta_l)
         return theta_g, tok_g, theta_l, tok_l
 
-    def landmarks_and_embeddings(self, raw_g, noise_g, img_g, raw_l, noise_l, idx_l, img_l):
+    def landmarks_and_embeddings(self, raw_g, noise_g, img_g, raw_l, noise_l, idx_l, img_l, refresh=True):
         """Fused form: landmark tail, then gather -> patch_to_embedding on the tensor cores.
         Returns (student_global, teacher_global, student_local) embedded tokens (bf16); the
         patch mosaics / token tensors of the reference are never materialised."""
-        self.embed_global.refresh()        # weights moved by the optimizer / EMA since last step
-        self.embed_local.refresh()
+        if refresh:
+            self.embed_global.refresh()    # weights moved by the optimizer / EMA since last step
+            self.embed_local.refresh()
         theta_g = landmark_post(raw_g, noise_g)
         s_g, t_g = gather_embed(img_g, theta_g, self.embed_global)
         theta_l = landmark_post(raw_l, noise_l, idx_l)
@@ -63,8 +64,8 @@ class SSLHotPath:
         loss.backward()
         return loss.detach(), s.grad
 
-    def ema_step(self, m):
-        self.ema.step(m)
+    def ema_step(self, m, max_ctas=0):
+        self.ema.step(m, max_ctas)
 
 
 class GraphedSSLStep:
@@ -77,8 +78,14 @@ class GraphedSSLStep:
     embedded-token tensors.  The DINO centre is kept in a static buffer and updated in place at the
     end of the graph (the loss and its backward inside the graph still see the old centre, Q7)."""
 
-    def __init__(self, path: SSLHotPath, static_inputs: dict, epoch: int, momentum: float):
+    def __init__(self, path: SSLHotPath, static_inputs: dict, epoch: int, momentum: float, overlap_ema=True, ema_ctas=444):
+        """overlap_ema: put the teacher EMA on a second captured stream so that it runs concurrently
+        with the gather->embed / DINO kernels (read-heavy EMA + write-heavy token stores share HBM
+        better than either alone; in a training loop this is EMA(step i) under gather(step i+1))."""
         self.path, self.inp = path, static_inputs
+        self.overlap_ema = overlap_ema
+        self.ema_ctas = ema_ctas
+        self.side = torch.cuda.Stream()
         self.center = path.loss.center.detach().clone().contiguous()
         self.graph = torch.cuda.CUDAGraph()
         self.out = {}
@@ -95,14 +102,26 @@ class GraphedSSLStep:
     def _body(self, epoch, momentum):
         p, i = self.path, self.inp
         p.loss.center = self.center
+        main = torch.cuda.current_stream()
+        if self.overlap_ema:
+            # the EMA reads the teacher's patch_to_embedding weights that the weight-prep kernels
+            # also read, and writes them: run the prep first, then fork
+            p.embed_global.refresh()
+            p.embed_local.refresh()
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side):
+                p.ema_step(momentum, max_ctas=self.ema_ctas)
         s_g, t_g, s_l = p.landmarks_and_embeddings(i["raw_g"], i["noise_g"], i["img_g"], i["raw_l"], i["noise_l"],
-                                                   i["idx_l"], i["img_l"])
+                                                   i["idx_l"], i["img_l"], refresh=not self.overlap_ema)
         s = i["student_out"].detach().requires_grad_(True)
         loss = p.loss(s, i["teacher_out"], epoch)
         (grad,) = torch.autograd.grad(loss, s)
         self.center.copy_(p.loss.center)              # static centre buffer <- re-bound new centre
         p.loss.center = self.center
-        p.ema_step(momentum)
+        if self.overlap_ema:
+            main.wait_stream(self.side)
+        else:
+            p.ema_step(momentum)
         self.out = {"loss": loss.detach(), "grad_student": grad, "s_g": s_g, "t_g": t_g, "s_l": s_l}
 
     def replay(self):

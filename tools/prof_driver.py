@@ -13,10 +13,12 @@ from lafs_cvpr2024_b200 import _lib  # noqa: E402
 mode = sys.argv[1]
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 torch.manual_seed(0)
-if mode in ("pe_global", "pe_local"):
-    g = mode == "pe_global"
+if mode in ("pe_global", "pe_local", "pe_global_u8"):
+    g = mode != "pe_local"
     Bv, n = (512, 196) if g else (1024, 36)
     imgs = torch.rand(Bv, 3, 112, 112, device="cuda") * 2 - 1
+    if mode == "pe_global_u8":
+        imgs = torch.randint(0, 256, (Bv, 3, 112, 112), dtype=torch.uint8, device="cuda")
     th = torch.rand(Bv, n, 2, device="cuda") * 111
     a, b = torch.nn.Linear(192, 768).cuda(), torch.nn.Linear(192, 768).cuda()
     w = P.PatchEmbedWeights([(a.weight, a.bias), (b.weight, b.bias)] if g else [(a.weight, a.bias)])
