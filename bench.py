@@ -216,7 +216,6 @@ def run_ours(args):
     if sampler:
         sampler.start()
     ms_total, parts = timed(lambda i, ev: step(dev_in, args.warmup + i, ev), args.steps, per_kernel=True)
-    clocks = sampler.stop() if sampler else None
     # the same 15-kernel step captured into ONE CUDA graph and replayed (static device buffers):
     # this is the device-resident headline `value`; the eager run above gives the per-kernel split
     ginp = dict(dev_in, raw_g=st["raw_g"], raw_l=st["raw_l"], student_out=st["student_out"], teacher_out=st["teacher_out"])
@@ -278,7 +277,7 @@ def run_ours(args):
 
     ms_e2e, h2d = run_e2e(host)
     ms_e2e_f32, h2d_f32 = run_e2e(host_f32)
-    stage = None
+    clocks = sampler.stop() if sampler else None    # sampled across every timed region above
 
     # ---- secondary: class-sharded margin head (BASELINE configs[2], configs[3]) -----------------
     del st, path, dev_in
