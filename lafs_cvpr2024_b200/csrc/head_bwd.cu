@@ -24,7 +24,9 @@ constexpr int kStageA = kBM * kBK * 2;      // 16 KB
 constexpr int kStageB = kBN * kBK * 2;      // 32 KB
 constexpr int kStages = 4;
 constexpr int kThreads = 192;
-constexpr int kSmem = kStages * (kStageA + kStageB) + 1024 + 256;
+constexpr int kPitch = 36;                              // floats per staged row (144 B: 16-byte aligned, conflict-free)
+constexpr int kStageOut = 4 * 32 * kPitch * 4;          // per epilogue warp a [32 x 32] fp32 block: 18,432 B total
+constexpr int kSmem = kStages * (kStageA + kStageB) + kStageOut + 1024 + 256;
 }  // namespace gb
 
 // MN-major SW128 descriptor: LBO = distance between 64-element MN blocks, SBO = 1024 B
@@ -54,7 +56,8 @@ gemm_bwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* s_a = smem;
   uint8_t* s_b = smem + kStages * kStageA;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_b + kStages * kStageB);
+  float* s_out = reinterpret_cast<float*>(s_b + kStages * kStageB);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_b + kStages * kStageB + kStageOut);
   uint64_t* full = bars;                 // kStages
   uint64_t* empty = bars + kStages;      // kStages
   uint64_t* acc_full = bars + 2 * kStages;      // 2
@@ -144,30 +147,44 @@ gemm_bwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int mn = tile / p.splits;
       const int nt = mn % p.n_tiles, mt = mn / p.n_tiles;
       const int buf = acnt & 1;
-      const int row = mt * kBM + quarter * 32 + lane;
       mbar_wait(acc_full + buf, (acnt >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(buf * kBN) + ((uint32_t)(quarter * 32) << 16);
-      float* dst = p.out + (size_t)split * p.split_stride + (size_t)row * p.ldo + (size_t)nt * kBN;
+      // lane = output row in TMEM, but rows are ldo floats apart in memory: transpose each
+      // [32 rows x 32 cols] block through shared memory so that a warp-wide store writes four full
+      // 128-byte row segments instead of 32 scattered 16-byte pieces
+      float* stage = s_out + quarter * (32 * kPitch);
+      const int row_base = mt * kBM + quarter * 32;
+      float* dst0 = p.out + (size_t)split * p.split_stride + (size_t)nt * kBN;
 #pragma unroll 1
       for (int piece = 0; piece < kBN / 32; ++piece) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + (uint32_t)(piece * 32), v);
         tmem_ld_wait();
         const int c0 = nt * kBN + piece * 32;
-        if (row < p.M && c0 < p.N) {
-          if (c0 + 32 <= p.N) {
+        if (c0 >= p.N) break;                       // warp-uniform
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(dst + piece * 32 + j) =
-                  make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                              __uint_as_float(v[j + 3]));
-          } else {
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(stage + lane * kPitch + j) =
+              make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                          __uint_as_float(v[j + 3]));
+        __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c0 + j < p.N) dst[piece * 32 + j] = __uint_as_float(v[j]);
+        for (int r8 = 0; r8 < 8; ++r8) {
+          const int rr = r8 * 4 + (lane >> 3), part = lane & 7;       // 8 lanes cover one 128-byte row segment
+          const float4 val = *reinterpret_cast<const float4*>(stage + rr * kPitch + part * 4);
+          const int grow = row_base + rr, gcol = c0 + part * 4;
+          if (grow < p.M) {
+            float* d = dst0 + (size_t)grow * p.ldo + piece * 32 + part * 4;
+            if (gcol + 4 <= p.N) *reinterpret_cast<float4*>(d) = val;
+            else {
+              if (gcol < p.N) d[0] = val.x;
+              if (gcol + 1 < p.N) d[1] = val.y;
+              if (gcol + 2 < p.N) d[2] = val.z;
+            }
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
