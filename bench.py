@@ -381,22 +381,49 @@ def bench_head(P, world, rank, dev, dist, args):
         for _ in range(3):
             step()
         iters = max(5, min(args.steps, 20))
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(iters):
-            step()
-        e1.record()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1) / iters], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        out[name] = {"B_global": B, "classes": C, "D": D, "shards": world, "ms_fwd_bwd": round(ms, 4),
+
+        def time_it(fn):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / iters], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        ms_eager = time_it(step)
+        # the same step (kernels + NCCL exchanges) as one CUDA graph: at 8 shards the per-rank GEMMs are
+        # a few tens of microseconds and launch latency dominates the eager number
+        ms = ms_eager
+        mode = "eager"
+        try:
+            graph = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(graph):
+                step()
+            for _ in range(3):
+                graph.replay()
+            ms = time_it(graph.replay)
+            mode = "cuda_graph"
+            del graph
+        except Exception as e:  # capture not possible on this stack: keep the eager number
+            mode = "eager (graph capture failed: %s)" % str(e).splitlines()[0][:80]
+            torch.cuda.synchronize()
+        out[name] = {"B_global": B, "classes": C, "D": D, "shards": world, "ms_fwd_bwd": round(ms, 4), "launch": mode,
+                     "ms_fwd_bwd_eager": round(ms_eager, 4),
                      "faces_per_s": round(B / ms * 1e3, 1), "TFLOPs_6BCD": round(6.0 * B * C * D / ms / 1e9 / world, 1),
                      "note": "TFLOPs per GPU on the 6*B*C*D/R count; the step also recomputes the logits once (8*B*C*D issued)"}
         del h, x
