@@ -73,6 +73,8 @@ LAFS_API int lafs_ema_multi(const void* table, int nchunks, float m, float one_m
  *              by the 2*B teacher rows (consumed by lafs_dino_bwd)
  *   colsum_out [K]  fp32   sum over the 2*B teacher rows (the message of the reference's
  *              dist.all_reduce, lafs_train.py:674-675)
+ * center_out (may be NULL): single-process shortcut -- also writes the updated centre
+ *   center*momentum + (colsum/(2B))*(1-momentum) in the same pass (no all-reduce needed).
  * The result is deterministic (no floating-point atomics).
  * K must be a multiple of 8 (16-bit dtypes) or 4 (fp32); 2 <= ncrops <= 12.
  */
@@ -80,7 +82,8 @@ LAFS_API size_t lafs_dino_workspace_bytes(int B, int K, int ncrops);
 LAFS_API int lafs_dino_fwd(const void* student, const void* teacher, const float* center, int B, int K,
                   int ncrops, float inv_student_temp, float inv_teacher_temp, int dtype,
                   float* loss_out, float* row_stats, float* colsum_out, void* workspace,
-                  size_t workspace_bytes, lafs_stream_t stream);
+                  size_t workspace_bytes, float* center_out, float momentum, float one_minus_momentum,
+                  lafs_stream_t stream);
 /* grad_student[v*B+b, k] = grad_out * d loss / d student; grad_out is a device scalar
  * (the upstream gradient; autograd hands it over on the device). */
 LAFS_API int lafs_dino_bwd(const void* student, const void* teacher, const float* center,

@@ -26,7 +26,7 @@ SIGNATURES = {
     "lafs_device_ok": (_i, []),
     "lafs_ema_multi": (_i, [_p, _i, _f, _f, _i, _p]),
     "lafs_dino_workspace_bytes": (_z, [_i, _i, _i]),
-    "lafs_dino_fwd": (_i, [_p, _p, _p, _i, _i, _i, _f, _f, _i, _p, _p, _p, _p, _z, _p]),
+    "lafs_dino_fwd": (_i, [_p, _p, _p, _i, _i, _i, _f, _f, _i, _p, _p, _p, _p, _z, _p, _f, _f, _p]),
     "lafs_dino_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _i, _p, _p]),
     "lafs_center_ema": (_i, [_p, _p, _f, _f, _f, _i, _p, _p]),
     "lafs_colsum": (_i, [_p, _i, _i, _i, _p, _p, _z, _p]),

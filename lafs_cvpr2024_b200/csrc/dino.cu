@@ -213,46 +213,50 @@ dino_fwd_partial(const T* __restrict__ student, const T* __restrict__ teacher,
 
 // One warp per sample: merge the slice partials, emit row statistics and the sample's loss.
 constexpr int kFinalizeWarps = 2;   // small blocks: B/2 CTAs keep every SM busy on this latency-bound merge
+// One warp per sample: merge the slice partials, emit row statistics and the sample's loss.
+// Two passes over the (L1-resident) records: global maxima first, then sums rescaled to them --
+// independent FMAs instead of a serial online-softmax chain.
 template <int NCROPS>
 __global__ void __launch_bounds__(kFinalizeWarps * 32)
 dino_rows_finalize(const float* __restrict__ part, int B, int nslices, float inv_ts,
                    float* __restrict__ row_stats, float* __restrict__ sample_loss) {
   constexpr int REC = rec_floats(NCROPS);
+  constexpr int NR = 2 + NCROPS;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.x * kFinalizeWarps + warp;
   if (b >= B) return;
-  float m[2 + NCROPS], z[2 + NCROPS], a[2];
+  const float* base = part + (size_t)b * nslices * REC;
+  float m[NR];
 #pragma unroll
-  for (int i = 0; i < 2 + NCROPS; ++i) { m[i] = -INFINITY; z[i] = 0.f; }
+  for (int i = 0; i < NR; ++i) m[i] = -INFINITY;
+  for (int s = lane; s < nslices; s += 32) {
+    const float* r = base + (size_t)s * REC;
+    m[0] = fmaxf(m[0], r[0]);
+    m[1] = fmaxf(m[1], r[3]);
+#pragma unroll
+    for (int v = 0; v < NCROPS; ++v) m[2 + v] = fmaxf(m[2 + v], r[6 + 2 * v]);
+  }
+#pragma unroll
+  for (int i = 0; i < NR; ++i) m[i] = warp_max(m[i]);
+  float z[NR], a[2];
+#pragma unroll
+  for (int i = 0; i < NR; ++i) z[i] = 0.f;
   a[0] = a[1] = 0.f;
   for (int s = lane; s < nslices; s += 32) {
-    const float* r = part + ((size_t)b * nslices + s) * REC;
+    const float* r = base + (size_t)s * REC;
 #pragma unroll
     for (int iq = 0; iq < 2; ++iq) {
-      const float ms = r[3 * iq], zs = r[3 * iq + 1], as = r[3 * iq + 2];
-      const float mn = fmaxf(m[iq], ms);
-      const float f_old = ex2(m[iq] - mn), f_new = ex2(ms - mn);  // ex2(-inf) = 0
-      z[iq] = z[iq] * f_old + zs * f_new;
-      a[iq] = a[iq] * f_old + as * f_new;
-      m[iq] = mn;
+      const float f = ex2(r[3 * iq] - m[iq]);
+      z[iq] = fmaf(r[3 * iq + 1], f, z[iq]);
+      a[iq] = fmaf(r[3 * iq + 2], f, a[iq]);
     }
 #pragma unroll
-    for (int v = 0; v < NCROPS; ++v) {
-      const float ms = r[6 + 2 * v], zs = r[7 + 2 * v];
-      const float mn = fmaxf(m[2 + v], ms);
-      z[2 + v] = z[2 + v] * ex2(m[2 + v] - mn) + zs * ex2(ms - mn);
-      m[2 + v] = mn;
-    }
+    for (int v = 0; v < NCROPS; ++v) z[2 + v] = fmaf(r[7 + 2 * v], ex2(r[6 + 2 * v] - m[2 + v]), z[2 + v]);
   }
-  // butterfly merge across lanes (lanes without slices carry m=-inf, z=0)
 #pragma unroll
-  for (int i = 0; i < 2 + NCROPS; ++i) {
-    const float mw = warp_max(m[i]);
-    const float f = (m[i] == -INFINITY) ? 0.f : ex2(m[i] - mw);
-    z[i] = warp_sum(z[i] * f);
-    if (i < 2) a[i] = warp_sum(a[i] * f);
-    m[i] = mw;
-  }
+  for (int i = 0; i < NR; ++i) z[i] = warp_sum(z[i]);
+  a[0] = warp_sum(a[0]);
+  a[1] = warp_sum(a[1]);
   if (lane == 0) {
     float loss = 0.f;
 #pragma unroll
@@ -274,12 +278,17 @@ dino_rows_finalize(const float* __restrict__ part, int B, int nslices, float inv
 // block 0: fixed-order sum of the per-sample losses; all blocks: merge column-sum partials.
 __global__ void __launch_bounds__(kDinoThreads)
 dino_tail(const float* __restrict__ sample_loss, int B, float inv_norm, float* __restrict__ loss_out,
-          const float* __restrict__ colsum_part, int ngroups, int K, float* __restrict__ colsum_out) {
+          const float* __restrict__ colsum_part, int ngroups, int K, float* __restrict__ colsum_out,
+          const float* __restrict__ center, float* __restrict__ center_out, float count, float mom, float om) {
   const int k = blockIdx.x * kDinoThreads + threadIdx.x;
   if (k < K) {
     float acc = 0.f;
     for (int g = 0; g < ngroups; ++g) acc += colsum_part[(size_t)g * K + k];
     colsum_out[k] = acc;
+    // single-process case: the centre EMA (lafs_train.py:676-679) rides along (same arithmetic as
+    // center_ema_kernel); with several ranks the caller all-reduces colsum first
+    if (center_out != nullptr)
+      center_out[k] = __fadd_rn(__fmul_rn(center[k], mom), __fmul_rn(__fdiv_rn(acc, count), om));
   }
   if (blockIdx.x == 0) {
     __shared__ float red[kDinoThreads];
@@ -424,7 +433,8 @@ static DinoPlan make_plan(int B, int K, int ncrops, int elem_bytes) {
 template <typename T, int NCROPS>
 static int launch_fwd(const void* student, const void* teacher, const float* center, int B, int K,
                       float inv_ts, float inv_tt, float* loss_out, float* row_stats,
-                      float* colsum_out, char* ws, const DinoPlan& p, cudaStream_t st) {
+                      float* colsum_out, char* ws, const DinoPlan& p, cudaStream_t st,
+                      float* center_out, float mom, float om) {
   float* part = reinterpret_cast<float*>(ws + p.off_part);
   float* colsum_part = reinterpret_cast<float*>(ws + p.off_colsum);
   float* sample_loss = reinterpret_cast<float*>(ws + p.off_sample);
@@ -441,7 +451,8 @@ static int launch_fwd(const void* student, const void* teacher, const float* cen
       part, B, p.nslices, inv_ts, row_stats, sample_loss);
   const float inv_norm = 1.f / ((float)(2 * NCROPS - 2) * (float)B);
   dino_tail<<<(K + kDinoThreads - 1) / kDinoThreads, kDinoThreads, 0, st>>>(
-      sample_loss, B, inv_norm, loss_out, colsum_part, p.ngroups, K, colsum_out);
+      sample_loss, B, inv_norm, loss_out, colsum_part, p.ngroups, K, colsum_out, center, center_out,
+      (float)(2 * B), mom, om);
   return check_launch("lafs_dino_fwd");
 }
 
@@ -485,7 +496,8 @@ static int dino_check(const void* s, const void* t, const float* c, int B, int K
 extern "C" int lafs_dino_fwd(const void* student, const void* teacher, const float* center, int B, int K,
                              int ncrops, float inv_student_temp, float inv_teacher_temp, int dtype,
                              float* loss_out, float* row_stats, float* colsum_out, void* workspace,
-                             size_t workspace_bytes, lafs_stream_t stream) {
+                             size_t workspace_bytes, float* center_out, float momentum,
+                             float one_minus_momentum, lafs_stream_t stream) {
   if (int brc = lafs::bind_device_of(student)) return brc;
   using namespace lafs;
   int rc = dino_check(student, teacher, center, B, K, ncrops, dtype, "lafs_dino_fwd");
@@ -501,12 +513,15 @@ extern "C" int lafs_dino_fwd(const void* student, const void* teacher, const flo
   case N:                                                                                                \
     if (dtype == LAFS_F32)                                                                               \
       return launch_fwd<float, N>(student, teacher, center, B, K, inv_student_temp, inv_teacher_temp,    \
-                                  loss_out, row_stats, colsum_out, ws, p, st);                           \
+                                  loss_out, row_stats, colsum_out, ws, p, st, center_out, momentum,       \
+                                  one_minus_momentum);                                                   \
     if (dtype == LAFS_BF16)                                                                              \
       return launch_fwd<__nv_bfloat16, N>(student, teacher, center, B, K, inv_student_temp,              \
-                                          inv_teacher_temp, loss_out, row_stats, colsum_out, ws, p, st); \
+                                          inv_teacher_temp, loss_out, row_stats, colsum_out, ws, p, st,  \
+                                          center_out, momentum, one_minus_momentum);                     \
     return launch_fwd<__half, N>(student, teacher, center, B, K, inv_student_temp, inv_teacher_temp,     \
-                                 loss_out, row_stats, colsum_out, ws, p, st);
+                                 loss_out, row_stats, colsum_out, ws, p, st, center_out, momentum,       \
+                                 one_minus_momentum);
   switch (ncrops) { LAFS_DINO_CROPS(LAFS_CASE) }
 #undef LAFS_CASE
   return LAFS_ERR_ARG;

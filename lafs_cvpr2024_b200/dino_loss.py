@@ -24,7 +24,7 @@ def _workspace(dev, nbytes):
 
 class _DinoLossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, student, teacher, center, ncrops, inv_ts, inv_tt, stash):
+    def forward(ctx, student, teacher, center, ncrops, inv_ts, inv_tt, stash, momentum):
         _lib.require_cuda(student, teacher, center)
         if student.dim() != 2 or teacher.dim() != 2:
             raise ValueError("student_output / teacher_output must be 2-D [rows, out_dim]")
@@ -46,12 +46,20 @@ class _DinoLossFn(torch.autograd.Function):
         if nbytes == 0:
             raise ValueError(f"unsupported DINO shape B={B} K={K} ncrops={ncrops}")
         ws = _workspace(dev, nbytes)
+        # one process: the centre EMA is produced by the same launch (no all-reduce in between)
+        new_center = None
+        if momentum is not None:
+            new_center = torch.empty(1, K, dtype=torch.float32, device=dev)
+        mom = float(np.float32(momentum)) if momentum is not None else 0.0
+        om = float(np.float32(1.0 - momentum)) if momentum is not None else 0.0
         _lib.call("lafs_dino_fwd", s.data_ptr(), t.data_ptr(), c.data_ptr(), B, K, ncrops,
                   float(inv_ts), float(inv_tt), _lib.dtype_code(s), loss.data_ptr(),
-                  row_stats.data_ptr(), colsum.data_ptr(), ws.data_ptr(), nbytes, _lib.stream())
+                  row_stats.data_ptr(), colsum.data_ptr(), ws.data_ptr(), nbytes, _lib.ptr(new_center), mom, om,
+                  _lib.stream())
         ctx.save_for_backward(s, t, c, row_stats)
         ctx.meta = (B, K, ncrops, float(inv_ts), float(inv_tt))
         if stash is not None:
+            stash["new_center"] = new_center
             stash["colsum"] = colsum
             stash["teacher"] = (teacher.data_ptr(), teacher._version, tuple(teacher.shape))
         ctx.mark_non_differentiable(colsum)
@@ -66,7 +74,7 @@ class _DinoLossFn(torch.autograd.Function):
         _lib.call("lafs_dino_bwd", s.data_ptr(), t.data_ptr(), c.data_ptr(), row_stats.data_ptr(),
                   g.data_ptr(), B, K, ncrops, inv_ts, inv_tt, _lib.dtype_code(s), grad_s.data_ptr(),
                   _lib.stream())
-        return grad_s, None, None, None, None, None, None
+        return grad_s, None, None, None, None, None, None, None
 
 
 class DINOLoss(nn.Module):
@@ -87,8 +95,10 @@ class DINOLoss(nn.Module):
 
     def forward(self, student_output, teacher_output, epoch):
         temp = self.teacher_temp_schedule[epoch]
+        single = not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
         loss, _ = _DinoLossFn.apply(student_output, teacher_output, self.center, self.ncrops,
-                                    1.0 / self.student_temp, 1.0 / float(temp), self._stash)
+                                    1.0 / self.student_temp, 1.0 / float(temp), self._stash,
+                                    float(self.center_momentum) if single else None)
         self.update_center(teacher_output)
         return loss
 
@@ -101,6 +111,10 @@ class DINOLoss(nn.Module):
         if self._stash.get("teacher") == tag:
             colsum = self._stash.pop("colsum")       # by-product of forward: no extra pass
             self._stash.pop("teacher", None)
+            new_center = self._stash.pop("new_center", None)
+            if new_center is not None:               # single process: already computed in the same launch
+                self.center = new_center
+                return
         else:
             t = teacher_output.detach().contiguous()
             colsum = torch.empty(K, dtype=torch.float32, device=t.device)

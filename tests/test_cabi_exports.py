@@ -42,7 +42,7 @@ def test_argument_errors_without_gpu(lib):
     assert h.lafs_dino_workspace_bytes(256, 65536, 1) == 0
     assert h.lafs_dino_workspace_bytes(0, 65536, 6) == 0
     # null pointers / bad sizes are rejected before any CUDA call
-    assert h.lafs_dino_fwd(None, None, None, 4, 1024, 6, 10.0, 25.0, 1, None, None, None, None, 0, None) == -1
+    assert h.lafs_dino_fwd(None, None, None, 4, 1024, 6, 10.0, 25.0, 1, None, None, None, None, 0, None, 0.9, 0.1, None) == -1
     assert b"null" in h.lafs_last_error_string()
     assert h.lafs_gather_fwd(None, None, None, 1, 3, 112, 112, 196, 0, 0, None) == -1
     assert h.lafs_ema_multi(None, 0, 0.9, 0.1, 0, None) == 0       # empty list is a no-op

@@ -9,7 +9,7 @@ s = torch.randn(nc * B, K, device="cuda", dtype=torch.bfloat16); t = torch.randn
 c = torch.randn(K, device="cuda") * 0.1
 loss = torch.empty((), device="cuda"); rs = torch.empty((nc + 2) * B, device="cuda"); cs = torch.empty(K, device="cuda")
 nb = _lib.lib().lafs_dino_workspace_bytes(B, K, nc); ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
-f = lambda: _lib.call("lafs_dino_fwd", s.data_ptr(), t.data_ptr(), c.data_ptr(), B, K, nc, 10.0, 25.0, 1, loss.data_ptr(), rs.data_ptr(), cs.data_ptr(), ws.data_ptr(), nb, _lib.stream())
+f = lambda: _lib.call("lafs_dino_fwd", s.data_ptr(), t.data_ptr(), c.data_ptr(), B, K, nc, 10.0, 25.0, 1, loss.data_ptr(), rs.data_ptr(), cs.data_ptr(), ws.data_ptr(), nb, None, 0.0, 0.0, _lib.stream())
 for _ in range(5): f()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

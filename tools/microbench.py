@@ -56,7 +56,7 @@ def main():
         ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
         gs = torch.empty_like(s); go = torch.ones((), device="cuda")
         f = lambda: _lib.call("lafs_dino_fwd", s.data_ptr(), t.data_ptr(), c.data_ptr(), B, K, ncrops, 10.0, 25.0, 1,
-                              loss.data_ptr(), rs.data_ptr(), cs.data_ptr(), ws.data_ptr(), nb, _lib.stream())
+                              loss.data_ptr(), rs.data_ptr(), cs.data_ptr(), ws.data_ptr(), nb, None, 0.0, 0.0, _lib.stream())
         b = lambda: _lib.call("lafs_dino_bwd", s.data_ptr(), t.data_ptr(), c.data_ptr(), rs.data_ptr(), go.data_ptr(),
                               B, K, ncrops, 10.0, 25.0, 1, gs.data_ptr(), _lib.stream())
         mf, bf = timeit(f)
