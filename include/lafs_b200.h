@@ -90,6 +90,18 @@ LAFS_API int lafs_dino_bwd(const void* student, const void* teacher, const float
                   const float* row_stats, const float* grad_out, int B, int K, int ncrops,
                   float inv_student_temp, float inv_teacher_temp, int dtype, void* grad_student,
                   lafs_stream_t stream);
+/* Forward and backward from one call (no autograd round trip), for training loops where the upstream
+ * gradient of the loss is known when the loss is computed (grad_out: device scalar, 1 for a root
+ * loss).  Can process the batch in waves of samples (env LAFS_DINO_WAVE) so that the gradient pass
+ * re-reads from L2; measured slower than one wave on B200, which is the default.  Outputs as
+ * lafs_dino_fwd + lafs_dino_bwd; workspace from lafs_dino_fused_workspace_bytes. */
+LAFS_API size_t lafs_dino_fused_workspace_bytes(int B, int K, int ncrops);
+LAFS_API int lafs_dino_fwd_bwd(const void* student, const void* teacher, const float* center,
+                               const float* grad_out, int B, int K, int ncrops, float inv_student_temp,
+                               float inv_teacher_temp, int dtype, float* loss_out, float* row_stats,
+                               float* colsum_out, void* grad_student, void* workspace, size_t workspace_bytes,
+                               float* center_out, float momentum, float one_minus_momentum,
+                               lafs_stream_t stream);
 /* center_out = center*momentum + (colsum/count)*(1-momentum)   lafs_train.py:676-679
  * (count = 2B*world_size; colsum already all-reduced by the caller when world>1).
  * center_out may alias center; the reference re-binds a NEW tensor, and the

@@ -27,6 +27,8 @@ SIGNATURES = {
     "lafs_ema_multi": (_i, [_p, _i, _f, _f, _i, _p]),
     "lafs_dino_workspace_bytes": (_z, [_i, _i, _i]),
     "lafs_dino_fwd": (_i, [_p, _p, _p, _i, _i, _i, _f, _f, _i, _p, _p, _p, _p, _z, _p, _f, _f, _p]),
+    "lafs_dino_fused_workspace_bytes": (_z, [_i, _i, _i]),
+    "lafs_dino_fwd_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _f, _f, _i, _p, _p, _p, _p, _p, _z, _p, _f, _f, _p]),
     "lafs_dino_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _i, _p, _p]),
     "lafs_center_ema": (_i, [_p, _p, _f, _f, _f, _i, _p, _p]),
     "lafs_colsum": (_i, [_p, _i, _i, _i, _p, _p, _z, _p]),

@@ -71,7 +71,8 @@ template <typename T, int NCROPS, bool RAGGED>
 __global__ void __launch_bounds__(kDinoThreads, 2)
 dino_fwd_partial(const T* __restrict__ student, const T* __restrict__ teacher,
                  const float* __restrict__ center, int B, int K, float a_s, float a_t,
-                 int nslices, int ngroups, float* __restrict__ part, float* __restrict__ colsum_part) {
+                 int nslices, int ngroups, float* __restrict__ part, float* __restrict__ colsum_part,
+                 int b_begin, int b_count) {
   constexpr int VEC = VecOf<T>::VEC;
   constexpr int NC = VEC;
   constexpr int REC = rec_floats(NCROPS);
@@ -81,8 +82,9 @@ dino_fwd_partial(const T* __restrict__ student, const T* __restrict__ teacher,
   // one 512 B segment per row per CTA the same kernel ran at 40 % of the HBM rate).
   const int slice = blockIdx.x * kDinoWarps + warp, group = blockIdx.y;
   if (slice >= nslices) return;
-  const int b_lo = (int)(((long long)B * group) / ngroups);
-  const int b_hi = (int)(((long long)B * (group + 1)) / ngroups);
+  // this launch covers samples [b_begin, b_begin + b_count) (the whole batch, or one L2-sized wave)
+  const int b_lo = b_begin + (int)(((long long)b_count * group) / ngroups);
+  const int b_hi = b_begin + (int)(((long long)b_count * (group + 1)) / ngroups);
 
   const int col = slice * (32 * VEC) + lane * VEC;
   const bool ok = !RAGGED || col < K;            // K % VEC == 0 is checked by the host
@@ -219,12 +221,13 @@ constexpr int kFinalizeWarps = 2;   // small blocks: B/2 CTAs keep every SM busy
 template <int NCROPS>
 __global__ void __launch_bounds__(kFinalizeWarps * 32)
 dino_rows_finalize(const float* __restrict__ part, int B, int nslices, float inv_ts,
-                   float* __restrict__ row_stats, float* __restrict__ sample_loss) {
+                   float* __restrict__ row_stats, float* __restrict__ sample_loss, int b_begin, int b_count) {
   constexpr int REC = rec_floats(NCROPS);
   constexpr int NR = 2 + NCROPS;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int b = blockIdx.x * kFinalizeWarps + warp;
-  if (b >= B) return;
+  const int bi = blockIdx.x * kFinalizeWarps + warp;
+  if (bi >= b_count) return;
+  const int b = b_begin + bi;
   const float* base = part + (size_t)b * nslices * REC;
   float m[NR];
 #pragma unroll
@@ -311,9 +314,9 @@ __global__ void __launch_bounds__(kDinoThreads)
 dino_bwd_kernel(const T* __restrict__ student, const T* __restrict__ teacher,
                 const float* __restrict__ center, const float* __restrict__ row_stats,
                 const float* __restrict__ grad_out, int B, int K, float a_s, float a_t,
-                float gcoef, T* __restrict__ grad_student) {
+                float gcoef, T* __restrict__ grad_student, int b_begin) {
   constexpr int VEC = VecOf<T>::VEC;
-  const int b = blockIdx.y;
+  const int b = b_begin + blockIdx.y;
   const int col = (blockIdx.x * kDinoThreads + threadIdx.x) * VEC;
   if (col >= K) return;
   uint4 tv[2], sv[NCROPS];
@@ -442,13 +445,13 @@ static int launch_fwd(const void* student, const void* teacher, const float* cen
   if (K % p.cols_per_slice == 0)
     dino_fwd_partial<T, NCROPS, false><<<grid, kDinoThreads, 0, st>>>(
         (const T*)student, (const T*)teacher, center, B, K, inv_ts * kLog2e, inv_tt * kLog2e,
-        p.nslices, p.ngroups, part, colsum_part);
+        p.nslices, p.ngroups, part, colsum_part, 0, B);
   else
     dino_fwd_partial<T, NCROPS, true><<<grid, kDinoThreads, 0, st>>>(
         (const T*)student, (const T*)teacher, center, B, K, inv_ts * kLog2e, inv_tt * kLog2e,
-        p.nslices, p.ngroups, part, colsum_part);
+        p.nslices, p.ngroups, part, colsum_part, 0, B);
   dino_rows_finalize<NCROPS><<<(B + kFinalizeWarps - 1) / kFinalizeWarps, kFinalizeWarps * 32, 0, st>>>(
-      part, B, p.nslices, inv_ts, row_stats, sample_loss);
+      part, B, p.nslices, inv_ts, row_stats, sample_loss, 0, B);
   const float inv_norm = 1.f / ((float)(2 * NCROPS - 2) * (float)B);
   dino_tail<<<(K + kDinoThreads - 1) / kDinoThreads, kDinoThreads, 0, st>>>(
       sample_loss, B, inv_norm, loss_out, colsum_part, p.ngroups, K, colsum_out, center, center_out,
@@ -465,8 +468,92 @@ static int launch_bwd(const void* student, const void* teacher, const float* cen
   const float gcoef = inv_ts / ((float)(2 * NCROPS - 2) * (float)B);
   dino_bwd_kernel<T, NCROPS><<<grid, kDinoThreads, 0, st>>>(
       (const T*)student, (const T*)teacher, center, row_stats, grad_out, B, K, inv_ts * kLog2e,
-      inv_tt * kLog2e, gcoef, (T*)grad_student);
+      inv_tt * kLog2e, gcoef, (T*)grad_student, 0);
   return check_launch("lafs_dino_bwd");
+}
+
+// Forward AND backward from one entry point, optionally in waves of samples so that the gradient
+// pass of a wave re-reads from L2 what its forward pass has just streamed.  Measured on B200
+// (tools/dino_fused_sweep.py, B=256, K=65536): one wave 174 us, 128-sample waves 194 us, 64: 238 us,
+// 32: 307 us -- the shorter per-warp pipelines and partially filled grids of small waves cost more
+// than the L2 hits save, so the default is ONE wave (LAFS_DINO_WAVE overrides).  Used when the
+// upstream gradient of the loss is known when the loss is computed (grad_out device scalar).
+constexpr int kMaxColsumRows = 64;
+struct FusedPlan {
+  int wave, nwaves, ngroups, nslices, cols_per_slice;
+  size_t off_part, off_colsum, off_sample, total;
+};
+static FusedPlan make_fused_plan(int B, int K, int ncrops, int elem_bytes) {
+  FusedPlan p;
+  const int vec = 16 / elem_bytes;
+  p.cols_per_slice = 32 * vec;
+  p.nslices = (K + p.cols_per_slice - 1) / p.cols_per_slice;
+  const double bytes_per_sample = (double)(ncrops + 2) * K * elem_bytes;
+  int wave = B;
+  (void)bytes_per_sample;
+  if (const char* e = getenv("LAFS_DINO_WAVE")) wave = atoi(e);
+  if (wave < 8) wave = 8;
+  if (wave > B) wave = B;
+  p.nwaves = (B + wave - 1) / wave;
+  if (p.nwaves > 16) { p.nwaves = 16; }
+  p.wave = (B + p.nwaves - 1) / p.nwaves;
+  p.nwaves = (B + p.wave - 1) / p.wave;
+  int g = kMaxColsumRows / p.nwaves;
+  if (g > kMaxGroups) g = kMaxGroups;
+  const int xctas = (p.nslices + kDinoWarps - 1) / kDinoWarps;
+  const int want = (2 * kNumSMs + xctas - 1) / xctas;            // >= one full wave of CTAs
+  if (g > want) g = want;
+  if (g > p.wave) g = p.wave;
+  if (const char* e = getenv("LAFS_DINO_GROUPS")) { const int v = atoi(e); if (v >= 1 && v <= g) g = v; }
+  if (g < 1) g = 1;
+  if (p.nwaves == 1) g = make_plan(B, K, ncrops, elem_bytes).ngroups;   // same grid as lafs_dino_fwd
+  p.ngroups = g;
+  size_t o = 0;
+  p.off_part = o;   o += (size_t)B * p.nslices * rec_floats(ncrops) * sizeof(float);
+  o = (o + 255) & ~(size_t)255;
+  p.off_colsum = o; o += (size_t)p.nwaves * p.ngroups * K * sizeof(float);
+  o = (o + 255) & ~(size_t)255;
+  p.off_sample = o; o += (size_t)B * sizeof(float);
+  p.total = (o + 255) & ~(size_t)255;
+  return p;
+}
+
+template <typename T, int NCROPS>
+static int launch_fused(const void* student, const void* teacher, const float* center, const float* grad_out,
+                        int B, int K, float inv_ts, float inv_tt, float* loss_out, float* row_stats,
+                        float* colsum_out, void* grad_student, char* ws, const FusedPlan& p, cudaStream_t st,
+                        float* center_out, float mom, float om) {
+  constexpr int VEC = VecOf<T>::VEC;
+  float* part = reinterpret_cast<float*>(ws + p.off_part);
+  float* colsum_part = reinterpret_cast<float*>(ws + p.off_colsum);
+  float* sample_loss = reinterpret_cast<float*>(ws + p.off_sample);
+  const float gcoef = inv_ts / ((float)(2 * NCROPS - 2) * (float)B);
+  const bool ragged = K % p.cols_per_slice != 0;
+  for (int w = 0; w < p.nwaves; ++w) {
+    const int b0 = w * p.wave;
+    const int bc = (B - b0) < p.wave ? (B - b0) : p.wave;
+    dim3 grid((p.nslices + kDinoWarps - 1) / kDinoWarps, p.ngroups);
+    float* cpart = colsum_part + (size_t)w * p.ngroups * K;
+    if (!ragged)
+      dino_fwd_partial<T, NCROPS, false><<<grid, kDinoThreads, 0, st>>>(
+          (const T*)student, (const T*)teacher, center, B, K, inv_ts * kLog2e, inv_tt * kLog2e,
+          p.nslices, p.ngroups, part, cpart, b0, bc);
+    else
+      dino_fwd_partial<T, NCROPS, true><<<grid, kDinoThreads, 0, st>>>(
+          (const T*)student, (const T*)teacher, center, B, K, inv_ts * kLog2e, inv_tt * kLog2e,
+          p.nslices, p.ngroups, part, cpart, b0, bc);
+    dino_rows_finalize<NCROPS><<<(bc + kFinalizeWarps - 1) / kFinalizeWarps, kFinalizeWarps * 32, 0, st>>>(
+        part, B, p.nslices, inv_ts, row_stats, sample_loss, b0, bc);
+    dim3 gb((K / VEC + kDinoThreads - 1) / kDinoThreads, bc);
+    dino_bwd_kernel<T, NCROPS><<<gb, kDinoThreads, 0, st>>>(
+        (const T*)student, (const T*)teacher, center, row_stats, grad_out, B, K, inv_ts * kLog2e,
+        inv_tt * kLog2e, gcoef, (T*)grad_student, b0);
+  }
+  const float inv_norm = 1.f / ((float)(2 * NCROPS - 2) * (float)B);
+  dino_tail<<<(K + kDinoThreads - 1) / kDinoThreads, kDinoThreads, 0, st>>>(
+      sample_loss, B, inv_norm, loss_out, colsum_part, p.nwaves * p.ngroups, K, colsum_out, center, center_out,
+      (float)(2 * B), mom, om);
+  return check_launch("lafs_dino_fwd_bwd");
 }
 
 #define LAFS_DINO_CROPS(M) M(2) M(3) M(4) M(5) M(6) M(7) M(8) M(9) M(10) M(11) M(12)
@@ -522,6 +609,48 @@ extern "C" int lafs_dino_fwd(const void* student, const void* teacher, const flo
     return launch_fwd<__half, N>(student, teacher, center, B, K, inv_student_temp, inv_teacher_temp,     \
                                  loss_out, row_stats, colsum_out, ws, p, st, center_out, momentum,       \
                                  one_minus_momentum);
+  switch (ncrops) { LAFS_DINO_CROPS(LAFS_CASE) }
+#undef LAFS_CASE
+  return LAFS_ERR_ARG;
+}
+
+extern "C" size_t lafs_dino_fused_workspace_bytes(int B, int K, int ncrops) {
+  if (B <= 0 || K <= 0 || ncrops < 2 || ncrops > 12) return 0;
+  return lafs::make_fused_plan(B, K, ncrops, 4).total + (size_t)lafs::kMaxColsumRows * K * sizeof(float);
+}
+
+extern "C" int lafs_dino_fwd_bwd(const void* student, const void* teacher, const float* center,
+                                 const float* grad_out, int B, int K, int ncrops, float inv_student_temp,
+                                 float inv_teacher_temp, int dtype, float* loss_out, float* row_stats,
+                                 float* colsum_out, void* grad_student, void* workspace, size_t workspace_bytes,
+                                 float* center_out, float momentum, float one_minus_momentum,
+                                 lafs_stream_t stream) {
+  if (int brc = lafs::bind_device_of(student)) return brc;
+  using namespace lafs;
+  int rc = dino_check(student, teacher, center, B, K, ncrops, dtype, "lafs_dino_fwd_bwd");
+  if (rc) return rc;
+  LAFS_REQUIRE(grad_out && loss_out && row_stats && colsum_out && grad_student && workspace, LAFS_ERR_ARG,
+               "lafs_dino_fwd_bwd: null pointer");
+  LAFS_REQUIRE(((uintptr_t)grad_student & 15u) == 0 && ((uintptr_t)workspace & 255u) == 0, LAFS_ERR_ARG,
+               "lafs_dino_fwd_bwd: misaligned grad_student / workspace");
+  const FusedPlan p = make_fused_plan(B, K, ncrops, dtype == LAFS_F32 ? 4 : 2);
+  LAFS_REQUIRE(workspace_bytes >= p.total, LAFS_ERR_WORKSPACE, "lafs_dino_fwd_bwd: workspace %zu < %zu",
+               workspace_bytes, p.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+#define LAFS_CASE(N)                                                                                          \
+  case N:                                                                                                     \
+    if (dtype == LAFS_F32)                                                                                    \
+      return launch_fused<float, N>(student, teacher, center, grad_out, B, K, inv_student_temp,              \
+                                    inv_teacher_temp, loss_out, row_stats, colsum_out, grad_student, ws, p,  \
+                                    st, center_out, momentum, one_minus_momentum);                            \
+    if (dtype == LAFS_BF16)                                                                                   \
+      return launch_fused<__nv_bfloat16, N>(student, teacher, center, grad_out, B, K, inv_student_temp,      \
+                                            inv_teacher_temp, loss_out, row_stats, colsum_out, grad_student, \
+                                            ws, p, st, center_out, momentum, one_minus_momentum);             \
+    return launch_fused<__half, N>(student, teacher, center, grad_out, B, K, inv_student_temp,               \
+                                   inv_teacher_temp, loss_out, row_stats, colsum_out, grad_student, ws, p,   \
+                                   st, center_out, momentum, one_minus_momentum);
   switch (ncrops) { LAFS_DINO_CROPS(LAFS_CASE) }
 #undef LAFS_CASE
   return LAFS_ERR_ARG;

@@ -103,6 +103,47 @@ class DINOLoss(nn.Module):
         return loss
 
     @torch.no_grad()
+    def loss_and_grad(self, student_output, teacher_output, epoch, grad_scale=None):
+        """loss and d(loss)/d(student_output) in one call (training loops that own the backward of
+        the head, e.g. SSLHotPath): one C call, no autograd graph.  grad_scale: optional device scalar the
+        gradient is multiplied with (AMP loss scale); default 1.  Also updates the centre."""
+        _lib.require_cuda(student_output, teacher_output)
+        K = student_output.shape[1]
+        B = student_output.shape[0] // self.ncrops
+        s = student_output.detach().contiguous()
+        t = teacher_output.detach().to(s.dtype).contiguous()
+        c = self.center.detach().float().contiguous()
+        dev = s.device
+        if teacher_output.shape != (2 * B, K) or c.numel() != K or student_output.shape[0] != self.ncrops * B:
+            raise ValueError("shape mismatch between student_output, teacher_output and center")
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        row_stats = torch.empty((self.ncrops + 2) * B, dtype=torch.float32, device=dev)
+        colsum = torch.empty(K, dtype=torch.float32, device=dev)
+        grad = torch.empty_like(s)
+        g = grad_scale if grad_scale is not None else torch.ones((), dtype=torch.float32, device=dev)
+        nbytes = _lib.lib().lafs_dino_fused_workspace_bytes(B, K, self.ncrops)
+        if nbytes == 0:
+            raise ValueError(f"unsupported DINO shape B={B} K={K} ncrops={self.ncrops}")
+        ws = _workspace(dev, nbytes)
+        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        new_center = torch.empty(1, K, dtype=torch.float32, device=dev) if world == 1 else None
+        m = float(self.center_momentum)
+        temp = float(self.teacher_temp_schedule[epoch])
+        _lib.call("lafs_dino_fwd_bwd", s.data_ptr(), t.data_ptr(), c.data_ptr(), g.data_ptr(), B, K, self.ncrops,
+                  1.0 / self.student_temp, 1.0 / temp, _lib.dtype_code(s), loss.data_ptr(), row_stats.data_ptr(),
+                  colsum.data_ptr(), grad.data_ptr(), ws.data_ptr(), nbytes, _lib.ptr(new_center),
+                  float(np.float32(m)), float(np.float32(1.0 - m)), _lib.stream())
+        if world == 1:
+            self.center = new_center
+        else:
+            dist.all_reduce(colsum)
+            nc = torch.empty(1, K, dtype=torch.float32, device=dev)
+            _lib.call("lafs_center_ema", c.data_ptr(), colsum.data_ptr(), float(2 * B * world), float(np.float32(m)),
+                      float(np.float32(1.0 - m)), K, nc.data_ptr(), _lib.stream())
+            self.center = nc
+        return loss, grad
+
+    @torch.no_grad()
     def update_center(self, teacher_output):
         """center <- center*m + (all_reduce(sum_rows teacher)/(rows*world))*(1-m)."""
         _lib.require_cuda(teacher_output)

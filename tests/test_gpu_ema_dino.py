@@ -174,3 +174,26 @@ def test_update_center_standalone(P):
     crit.update_center(t)
     ref = O.dino_center_update(torch.zeros(1, K), t.cpu())
     torch.testing.assert_close(crit.center.cpu(), ref, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("B,K,ncrops,dtype", [(7, 1000, 3, torch.float32), (96, 4096, 6, torch.bfloat16),
+                                               (256, 65536, 6, torch.bfloat16)])
+def test_dino_wave_fused_fwd_bwd_equals_separate(P, B, K, ncrops, dtype):
+    """loss_and_grad (one fused call) == forward() + backward()."""
+    torch.manual_seed(B + K)
+    s = (torch.randn(ncrops * B, K, device="cuda") * 2).to(dtype)
+    t = (torch.randn(2 * B, K, device="cuda") * 2).to(dtype)
+    c0 = torch.randn(1, K, device="cuda") * 0.3
+    a = P.DINOLoss(K, ncrops, 0.04, 0.07, 30, 41).cuda(); a.center = c0.clone()
+    b = P.DINOLoss(K, ncrops, 0.04, 0.07, 30, 41).cuda(); b.center = c0.clone()
+    sg = s.clone().requires_grad_(True)
+    la = a(sg, t, 4)
+    la.backward()
+    lb, gb = b.loss_and_grad(s, t, 4)
+    assert float(la) == float(lb)
+    assert torch.equal(sg.grad, gb)
+    torch.testing.assert_close(a.center, b.center, rtol=1e-5, atol=1e-6)   # column sums merge in a different order
+    sc = torch.full((), 3.0, device="cuda")
+    b.center = c0.clone()
+    lc, gc = b.loss_and_grad(s, t, 4, grad_scale=sc)
+    torch.testing.assert_close(gc.float(), gb.float() * 3.0, rtol=2 ** -7, atol=1e-30)   # bf16 denormals

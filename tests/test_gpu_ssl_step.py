@@ -82,7 +82,7 @@ def test_graph_replay_equals_eager_over_steps():
     for _ in range(3):
         path_e.landmarks_and_embeddings(dev["raw_g"], dev["noise_g"], dev["img_g"], dev["raw_l"], dev["noise_l"],
                                         dev["idx_l"], dev["img_l"])
-        loss, grad_e = path_e.loss_and_grad(dev["student_out"], dev["teacher_out"], 5)
+        loss, grad_e = path_e.loss_and_grad(dev["student_out"], dev["teacher_out"], 5)   # wave-fused, as in the graph
         path_e.ema_step(0.99)
         losses_e.append(float(loss))
     # graph: capture (its two warm-up runs + capture must not advance the state we compare)

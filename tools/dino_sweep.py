@@ -18,6 +18,6 @@ for _ in range(30): f()
 e1.record(); torch.cuda.synchronize()
 print("%%.1f us  loss %%.6f" %% (e0.elapsed_time(e1) / 30 * 1000, float(loss)))
 ''' % ROOT
-for g in (0,):
+for g in (0,):  # groups
     r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, LAFS_DINO_GROUPS=str(g)), capture_output=True, text=True)
     print("groups=%d:" % g, r.stdout.strip(), r.stderr.strip()[-200:])

@@ -16,7 +16,7 @@ path = SSLHotPath(bench.OUT_DIM, L, st["teacher_params"], st["student_params"],
                   teacher_embed=(st["teacher_params"][1], st["teacher_params"][2]))
 path.loss.center = torch.randn(1, bench.OUT_DIM, device=dev) * 0.1
 import sys as _s
-g = GraphedSSLStep(path, inp, epoch=3, momentum=0.996, overlap_ema=("--no-overlap" not in _s.argv),
+g = GraphedSSLStep(path, inp, epoch=3, momentum=0.996, overlap_ema=("--overlap" in _s.argv),
                    ema_ctas=int(os.environ.get("EMA_CTAS", "148")))
 def t(fn, n=50):
     for _ in range(5): fn()
