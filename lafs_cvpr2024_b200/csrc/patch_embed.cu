@@ -74,6 +74,8 @@ struct EmbedParams {
   int Bv, n, n_pad, dim, n_models;
   int gfaces;               // faces whose tokens share one tile / one pass over the weights (G*n <= 200)
   int ngroups;              // ceil(Bv / gfaces)
+  int nfull;                // groups [0, nfull) are whole work units; each later group is split into
+  int nunits;               //   two units (first / second half of the weight chunks) for load balance
   int mchunks;              // n_models * dim / 128
   float in_scale, in_shift; // normalised pixel = in_scale * raw + in_shift   (1, 0 for fp32 input)
   float pad_raw;            // raw value of a zero-padded (out-of-image) pixel = -in_shift / in_scale
@@ -193,7 +195,12 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
 
   // work unit = a GROUP of p.gfaces consecutive faces (1 for 196 landmarks, 5 for 36): their tokens
   // fill one tile, so every weight chunk fetched from L2 is used for all of them
-  const int ngroups_mine = (p.ngroups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // The units of the last, partially filled round are half groups (same tokens, half of the weight
+  // chunks each), so that round costs half a unit instead of a whole one.
+  const int nunits_mine = (p.nunits - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto unit_group = [&](int u) { return u < p.nfull ? u : p.nfull + ((u - p.nfull) >> 1); };
+  auto unit_mc0 = [&](int u) { return u < p.nfull ? 0 : ((u - p.nfull) & 1) * (p.mchunks >> 1); };
+  auto unit_mcn = [&](int u) { return u < p.nfull ? p.mchunks : (p.mchunks >> 1); };
   auto group_faces = [&](int g) { return min(p.gfaces, p.Bv - g * p.gfaces); };
   auto group_ntok = [&](int g) { return group_faces(g) * p.n; };
 
@@ -202,8 +209,8 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
     if (lane == 0) {
       const InT* imgs = reinterpret_cast<const InT*>(p.imgs);
       uint32_t cnt = 0;
-      for (int gi = 0; gi < ngroups_mine; ++gi) {
-        const int g = blockIdx.x + gi * gridDim.x;
+      for (int gi = 0; gi < nunits_mine; ++gi) {
+        const int g = unit_group(blockIdx.x + gi * gridDim.x);
         const int nf = group_faces(g);
         for (int ff = 0; ff < nf; ++ff) {
           const int f = g * p.gfaces + ff;
@@ -221,31 +228,36 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
     // ===================== weight chunk producer =====================
     if (lane == 0) {
       uint32_t cnt = 0;
-      for (int gi = 0; gi < ngroups_mine; ++gi)
-        for (int mc = 0; mc < p.mchunks; ++mc)
+      for (int gi = 0; gi < nunits_mine; ++gi) {
+        const int u = blockIdx.x + gi * gridDim.x;
+        const int mc0 = unit_mc0(u), mc1 = mc0 + unit_mcn(u);
+        for (int mc = mc0; mc < mc1; ++mc)
           for (int c = 0; c < kC; ++c, ++cnt) {
             const int st = cnt % kWStages;
             mbar_wait(w_empty + st, ((cnt / kWStages) & 1) ^ 1);
             mbar_arrive_expect_tx(w_full + st, kWStageBytes);
             tma_load_2d(s_w + st * kWStageBytes, &tmap_w, w_full + st, c * 64, mc * 128);
           }
+      }
     }
   } else if (warp == kWarpMma) {
     // ===================== UMMA issuer =====================
     if (lane == 0) {
       uint32_t wcnt = 0, acnt = 0;
-      for (int fi = 0; fi < ngroups_mine; ++fi) {
+      for (int fi = 0; fi < nunits_mine; ++fi) {
+        const int u = blockIdx.x + fi * gridDim.x;
         const int tb = fi % NTB;
         const uint32_t tuse = (uint32_t)(fi / NTB);
-        const int npad_g = (group_ntok(blockIdx.x + fi * gridDim.x) + 15) & ~15;
+        const int npad_g = (group_ntok(unit_group(u)) + 15) & ~15;
         const uint32_t idesc = make_idesc_bf16(128, npad_g);
-        for (int mc = 0; mc < p.mchunks; ++mc, ++acnt) {
+        const int mc0 = unit_mc0(u), mc1 = mc0 + unit_mcn(u);
+        for (int mc = mc0; mc < mc1; ++mc, ++acnt) {
           const int buf = acnt & 1;
           mbar_wait(acc_empty + buf, ((acnt >> 1) & 1) ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
           for (int c = 0; c < kC; ++c, ++wcnt) {
-            if (mc == 0) { mbar_wait(tok_full + tb * 3 + c, tuse & 1); }
+            if (mc == mc0) { mbar_wait(tok_full + tb * 3 + c, tuse & 1); }
             const int st = wcnt % kWStages;
             mbar_wait(w_full + st, (wcnt / kWStages) & 1);
             tc_fence_after();
@@ -275,11 +287,13 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
     const int half = (warp - kWarpEpi0) >> 2;
     const int dim = DIM > 0 ? DIM : p.dim;
     uint32_t acnt = 0;
-    for (int fi = 0; fi < ngroups_mine; ++fi) {
-      const int g = blockIdx.x + fi * gridDim.x;
+    for (int fi = 0; fi < nunits_mine; ++fi) {
+      const int u = blockIdx.x + fi * gridDim.x;
+      const int g = unit_group(u);
       const int f = g * p.gfaces;                          // first face: the group's tokens are contiguous in `out`
       const int ntok = group_ntok(g), npad = (ntok + 15) & ~15;
-      for (int mc = 0; mc < p.mchunks; ++mc, ++acnt) {
+      const int mc0 = unit_mc0(u), mc1 = mc0 + unit_mcn(u);
+      for (int mc = mc0; mc < mc1; ++mc, ++acnt) {
         const int buf = acnt & 1;
         const int d = mc * 128 + quarter * 32 + lane;      // row of the stacked [n_models*dim] weight
         const int model = d >= dim ? 1 : 0, dd = d - model * dim;
@@ -329,8 +343,8 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
     const int gt = threadIdx.x - kWarpGather0 * 32;        // 0..255
     const float a_in = p.in_scale, b_in = p.in_shift, pad = p.pad_raw;
     uint32_t pcnt = 0;
-    for (int fi = 0; fi < ngroups_mine; ++fi) {
-      const int g = blockIdx.x + fi * gridDim.x;
+    for (int fi = 0; fi < nunits_mine; ++fi) {
+      const int g = unit_group(blockIdx.x + fi * gridDim.x);
       const int nf = group_faces(g);
       const int tb = fi % NTB;
       const uint32_t tuse = (uint32_t)(fi / NTB);
@@ -388,7 +402,7 @@ static int launch_embed(const CUtensorMap& tw, const EmbedParams& p, int out_dty
   constexpr int smem = pe::Layout<InT>::kSmemBytes;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   LAFS_REQUIRE(e == cudaSuccess, LAFS_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  const int grid = p.ngroups < kNumSMs ? p.ngroups : kNumSMs;
+  const int grid = p.nunits < kNumSMs ? p.nunits : kNumSMs;
   kern<<<grid, pe::kThreads, smem, st>>>(tw, p);
   return check_launch("lafs_gather_embed_fwd");
 }
@@ -430,21 +444,34 @@ extern "C" int lafs_gather_embed_fwd(const void* imgs, int in_dtype, float in_sc
   p.Bv = Bv; p.n = n; p.n_pad = (n + 15) & ~15; p.dim = dim; p.n_models = n_models;
   p.mchunks = n_models * dim / 128;
   // faces per group: as many as fit the tile, traded against load balance over the 148 CTAs.
-  // cost model per CTA: rounds * (one latency-bound pass over the weights ~ 6 face-equivalents + G faces)
+  // cost per CTA ~ (half-)rounds * faces per group (a sweep over G for the 36-landmark views showed the
+  // pass over the weights itself is not the limiter: 52-56 us for every G); ties go to the larger
+  // group.  The groups of a last, at most half-filled round are split into two half units (first /
+  // second half of the weight chunks), which makes that round cost half.
   {
     int gmax = pe::kTokRows / n < 1 ? 1 : pe::kTokRows / n;
     if (gmax > Bv) gmax = Bv;
-    int best_g = 1;
     long long best_cost = -1;
-    for (int g = 1; g <= gmax; ++g) {
-      const int groups = (Bv + g - 1) / g;
-      const long long rounds = (groups + kNumSMs - 1) / kNumSMs;
-      const long long cost = rounds * (6 + g);
-      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_g = g; }
+    int gmin = 1;
+    if (const char* e = getenv("LAFS_PE_GFACES")) {   // development override
+      const int v = atoi(e);
+      if (v >= 1 && v <= gmax) gmin = gmax = v;
     }
-    p.gfaces = best_g;
+    for (int g = gmin; g <= gmax; ++g) {
+      const int groups = (Bv + g - 1) / g;
+      const int rem = groups % kNumSMs;
+      const bool split = groups > kNumSMs && rem > 0 && 2 * rem <= kNumSMs && (p.mchunks % 2 == 0);
+      const long long half_rounds = 2LL * (groups / kNumSMs) + (rem == 0 ? 0 : (split ? 1 : 2));
+      const long long cost = half_rounds * g;
+      if (best_cost < 0 || cost <= best_cost) {
+        best_cost = cost;
+        p.gfaces = g;
+        p.ngroups = groups;
+        p.nfull = split ? groups - rem : groups;
+        p.nunits = p.nfull + 2 * (groups - p.nfull);
+      }
+    }
   }
-  p.ngroups = (Bv + p.gfaces - 1) / p.gfaces;
   if (in_dtype == LAFS_U8) { p.in_scale = in_scale; p.in_shift = in_shift; p.pad_raw = -in_shift / in_scale; }
   else { p.in_scale = 1.f; p.in_shift = 0.f; p.pad_raw = 0.f; }
   if (const char* dbg = getenv("LAFS_PE_DEBUG")) p.debug = atoi(dbg);
