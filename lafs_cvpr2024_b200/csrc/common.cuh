@@ -58,6 +58,16 @@ __device__ __forceinline__ float warp_max_redux(float v) {
   return __int_as_float(i);
 }
 
+// Warp sum of values known to lie in [0, 256] per lane-group total (softmax partial sums relative to
+// the slice maximum: every term is <= 1 and a 256-column slice holds at most 256 of them) with ONE
+// integer REDUX: 2^-22 fixed point, i.e. <= 2^-17 absolute error on a sum that is >= 1.  Integer
+// addition is associative, so the result is also order-independent.
+__device__ __forceinline__ float warp_sum_unit_terms(float v) {
+  int i = __float2int_rn(v * 4194304.0f);
+  i = __reduce_add_sync(0xffffffffu, i);
+  return (float)i * (1.0f / 4194304.0f);
+}
+
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

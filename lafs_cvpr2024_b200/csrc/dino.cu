@@ -186,7 +186,7 @@ dino_fwd_partial(const T* __restrict__ student, const T* __restrict__ teacher,
 #pragma unroll
         for (int j = 0; j < NC; ++j) a1 = fmaf(e[1][j], -sv[j], a1);
       }
-      sum = warp_sum(sum);
+      sum = warp_sum_unit_terms(sum);   // terms are exp2(. - slice max) <= 1, at most 256 per slice
       if (lane == 0) *reinterpret_cast<float2*>(dst + 6 + 2 * v) = make_float2(mx, sum);
     }
 #pragma unroll
@@ -195,8 +195,8 @@ dino_fwd_partial(const T* __restrict__ student, const T* __restrict__ teacher,
       a1 = fmaf(e[1][j], S[j], a1);
     }
     // ---- warp reduction of the additive statistics ---------------------------------------
-    zpart[0] = warp_sum(zpart[0]); a0 = warp_sum(a0);
-    zpart[1] = warp_sum(zpart[1]); a1 = warp_sum(a1);
+    zpart[0] = warp_sum_unit_terms(zpart[0]); a0 = warp_sum(a0);
+    zpart[1] = warp_sum_unit_terms(zpart[1]); a1 = warp_sum(a1);
     if (lane == 0) {
       dst[1] = zpart[0]; dst[2] = a0;
       dst[4] = zpart[1]; dst[5] = a1;
