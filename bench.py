@@ -55,6 +55,18 @@ def vit_b_param_shapes(out_dim=OUT_DIM):
     return shapes
 
 
+def ncu_traffic(report):
+    """DRAM bytes per launch of a kernel from the committed ncu capture (profiles/*_traffic.json)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    if not files:
+        return None
+    try:
+        return float(json.load(open(files[-1]))[report]["dram_bytes"])
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -345,7 +357,10 @@ def run_ours(args):
         "gpu_launches": 15,   # 2 landmark, 3 weight prep, 2 gather-embed, 3 dino fwd, 1 centre, 1 dino bwd, 1 ema (+2 events)
         "clocks": clocks,
         "roofline": {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["GBps"], "peak": pk["hbm"], "unit": "GB/s",
-                     "frac": kernels[dom]["frac_hbm"], "traffic": None, "peak_source": pk["src"]},
+                     "frac": kernels[dom]["frac_hbm"], "alg_bytes": kernels[dom]["alg_bytes"],
+                     "traffic": ncu_traffic({"ema": "ema_bench", "dino_bwd": "dino_bwd", "dino_fwd+center": "dino_fwd",
+                                             "landmark+gather_embed": "pe_global_u8"}.get(dom, dom)),
+                     "peak_source": pk["src"]},
         "kernels": kernels,
     }
     for name, h in head.items():

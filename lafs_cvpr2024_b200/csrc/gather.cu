@@ -148,7 +148,9 @@ gather_bwd_kernel(const float* __restrict__ imgs, const float* __restrict__ thet
 }
 
 // ---- landmark tail: joint min-max scaling (+noise, +re-sampling) ------------------------------
-// one warp per sample
+// one warp per sample; all of a sample's values are fetched with independent loads first (the
+// kernel is pure latency: 2n <= 32*kLmVals values per sample), then reduced and rescaled.
+constexpr int kLmVals = 13;   // 13 * 32 = 416 >= 392 = 2 * 196
 __global__ void __launch_bounds__(128)
 landmark_post_kernel(const float* __restrict__ raw, const float* __restrict__ noise,
                      const int64_t* __restrict__ extract_id, float* __restrict__ theta_out,
@@ -156,25 +158,53 @@ landmark_post_kernel(const float* __restrict__ raw, const float* __restrict__ no
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (b >= B) return;
-  const float* x = raw + (size_t)b * 2 * n;
+  const int m = 2 * n;
+  const float* x = raw + (size_t)b * m;
+  const bool small = m <= 32 * kLmVals;
+  float v[kLmVals];
   float mn = INFINITY, mx = -INFINITY;
-  for (int e = lane; e < 2 * n; e += 32) {
-    const float v = __ldg(x + e);
-    mn = fminf(mn, v);
-    mx = fmaxf(mx, v);
+  if (small) {
+#pragma unroll
+    for (int i = 0; i < kLmVals; ++i) {
+      const int e = lane + 32 * i;
+      v[i] = e < m ? __ldg(x + e) : NAN;
+    }
+#pragma unroll
+    for (int i = 0; i < kLmVals; ++i) {       // fminf / fmaxf ignore the NaN padding
+      mn = fminf(mn, v[i]);
+      mx = fmaxf(mx, v[i]);
+    }
+  } else {
+    for (int e = lane; e < m; e += 32) {
+      const float t = __ldg(x + e);
+      mn = fminf(mn, t);
+      mx = fmaxf(mx, t);
+    }
   }
   mx = warp_max(mx);
   mn = -warp_max(-mn);
   const float range = __fsub_rn(mx, mn);
   if (minmax_out != nullptr && lane == 0) { minmax_out[2 * b] = mn; minmax_out[2 * b + 1] = mx; }
+  // (theta - t_min)/(t_max - t_min)*111, then + noise   (ViT_face.py:1351,1362)
+  if (extract_id == nullptr && small) {
+#pragma unroll
+    for (int i = 0; i < kLmVals; ++i) {
+      const int e = lane + 32 * i;
+      if (e < m) {
+        float t = __fmul_rn(__fdiv_rn(__fsub_rn(v[i], mn), range), scale);
+        if (noise != nullptr) t = __fadd_rn(t, __ldg(noise + (size_t)b * m + e));
+        theta_out[(size_t)b * m + e] = t;
+      }
+    }
+    return;
+  }
   const int n_out = extract_id != nullptr ? keep : n;
   for (int e = lane; e < 2 * n_out; e += 32) {
     const int kk = e >> 1, d = e & 1;
     const int src = extract_id != nullptr ? (int)__ldg(extract_id + (size_t)b * keep + kk) : kk;
-    // (theta - t_min)/(t_max - t_min)*111, then + noise   (ViT_face.py:1351,1362)
-    float v = __fmul_rn(__fdiv_rn(__fsub_rn(__ldg(x + 2 * src + d), mn), range), scale);
-    if (noise != nullptr) v = __fadd_rn(v, __ldg(noise + ((size_t)b * n + src) * 2 + d));
-    theta_out[((size_t)b * n_out + kk) * 2 + d] = v;
+    float t = __fmul_rn(__fdiv_rn(__fsub_rn(__ldg(x + 2 * src + d), mn), range), scale);
+    if (noise != nullptr) t = __fadd_rn(t, __ldg(noise + ((size_t)b * n + src) * 2 + d));
+    theta_out[((size_t)b * n_out + kk) * 2 + d] = t;
   }
 }
 

@@ -10,6 +10,9 @@ cap() {  # name regex driver-mode skip
   ncu --set full --clock-control none --import-source on -k regex:$2 -s $4 -c 1 -o gpurun_out/$1 \
       python tools/prof_driver.py $3 3 > gpurun_out/$1.log 2>&1
 }
+# the dominant kernel of the bench step, captured from the bench command itself (full 147-tensor list)
+ncu --set full --clock-control none --import-source on -k regex:ema_multi_kernel -s 4 -c 1 -o gpurun_out/ema_bench \
+    python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ema_bench.log 2>&1
 cap ema ema_multi_kernel ema 1
 cap dino_fwd dino_fwd_partial dino 1
 cap dino_bwd dino_bwd_kernel dino 1

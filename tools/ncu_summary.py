@@ -42,6 +42,23 @@ def main(tag):
         w.writeheader()
         w.writerows(out_rows)
     print(path, len(out_rows), "kernels")
+    # DRAM traffic per launch (read + write) for bench.py's roofline.traffic
+    import json
+    traffic = {}
+    for r in out_rows:
+        rd = next((float(v) for k, v in r.items() if k.startswith("dram__bytes_read.sum [")), None)
+        wr = next((float(v) for k, v in r.items() if k.startswith("dram__bytes_write.sum [")), None)
+        ru = next((k for k in r if k.startswith("dram__bytes_read.sum [")), "")
+        mult = {"[Gbyte]": 1e9, "[Mbyte]": 1e6, "[Kbyte]": 1e3, "[byte]": 1.0}
+        def scale(key):
+            for u, m in mult.items():
+                if key.endswith(u):
+                    return m
+            return 1.0
+        wu = next((k for k in r if k.startswith("dram__bytes_write.sum [")), "")
+        if rd is not None and wr is not None:
+            traffic[r["report"].replace(".ncu-rep", "")] = {"kernel": r["kernel"], "dram_bytes": rd * scale(ru) + wr * scale(wu)}
+    json.dump(traffic, open(os.path.join(ROOT, "profiles", f"{tag}_traffic.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":
