@@ -49,13 +49,12 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-// float max over the warp with one REDUX on an order-preserving integer key.
+// float max over the warp: sm_100a reduces fp32 natively (one CREDUX.MAX.F32, result in a uniform
+// register) -- no order-preserving integer key needed.
 __device__ __forceinline__ float warp_max_redux(float v) {
-  int i = __float_as_int(v);
-  i ^= (i >> 31) & 0x7fffffff;
-  i = __reduce_max_sync(0xffffffffu, i);
-  i ^= (i >> 31) & 0x7fffffff;
-  return __int_as_float(i);
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
 }
 
 // Warp sum of values known to lie in [0, 256] per lane-group total (softmax partial sums relative to
@@ -103,6 +102,13 @@ __device__ __forceinline__ void st_stream_u4(void* p, uint4 v) {
 __device__ __forceinline__ void st_stream_f4(void* p, float4 v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
                :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// 256-bit store (sm_100: STG.256): one instruction covers a 32-byte sector per lane.  p must be
+// 32-byte aligned.
+__device__ __forceinline__ void st_global_256(void* p, uint4 a, uint4 b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
 }
 
 // 16-bit pair unpack / pack.  T = __nv_bfloat16 or __half.

@@ -72,11 +72,14 @@ __global__ void __launch_bounds__(kDinoThreads, 2)
 dino_fwd_partial(const T* __restrict__ student, const T* __restrict__ teacher,
                  const float* __restrict__ center, int B, int K, float a_s, float a_t,
                  int nslices, int ngroups, float* __restrict__ part, float* __restrict__ colsum_part,
-                 int b_begin, int b_count) {
+                 int b_begin, int b_count, unsigned* __restrict__ done_counter) {
   constexpr int VEC = VecOf<T>::VEC;
   constexpr int NC = VEC;
   constexpr int REC = rec_floats(NCROPS);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // arrival counter of dino_finish (the next kernel on the stream): reset here so that the workspace
+  // needs no initialisation by the caller
+  if (done_counter != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *done_counter = 0u;
   // The 8 warps of a CTA own 8 ADJACENT slices and walk over the same samples at the same pace, so
   // a CTA touches 8 x 512 B = 4 KB contiguous bytes of every row it reads (DRAM page locality: with
   // one 512 B segment per row per CTA the same kernel ran at 40 % of the HBM rate).
@@ -195,11 +198,18 @@ dino_fwd_partial(const T* __restrict__ student, const T* __restrict__ teacher,
       a1 = fmaf(e[1][j], S[j], a1);
     }
     // ---- warp reduction of the additive statistics ---------------------------------------
-    zpart[0] = warp_sum_unit_terms(zpart[0]); a0 = warp_sum(a0);
-    zpart[1] = warp_sum_unit_terms(zpart[1]); a1 = warp_sum(a1);
-    if (lane == 0) {
-      dst[1] = zpart[0]; dst[2] = a0;
-      dst[4] = zpart[1]; dst[5] = a1;
+    zpart[0] = warp_sum_unit_terms(zpart[0]);
+    zpart[1] = warp_sum_unit_terms(zpart[1]);
+    // a0 and a1 share one butterfly: after the first exchange the lower half-warp carries a0 and the
+    // upper half-warp a1 (5 shuffles instead of 10); lane 0 ends with sum(a0), lane 16 with sum(a1)
+    {
+      const bool up = (lane & 16) != 0;
+      float mine = up ? a1 : a0;
+      mine += __shfl_xor_sync(0xffffffffu, up ? a0 : a1, 16);
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+      if (lane == 0) { dst[1] = zpart[0]; dst[2] = mine; dst[4] = zpart[1]; }
+      if (lane == 16) dst[5] = mine;
     }
     off += step;
   }
@@ -307,6 +317,122 @@ dino_tail(const float* __restrict__ sample_loss, int B, float inv_norm, float* _
   }
 }
 
+// Everything that follows the streaming pass, in ONE launch of 64-thread blocks:
+//   blocks [0, nfin)      : one warp per sample -- the sample's slice records (contiguous, 72 B x
+//                           nslices) are staged into shared memory with coalesced 128-bit loads, then
+//                           merged in two passes exactly like dino_rows_finalize; the warp that
+//                           arrives last (device-wide counter) adds the per-sample losses in a fixed
+//                           order, so the result does not depend on the arrival order;
+//   blocks [nfin, gridDim): column-sum partials -> column sums (+ the centre EMA when one process
+//                           owns the whole batch), 4 columns per thread.
+template <int NCROPS>
+__global__ void __launch_bounds__(64)
+dino_finish(const float* __restrict__ part, int B, int nslices, float inv_ts, float* __restrict__ row_stats,
+            float* __restrict__ sample_loss, int nfin, float inv_norm, float* __restrict__ loss_out,
+            unsigned* __restrict__ done_counter, const float* __restrict__ colsum_part, int ngroups, int K,
+            float* __restrict__ colsum_out, const float* __restrict__ center, float* __restrict__ center_out,
+            float count, float mom, float om) {
+  constexpr int REC = rec_floats(NCROPS);
+  constexpr int NR = 2 + NCROPS;
+  extern __shared__ __align__(16) float fin_smem[];
+  if ((int)blockIdx.x >= nfin) {
+    const int k = (((int)blockIdx.x - nfin) * 64 + (int)threadIdx.x) * 4;
+    if (k < K) {                                        // K % 4 == 0 (checked by the host)
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int g = 0; g < ngroups; ++g) {
+        const float4 v = *reinterpret_cast<const float4*>(colsum_part + (size_t)g * K + k);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      *reinterpret_cast<float4*>(colsum_out + k) = acc;
+      if (center_out != nullptr) {                      // same arithmetic as center_ema_kernel
+        const float4 c = *reinterpret_cast<const float4*>(center + k);
+        float4 o;
+        o.x = __fadd_rn(__fmul_rn(c.x, mom), __fmul_rn(__fdiv_rn(acc.x, count), om));
+        o.y = __fadd_rn(__fmul_rn(c.y, mom), __fmul_rn(__fdiv_rn(acc.y, count), om));
+        o.z = __fadd_rn(__fmul_rn(c.z, mom), __fmul_rn(__fdiv_rn(acc.z, count), om));
+        o.w = __fadd_rn(__fmul_rn(c.w, mom), __fmul_rn(__fdiv_rn(acc.w, count), om));
+        *reinterpret_cast<float4*>(center_out + k) = o;
+      }
+    }
+    return;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x * 2 + warp;
+  if (b < B) {
+    const int nrec = nslices * REC;
+    float* rec = fin_smem + (size_t)warp * ((nrec + 3) & ~3);
+    const float* src = part + (size_t)b * nrec;
+    if ((nrec & 3) == 0) {
+      for (int i = lane; i < nrec / 4; i += 32)
+        *reinterpret_cast<float4*>(rec + 4 * i) = *reinterpret_cast<const float4*>(src + 4 * i);
+    } else {
+      for (int i = lane; i < nrec; i += 32) rec[i] = src[i];
+    }
+    __syncwarp();
+    float m[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) m[i] = -INFINITY;
+    for (int s = lane; s < nslices; s += 32) {
+      const float* r = rec + s * REC;
+      m[0] = fmaxf(m[0], r[0]);
+      m[1] = fmaxf(m[1], r[3]);
+#pragma unroll
+      for (int v = 0; v < NCROPS; ++v) m[2 + v] = fmaxf(m[2 + v], r[6 + 2 * v]);
+    }
+#pragma unroll
+    for (int i = 0; i < NR; ++i) m[i] = warp_max(m[i]);
+    float z[NR], a[2];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) z[i] = 0.f;
+    a[0] = a[1] = 0.f;
+    for (int s = lane; s < nslices; s += 32) {
+      const float* r = rec + s * REC;
+#pragma unroll
+      for (int iq = 0; iq < 2; ++iq) {
+        const float f = ex2(r[3 * iq] - m[iq]);
+        z[iq] = fmaf(r[3 * iq + 1], f, z[iq]);
+        a[iq] = fmaf(r[3 * iq + 2], f, a[iq]);
+      }
+#pragma unroll
+      for (int v = 0; v < NCROPS; ++v) z[2 + v] = fmaf(r[7 + 2 * v], ex2(r[6 + 2 * v] - m[2 + v]), z[2 + v]);
+    }
+#pragma unroll
+    for (int i = 0; i < NR; ++i) z[i] = warp_sum(z[i]);
+    a[0] = warp_sum(a[0]);
+    a[1] = warp_sum(a[1]);
+    if (lane == 0) {
+      float loss = 0.f;
+#pragma unroll
+      for (int v = 0; v < NCROPS; ++v) {
+        const float l2 = m[2 + v] + lg2(z[2 + v]);  // log2-domain lse of s_v/ts
+        row_stats[(size_t)v * B + b] = l2;
+        loss += (v < 2 ? 1.f : 2.f) * l2;
+      }
+      loss *= kLn2;
+#pragma unroll
+      for (int iq = 0; iq < 2; ++iq) {
+        row_stats[(size_t)(NCROPS + iq) * B + b] = m[iq] + lg2(z[iq]);
+        loss -= inv_ts * (a[iq] / z[iq]);
+      }
+      sample_loss[b] = loss;
+    }
+  }
+  // ---- the warp that arrives last sums the per-sample losses (fixed order) ---------------------------
+  int last = 0;
+  if (lane == 0) {
+    __threadfence();
+    last = atomicAdd(done_counter, 1u) == (unsigned)(2 * nfin - 1);
+  }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (last) {
+    __threadfence();
+    float acc = 0.f;
+    for (int i = lane; i < B; i += 32) acc += __ldcg(sample_loss + i);
+    acc = warp_sum(acc);
+    if (lane == 0) *loss_out = acc * inv_norm;
+  }
+}
+
 // Gradient pass: ds[v,b,k] = g * ( n_v * softmax(s_v/ts)_k - sum_{iq != v} q_iq,k ),
 // g = grad_out / (ts * n_terms * B).  Purely element-wise given the saved row statistics.
 template <typename T, int NCROPS>
@@ -394,7 +520,7 @@ __global__ void center_ema_kernel(const float* __restrict__ center, const float*
 // ---- host side ---------------------------------------------------------------------------
 struct DinoPlan {
   int U, cols_per_slice, nslices, ngroups;
-  size_t off_part, off_colsum, off_sample, total;
+  size_t off_part, off_colsum, off_sample, off_counter, total;
 };
 
 static DinoPlan make_plan(int B, int K, int ncrops, int elem_bytes) {
@@ -429,8 +555,35 @@ static DinoPlan make_plan(int B, int K, int ncrops, int elem_bytes) {
   p.off_colsum = o; o += (size_t)p.ngroups * K * sizeof(float);
   o = (o + 255) & ~(size_t)255;
   p.off_sample = o; o += (size_t)B * sizeof(float);
+  o = (o + 255) & ~(size_t)255;
+  p.off_counter = o; o += 256;
   p.total = (o + 255) & ~(size_t)255;
   return p;
+}
+
+// dino_finish: shared-memory staging of two samples' slice records; falls back to the two small
+// kernels when that does not fit (huge out_dim with fp32 logits and many crops)
+template <int NCROPS>
+static bool launch_finish(const float* part, int B, int nslices, float inv_ts, float* row_stats, float* sample_loss,
+                          float* loss_out, unsigned* counter, const float* colsum_part, int ngroups, int K,
+                          float* colsum_out, const float* center, float* center_out, float mom, float om,
+                          cudaStream_t st) {
+  const size_t nrec = ((size_t)nslices * rec_floats(NCROPS) + 3) & ~(size_t)3;
+  const size_t smem = 2 * nrec * sizeof(float);
+  if (smem > 200 * 1024) return false;
+  auto kern = dino_finish<NCROPS>;
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  const int nfin = (B + 1) / 2;
+  const int ncol = (K / 4 + 63) / 64;
+  const float inv_norm = 1.f / ((float)(2 * NCROPS - 2) * (float)B);
+  kern<<<nfin + ncol, 64, smem, st>>>(part, B, nslices, inv_ts, row_stats, sample_loss, nfin, inv_norm, loss_out,
+                                      counter, colsum_part, ngroups, K, colsum_out, center, center_out,
+                                      (float)(2 * B), mom, om);
+  return true;
 }
 
 template <typename T, int NCROPS>
@@ -441,15 +594,19 @@ static int launch_fwd(const void* student, const void* teacher, const float* cen
   float* part = reinterpret_cast<float*>(ws + p.off_part);
   float* colsum_part = reinterpret_cast<float*>(ws + p.off_colsum);
   float* sample_loss = reinterpret_cast<float*>(ws + p.off_sample);
+  unsigned* counter = reinterpret_cast<unsigned*>(ws + p.off_counter);
   dim3 grid((p.nslices + kDinoWarps - 1) / kDinoWarps, p.ngroups);
   if (K % p.cols_per_slice == 0)
     dino_fwd_partial<T, NCROPS, false><<<grid, kDinoThreads, 0, st>>>(
         (const T*)student, (const T*)teacher, center, B, K, inv_ts * kLog2e, inv_tt * kLog2e,
-        p.nslices, p.ngroups, part, colsum_part, 0, B);
+        p.nslices, p.ngroups, part, colsum_part, 0, B, counter);
   else
     dino_fwd_partial<T, NCROPS, true><<<grid, kDinoThreads, 0, st>>>(
         (const T*)student, (const T*)teacher, center, B, K, inv_ts * kLog2e, inv_tt * kLog2e,
-        p.nslices, p.ngroups, part, colsum_part, 0, B);
+        p.nslices, p.ngroups, part, colsum_part, 0, B, counter);
+  if (launch_finish<NCROPS>(part, B, p.nslices, inv_ts, row_stats, sample_loss, loss_out, counter, colsum_part,
+                            p.ngroups, K, colsum_out, center, center_out, mom, om, st))
+    return check_launch("lafs_dino_fwd");
   dino_rows_finalize<NCROPS><<<(B + kFinalizeWarps - 1) / kFinalizeWarps, kFinalizeWarps * 32, 0, st>>>(
       part, B, p.nslices, inv_ts, row_stats, sample_loss, 0, B);
   const float inv_norm = 1.f / ((float)(2 * NCROPS - 2) * (float)B);
@@ -481,7 +638,7 @@ static int launch_bwd(const void* student, const void* teacher, const float* cen
 constexpr int kMaxColsumRows = 64;
 struct FusedPlan {
   int wave, nwaves, ngroups, nslices, cols_per_slice;
-  size_t off_part, off_colsum, off_sample, total;
+  size_t off_part, off_colsum, off_sample, off_counter, total;
 };
 static FusedPlan make_fused_plan(int B, int K, int ncrops, int elem_bytes) {
   FusedPlan p;
@@ -514,6 +671,8 @@ static FusedPlan make_fused_plan(int B, int K, int ncrops, int elem_bytes) {
   p.off_colsum = o; o += (size_t)p.nwaves * p.ngroups * K * sizeof(float);
   o = (o + 255) & ~(size_t)255;
   p.off_sample = o; o += (size_t)B * sizeof(float);
+  o = (o + 255) & ~(size_t)255;
+  p.off_counter = o; o += 256;
   p.total = (o + 255) & ~(size_t)255;
   return p;
 }
@@ -529,6 +688,7 @@ static int launch_fused(const void* student, const void* teacher, const float* c
   float* sample_loss = reinterpret_cast<float*>(ws + p.off_sample);
   const float gcoef = inv_ts / ((float)(2 * NCROPS - 2) * (float)B);
   const bool ragged = K % p.cols_per_slice != 0;
+  unsigned* counter = reinterpret_cast<unsigned*>(ws + p.off_counter);
   for (int w = 0; w < p.nwaves; ++w) {
     const int b0 = w * p.wave;
     const int bc = (B - b0) < p.wave ? (B - b0) : p.wave;
@@ -537,11 +697,20 @@ static int launch_fused(const void* student, const void* teacher, const float* c
     if (!ragged)
       dino_fwd_partial<T, NCROPS, false><<<grid, kDinoThreads, 0, st>>>(
           (const T*)student, (const T*)teacher, center, B, K, inv_ts * kLog2e, inv_tt * kLog2e,
-          p.nslices, p.ngroups, part, cpart, b0, bc);
+          p.nslices, p.ngroups, part, cpart, b0, bc, counter);
     else
       dino_fwd_partial<T, NCROPS, true><<<grid, kDinoThreads, 0, st>>>(
           (const T*)student, (const T*)teacher, center, B, K, inv_ts * kLog2e, inv_tt * kLog2e,
-          p.nslices, p.ngroups, part, cpart, b0, bc);
+          p.nslices, p.ngroups, part, cpart, b0, bc, counter);
+    if (p.nwaves == 1 &&
+        launch_finish<NCROPS>(part, B, p.nslices, inv_ts, row_stats, sample_loss, loss_out, counter, colsum_part,
+                              p.ngroups, K, colsum_out, center, center_out, mom, om, st)) {
+      dim3 gb1((K / VEC + kDinoThreads - 1) / kDinoThreads, B);
+      dino_bwd_kernel<T, NCROPS><<<gb1, kDinoThreads, 0, st>>>(
+          (const T*)student, (const T*)teacher, center, row_stats, grad_out, B, K, inv_ts * kLog2e,
+          inv_tt * kLog2e, gcoef, (T*)grad_student, 0);
+      return check_launch("lafs_dino_fwd_bwd");
+    }
     dino_rows_finalize<NCROPS><<<(bc + kFinalizeWarps - 1) / kFinalizeWarps, kFinalizeWarps * 32, 0, st>>>(
         part, B, p.nslices, inv_ts, row_stats, sample_loss, b0, bc);
     dim3 gb((K / VEC + kDinoThreads - 1) / kDinoThreads, bc);

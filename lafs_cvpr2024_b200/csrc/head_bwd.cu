@@ -12,6 +12,7 @@
 // layout: atoms of 64 (MN, contiguous 128 B) x 8 (K rows), SBO = 1024 B between K groups,
 // LBO = bytes between consecutive 64-wide MN blocks; TMA boxes {64 MN, 64 K} land in exactly
 // that layout.
+#include <stdlib.h>
 #include "umma.cuh"
 #include "../../include/lafs_b200.h"
 
@@ -47,7 +48,11 @@ struct GemmParams {
   long long ldo, split_stride;
 };
 
-template <bool A_MN>
+// CL > 1: the CL CTAs of a cluster work on CL consecutive M tiles of the same (N tile, K split) in
+// lock step and share the B operand: each fetches 1/CL of every B k block (one {64 n, 64 k} box of
+// four) and multicasts it to the cluster, so the L2 -> SM fill of B drops by CL (dE: every M tile
+// contracts against the same W_hat range, and that fill is what bounds the single-CTA kernel).
+template <bool A_MN, int CL>
 __global__ void __launch_bounds__(gb::kThreads, 1)
 gemm_bwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const GemmParams p) {
@@ -68,30 +73,37 @@ gemm_bwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tmap_a);
     prefetch_tensormap(&tmap_b);
-    for (int i = 0; i < kStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, CL); }
     for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 2 * kBN);
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+  // work item = (M group of CL tiles, N tile, K split); CTA `rank` of the cluster takes M tile
+  // group * CL + rank (tiles past the end load zeros and store nothing)
+  const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int first = blockIdx.x / CL, stride = gridDim.x / CL;
+  const int m_groups = (p.m_tiles + CL - 1) / CL;
+  const int total_tiles = m_groups * p.n_tiles * p.splits;
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t cnt = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first; tile < total_tiles; tile += stride) {
         const int split = tile % p.splits;
         const int mn = tile / p.splits;
-        const int nt = mn % p.n_tiles, mt = mn / p.n_tiles;
+        const int nt = mn % p.n_tiles, mt = (mn / p.n_tiles) * CL + rank;
         const int kb0 = split * p.kblocks_per_split;
         const int kb1 = min(kb0 + p.kblocks_per_split, p.kblocks_total);
         for (int kb = kb0; kb < kb1; ++kb, ++cnt) {
           const int st = cnt % kStages;
-          mbar_wait(empty + st, ((cnt / kStages) & 1) ^ 1);
+          mbar_wait(empty + st, ((cnt / kStages) & 1) ^ 1);   // all CL consumers of this slot are done
           mbar_arrive_expect_tx(full + st, kStageA + kStageB);
           uint8_t* da = s_a + st * kStageA;
           uint8_t* db = s_b + st * kStageB;
@@ -102,8 +114,10 @@ gemm_bwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             tma_load_2d(da, &tmap_a, full + st, kb * kBK, mt * kBM);
           }
 #pragma unroll
-          for (int q = 0; q < 4; ++q)   // B global [K rows, N cols]: four boxes {64 n, 64 k}
-            tma_load_2d(db + q * 8192, &tmap_b, full + st, nt * kBN + q * 64, kb * kBK);
+          for (int q = 0; q < 4; ++q) {   // B global [K rows, N cols]: four boxes {64 n, 64 k}
+            if (CL == 1) tma_load_2d(db + q * 8192, &tmap_b, full + st, nt * kBN + q * 64, kb * kBK);
+            else if (q % CL == rank) tma_load_2d_mc(db + q * 8192, &tmap_b, full + st, nt * kBN + q * 64, kb * kBK, kMask);
+          }
         }
       }
     }
@@ -111,7 +125,7 @@ gemm_bwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(kBM, kBN, A_MN ? 1 : 0, 1);
       uint32_t cnt = 0, acnt = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acnt) {
+      for (int tile = first; tile < total_tiles; tile += stride, ++acnt) {
         const int split = tile % p.splits;
         const int kb0 = split * p.kblocks_per_split;
         const int kb1 = min(kb0 + p.kblocks_per_split, p.kblocks_total);
@@ -134,7 +148,8 @@ gemm_bwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             const uint64_t db = make_desc_mn_sw128(b_addr + kk * 2048, 8192);
             mma_f16_ss(d_tmem, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
           }
-          mma_commit(empty + st);
+          if (CL > 1) mma_commit_mc(empty + st, kMask);
+          else mma_commit(empty + st);
         }
         mma_commit(acc_full + buf);
       }
@@ -142,10 +157,10 @@ gemm_bwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   } else {
     const int quarter = warp & 3;
     uint32_t acnt = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acnt) {
+    for (int tile = first; tile < total_tiles; tile += stride, ++acnt) {
       const int split = tile % p.splits;
       const int mn = tile / p.splits;
-      const int nt = mn % p.n_tiles, mt = mn / p.n_tiles;
+      const int nt = mn % p.n_tiles, mt = (mn / p.n_tiles) * CL + rank;
       const int buf = acnt & 1;
       mbar_wait(acc_full + buf, (acnt >> 1) & 1);
       tc_fence_after();
@@ -192,11 +207,269 @@ gemm_bwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all();
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 2 * kBN);
   }
+}
+
+// ---- dW with the F.normalize Jacobian fused into the epilogue ---------------------------------------
+// One CTA owns 128 classes x ALL D columns (D <= 512 = the whole TMEM), so after the K = batch loop a
+// TMEM lane holds a complete row of dW_hat and the Jacobian
+//     grad_w[c,:] = (dW_hat[c,:] - w_hat[c,:] * <w_hat[c,:], dW_hat[c,:]>) * inv_norm_w[c]
+// is applied on the way out: grad_w is written exactly once (C*D*4 bytes) instead of the
+// write + read + read(w_hat) + write of a GEMM followed by normalize_bwd_kernel.
+// Every class tile contracts against the SAME E_hat [B, D]; with K = B = 512 a tile moves 128 KB of
+// G and 512 KB of E_hat for 67 MFLOP, i.e. the L2 -> SM fill bounds the kernel.  CL CTAs of a
+// cluster therefore work on CL neighbouring class tiles in lock step and each fetches 1/CL of every
+// E_hat k block, multicast to the whole cluster (E_hat fill traffic / CL).
+// Warps: 0 TMA, 1 UMMA, 2..9 epilogue (two per TMEM lane quarter, half of the columns each; the row
+// dot product is combined through shared memory).
+namespace dwf {
+constexpr int kBM = 128, kBK = 64;
+constexpr int kThreads = 320;
+constexpr int kStageA = kBM * kBK * 2;                  // 16 KB: two {64 m, 64 k} boxes
+constexpr int kMaxPieces = 8;                           // 32-column pieces per epilogue warp: D / 2 <= 256
+constexpr int kPitch = 36;
+constexpr int kStageOut = 8 * 32 * kPitch * 4;          // 36,864 B: a [32 x 32] fp32 block per epilogue warp
+__host__ __device__ constexpr int stage_b(int D) { return D * kBK * 2; }   // D/64 boxes of 8 KB
+}  // namespace dwf
+
+struct DwParams {
+  int C, D, B;               // M = classes, N = D, K = batch
+  int m_tiles, kblocks, stages, tmem_cols, super_tiles;
+  const __nv_bfloat16* w_hat;
+  const float* inv_norm;
+  float* out;                // [C][D] fp32
+};
+
+template <int CL>
+__global__ void __launch_bounds__(dwf::kThreads, 1)
+dw_fused_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_e, const DwParams p) {
+  using namespace dwf;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int stage_bytes = kStageA + stage_b(p.D);
+  float* s_out = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes);
+  float* s_dot = s_out + kStageOut / 4;                              // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_dot + 256);
+  uint64_t* full = bars;                 // stages
+  uint64_t* empty = bars + p.stages;     // stages
+  uint64_t* acc_full = empty + p.stages; // 1
+  uint64_t* acc_empty = acc_full + 1;    // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmap_g);
+    prefetch_tensormap(&tmap_e);
+    // a stage is refilled by every CTA of the cluster, so all CL consumers must have released it
+    for (int i = 0; i < p.stages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, CL); }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 8);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  if (CL > 1) cluster_sync_all();
+  else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int nboxes = p.D / 64;
+  const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / CL, nclusters = gridDim.x / CL;
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
+  // lock step: every CTA of a cluster runs the same number of tiles (tiles past the end are all-zero)
+#define LAFS_DW_TILES for (int sup = cluster_id; sup < p.super_tiles; sup += nclusters)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t cnt = 0;
+      LAFS_DW_TILES {
+        const int tile = sup * CL + rank;
+        for (int kb = 0; kb < p.kblocks; ++kb, ++cnt) {
+          const int st = cnt % p.stages;
+          mbar_wait(empty + st, ((cnt / p.stages) & 1) ^ 1);
+          mbar_arrive_expect_tx(full + st, (uint32_t)stage_bytes);
+          uint8_t* da = smem + (size_t)st * stage_bytes;
+          uint8_t* db = da + kStageA;
+          tma_load_2d(da, &tmap_g, full + st, tile * kBM, kb * kBK);            // G^T: {64 classes, 64 batch rows}
+          tma_load_2d(da + 8192, &tmap_g, full + st, tile * kBM + 64, kb * kBK);
+          for (int q = rank; q < nboxes; q += CL) {                              // E_hat: {64 d, 64 batch rows}
+            if (CL > 1) tma_load_2d_mc(db + q * 8192, &tmap_e, full + st, q * 64, kb * kBK, kMask);
+            else tma_load_2d(db + q * 8192, &tmap_e, full + st, q * 64, kb * kBK);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t cnt = 0, tcnt = 0;
+      LAFS_DW_TILES {
+        mbar_wait(acc_empty, (tcnt & 1) ^ 1);      // the epilogue has drained the previous tile
+        tc_fence_after();
+        for (int kb = 0; kb < p.kblocks; ++kb, ++cnt) {
+          const int st = cnt % p.stages;
+          mbar_wait(full + st, (cnt / p.stages) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + (size_t)st * stage_bytes);
+          const uint32_t b_addr = a_addr + kStageA;
+          for (int n0 = 0; n0 < p.D; n0 += 256) {
+            const int nsub = p.D - n0 < 256 ? p.D - n0 : 256;
+            const uint32_t idesc = make_idesc_bf16(kBM, nsub, 1, 1);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t da = make_desc_mn_sw128(a_addr + kk * 2048, 8192);
+              const uint64_t db = make_desc_mn_sw128(b_addr + (n0 / 64) * 8192 + kk * 2048, 8192);
+              mma_f16_ss(tmem_base + (uint32_t)n0, da, db, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+            }
+          }
+          if (CL > 1) mma_commit_mc(empty + st, kMask);
+          else mma_commit(empty + st);
+        }
+        mma_commit(acc_full);
+        ++tcnt;
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int ncol = p.D / 2;                   // columns of this warp: [half*ncol, (half+1)*ncol), a multiple of 32
+    const int col_lo = half * ncol;
+    float* stage = s_out + (warp - 2) * (32 * kPitch);
+    uint32_t tcnt = 0;
+    LAFS_DW_TILES {
+      const int tile = sup * CL + rank;
+      const int row_base = tile * kBM + quarter * 32;
+      const int grow = row_base + lane;           // the class this lane's TMEM row belongs to
+      const bool ok = grow < p.C;
+      const __nv_bfloat16* wrow = p.w_hat + (size_t)(ok ? grow : 0) * p.D + col_lo;
+      // This lane's half row of w_hat (<= 256 bf16 = 32 x 16 B) is fetched into registers BEFORE the
+      // accumulator is waited for: the loads (one 16-byte piece per row per instruction, i.e. latency
+      // bound) overlap the tile's MMA phase, and both epilogue passes then run from registers + TMEM.
+      uint4 w[kMaxPieces * 4];
+#pragma unroll
+      for (int i = 0; i < kMaxPieces; ++i) {
+        if (i * 32 < ncol) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) w[i * 4 + q] = ld_stream_u4(wrow + i * 32 + q * 8);
+        }
+      }
+      const float inv = ok ? __ldg(p.inv_norm + grow) : 0.f;
+      mbar_wait(acc_full, tcnt & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col_lo;
+      // ---- pass 1: <w_hat[c,:], dW_hat[c,:]> ------------------------------------------------------
+      float dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < kMaxPieces; ++i) {
+        if (i * 32 < ncol) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + (uint32_t)(i * 32), v);
+          tmem_ld_wait();
+          float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t ww[4] = {w[i * 4 + q].x, w[i * 4 + q].y, w[i * 4 + q].z, w[i * 4 + q].w};
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              d0 = fmaf(__uint_as_float(v[q * 8 + 2 * h]), Half2Ops<__nv_bfloat16>::lo(ww[h]), d0);
+              d1 = fmaf(__uint_as_float(v[q * 8 + 2 * h + 1]), Half2Ops<__nv_bfloat16>::hi(ww[h]), d1);
+            }
+          }
+          dot += d0 + d1;
+        }
+      }
+      s_dot[half * 128 + quarter * 32 + lane] = dot;
+      asm volatile("bar.sync 1, 256;" ::: "memory");       // the 8 epilogue warps
+      dot = s_dot[quarter * 32 + lane] + s_dot[128 + quarter * 32 + lane];
+      const float ndot = -dot * inv;
+      // ---- pass 2: Jacobian, transposed through shared memory into full 128-byte row segments -------
+#pragma unroll
+      for (int i = 0; i < kMaxPieces; ++i) {
+        if (i * 32 < ncol) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + (uint32_t)(i * 32), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t ww[4] = {w[i * 4 + q].x, w[i * 4 + q].y, w[i * 4 + q].z, w[i * 4 + q].w};
+            float o[8];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {   // (v - w*dot)*inv
+              o[2 * h] = fmaf(Half2Ops<__nv_bfloat16>::lo(ww[h]), ndot, __uint_as_float(v[q * 8 + 2 * h]) * inv);
+              o[2 * h + 1] = fmaf(Half2Ops<__nv_bfloat16>::hi(ww[h]), ndot, __uint_as_float(v[q * 8 + 2 * h + 1]) * inv);
+            }
+            *reinterpret_cast<float4*>(stage + lane * kPitch + q * 8) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(stage + lane * kPitch + q * 8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+          }
+          __syncwarp();
+          const int c0 = col_lo + i * 32;
+#pragma unroll
+          for (int r8 = 0; r8 < 8; ++r8) {
+            const int rr = r8 * 4 + (lane >> 3), part = lane & 7;       // 8 lanes cover one 128-byte row segment
+            const float4 val = *reinterpret_cast<const float4*>(stage + rr * kPitch + part * 4);
+            if (row_base + rr < p.C)
+              st_stream_f4(p.out + (size_t)(row_base + rr) * p.D + c0 + part * 4, val);
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
+      asm volatile("bar.sync 1, 256;" ::: "memory");       // s_dot is rewritten by the next tile
+      ++tcnt;
+    }
+  }
+#undef LAFS_DW_TILES
+  tc_fence_before();
+  if (CL > 1) cluster_sync_all();    // peers may still multicast into / arrive on this CTA's shared memory
+  else __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+template <int CL>
+static int launch_dw_fused(const CUtensorMap& ta, const CUtensorMap& tb, DwParams q, int smem, cudaStream_t st,
+                           bool* launched) {
+  *launched = false;
+  auto kern = dw_fused_kernel<CL>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  LAFS_REQUIRE(e == cudaSuccess, LAFS_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  q.super_tiles = (q.m_tiles + CL - 1) / CL;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(dwf::kThreads);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int nclusters = kNumSMs;
+  if (CL > 1) {
+    static int cached = -1, cached_smem = -1;           // once per process (see max_clusters)
+    if (cached < 0 || cached_smem != smem) {
+      cfg.gridDim = dim3(CL);
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+      cached = n; cached_smem = smem;
+    }
+    nclusters = cached;
+    if (nclusters < 1) return LAFS_OK;      // not launched: the caller falls back to a smaller cluster
+    if (nclusters * CL < (kNumSMs * 3) / 4) return LAFS_OK;   // too many SMs left idle by the cluster shape
+    if (nclusters * CL > kNumSMs) nclusters = kNumSMs / CL;
+  }
+  if (nclusters > q.super_tiles) nclusters = q.super_tiles;
+  cfg.gridDim = dim3(nclusters * CL);
+  e = cudaLaunchKernelEx(&cfg, kern, ta, tb, q);
+  LAFS_REQUIRE(e == cudaSuccess, LAFS_ERR_CUDA, "dw_fused_kernel launch: %s", cudaGetErrorString(e));
+  *launched = true;
+  return check_launch("lafs_head_bwd_weight(fused)");
 }
 
 // out[r, :] = (g[r, :] - x_hat[r, :] * <x_hat[r, :], g[r, :]>) * inv_norm[r]   (F.normalize backward)
@@ -278,15 +551,65 @@ static int encode_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uin
   return LAFS_OK;
 }
 
-template <bool A_MN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-  auto kern = gemm_bwd_kernel<A_MN>;
+// co-resident clusters of CL CTAs of gemm_bwd_kernel (0 if the query fails)
+template <bool A_MN, int CL>
+static int max_clusters_query();
+template <bool A_MN, int CL>
+static int max_clusters() {
+  if (CL == 1) return kNumSMs;
+  // a property of (kernel, shared-memory size, device model): queried once per process (one process
+  // drives one GPU model; a benign race at worst repeats the query)
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  cached = max_clusters_query<A_MN, CL>();
+  return cached;
+}
+template <bool A_MN, int CL>
+static int max_clusters_query() {
+  auto kern = gemm_bwd_kernel<A_MN, CL>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gb::kSmem) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(CL);
+  cfg.blockDim = dim3(gb::kThreads);
+  cfg.dynamicSmemBytes = gb::kSmem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n * CL > kNumSMs ? kNumSMs / CL : n;
+}
+
+template <bool A_MN, int CL>
+static int launch_gemm_cl(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int nclusters, cudaStream_t st) {
+  auto kern = gemm_bwd_kernel<A_MN, CL>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gb::kSmem);
   LAFS_REQUIRE(e == cudaSuccess, LAFS_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  const int total = p.m_tiles * p.n_tiles * p.splits;
-  const int grid = total < kNumSMs ? total : kNumSMs;
-  kern<<<grid, gb::kThreads, gb::kSmem, st>>>(ta, tb, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(gb::kThreads);
+  cfg.dynamicSmemBytes = gb::kSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  const int total = ((p.m_tiles + CL - 1) / CL) * p.n_tiles * p.splits;
+  cfg.gridDim = dim3((total < nclusters ? total : nclusters) * CL);
+  e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+  LAFS_REQUIRE(e == cudaSuccess, LAFS_ERR_CUDA, "gemm_bwd_kernel launch: %s", cudaGetErrorString(e));
   return check_launch("gemm_bwd_kernel");
+}
+
+template <bool A_MN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  return launch_gemm_cl<A_MN, 1>(ta, tb, p, kNumSMs, st);
 }
 
 static int de_splits(int B, int C_local, int D) {
@@ -325,13 +648,32 @@ extern "C" int lafs_head_bwd_embed(const void* grad_bf16, long long ldg, const v
   if (rc) return rc;
   GemmParams p{};
   p.M = B; p.N = D; p.K = C_local;
-  p.m_tiles = (B + 127) / 128; p.n_tiles = (D + 255) / 256; p.splits = splits;
+  p.m_tiles = (B + 127) / 128; p.n_tiles = (D + 255) / 256;
   p.kblocks_total = (C_local + 63) / 64;
-  p.kblocks_per_split = (p.kblocks_total + splits - 1) / splits;
-  p.splits = (p.kblocks_total + p.kblocks_per_split - 1) / p.kblocks_per_split;   // no empty K ranges
   p.out = (float*)workspace; p.ldo = D; p.split_stride = (long long)B * D;
+  // W_hat multicast width (LAFS_DE_CLUSTER: 1, 2 or 4): the widest cluster shape that still fills
+  // most of the machine with one wave of (M group, N tile, K split) work items
+  int want = 4;
+  if (const char* e = getenv("LAFS_DE_CLUSTER")) want = atoi(e);
+  int cl = 1, nclusters = kNumSMs;
+  if (want >= 4 && p.m_tiles % 4 == 0) {
+    const int n4 = max_clusters<false, 4>();
+    if (n4 * 4 >= (kNumSMs * 3) / 4) { cl = 4; nclusters = n4; }
+  }
+  if (cl == 1 && want >= 2 && p.m_tiles % 2 == 0) {
+    const int n2 = max_clusters<false, 2>();
+    if (n2 * 2 >= (kNumSMs * 3) / 4) { cl = 2; nclusters = n2; }
+  }
+  int s_max = nclusters / ((p.m_tiles / cl) * p.n_tiles);   // one wave
+  if (s_max < 1) s_max = 1;
+  if (s_max > splits) s_max = splits;                       // the workspace was sized for `splits`
+  if (s_max > p.kblocks_total) s_max = p.kblocks_total;
+  p.kblocks_per_split = (p.kblocks_total + s_max - 1) / s_max;
+  p.splits = (p.kblocks_total + p.kblocks_per_split - 1) / p.kblocks_per_split;   // no empty K ranges
   cudaStream_t st = (cudaStream_t)stream;
-  rc = launch_gemm<false>(ta, tb, p, st);
+  if (cl == 4) rc = launch_gemm_cl<false, 4>(ta, tb, p, nclusters, st);
+  else if (cl == 2) rc = launch_gemm_cl<false, 2>(ta, tb, p, nclusters, st);
+  else rc = launch_gemm_cl<false, 1>(ta, tb, p, kNumSMs, st);
   if (rc) return rc;
   const long long n = (long long)B * D;
   split_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const float*)workspace, p.splits, n, n, grad_e_hat);
@@ -352,12 +694,41 @@ extern "C" int lafs_head_bwd_weight(const void* grad_bf16, long long ldg, const 
   if (rc) return rc;
   rc = encode_bf16_2d(&tb, e_hat, (uint64_t)B, (uint64_t)D, (uint64_t)D * 2, 64, 64);                  // MN-major B: [K=B, N=D]
   if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const char* unfused = getenv("LAFS_DW_UNFUSED");
+  if (D <= 512 && !(unfused && atoi(unfused) != 0)) {
+    // fused path: full rows in TMEM, Jacobian in the epilogue
+    DwParams q{};
+    q.C = C_local; q.D = D; q.B = B;
+    q.m_tiles = (C_local + 127) / 128;
+    q.kblocks = (B + 63) / 64;
+    q.tmem_cols = D <= 32 ? 32 : D <= 64 ? 64 : D <= 128 ? 128 : D <= 256 ? 256 : 512;
+    const int stage_bytes = dwf::kStageA + dwf::stage_b(D);
+    const int tail = dwf::kStageOut + 1024 /*dots*/ + 1024 /*align*/ + 256 /*barriers*/;
+    q.stages = (227 * 1024 - tail) / stage_bytes;
+    if (q.stages > 6) q.stages = 6;
+    LAFS_REQUIRE(q.stages >= 2, LAFS_ERR_ARG, "lafs_head_bwd_weight: D=%d leaves no room for a 2-stage pipeline", D);
+    q.w_hat = (const __nv_bfloat16*)w_hat; q.inv_norm = inv_norm_w; q.out = grad_w;
+    const int smem = q.stages * stage_bytes + tail;
+    int cl = 4;                                        // E_hat multicast width (LAFS_DW_CLUSTER: 1, 2 or 4)
+    if (const char* e = getenv("LAFS_DW_CLUSTER")) cl = atoi(e);
+    const int nboxes = D / 64;
+    bool launched = false;
+    if (cl >= 4 && nboxes % 4 == 0 && q.m_tiles >= 4) {
+      rc = launch_dw_fused<4>(ta, tb, q, smem, st, &launched);
+      if (rc || launched) return rc;
+    }
+    if (cl >= 2 && nboxes % 2 == 0 && q.m_tiles >= 2) {
+      rc = launch_dw_fused<2>(ta, tb, q, smem, st, &launched);
+      if (rc || launched) return rc;
+    }
+    return launch_dw_fused<1>(ta, tb, q, smem, st, &launched);
+  }
   GemmParams p{};
   p.M = C_local; p.N = D; p.K = B;
   p.m_tiles = (C_local + 127) / 128; p.n_tiles = (D + 255) / 256; p.splits = 1;
   p.kblocks_total = (B + 63) / 64; p.kblocks_per_split = p.kblocks_total;
   p.out = grad_w; p.ldo = D; p.split_stride = 0;
-  cudaStream_t st = (cudaStream_t)stream;
   rc = launch_gemm<true>(ta, tb, p, st);
   if (rc) return rc;
   normalize_bwd_kernel<<<(C_local + 7) / 8, 256, 0, st>>>(grad_w, (const __nv_bfloat16*)w_hat, inv_norm_w, C_local, D, grad_w);

@@ -62,7 +62,9 @@ def _prep(x, want_inv=False):
 
 
 def _round8(n):
-    return (n + 7) // 8 * 8
+    """leading dimension of the bf16 logit gradient: a multiple of 16 elements keeps every row 32-byte
+    aligned (256-bit stores in the gradient epilogue; the GEMM operands need a multiple of 8)."""
+    return (n + 15) // 16 * 16
 
 
 def _head_backward(G, ldg, e_hat, w_hat, inv_e, inv_w, B, C, D, sharded):

@@ -10,8 +10,8 @@ What runs where
   * extraction + patch_to_embedding without gradients            -> lafs_gather_embed_fwd (tcgen05)
   * margin head `self.loss`                                      -> CosFace / ArcFace    (tcgen05)
   * transformer blocks, LayerNorm, MobileNetV3 landmark trunk    -> stock PyTorch, as in the
-    reference (outside the hot path); the trunk class is taken from the
-    reference checkout (`face_pre_pro.mobilenet.MobileNetV3_backbone`) or injected via `stn=`.
+    reference (outside the hot path); the trunk (landmark_trunk.py) keeps the
+    reference's module tree / checkpoint keys, and another module can be injected via `stn=`.
 
 Checkpoint compatibility: parameter / buffer names equal the reference's (`pos_embedding`,
 `patch_to_embedding.{weight,bias}`, `cls_token`, `transformer.layers.{i}.{0,1}.fn.…`,
@@ -31,14 +31,10 @@ MIN_NUM_PATCHES = 15  # ViT_face.py:21
 
 
 def _default_trunk():
-    try:
-        from face_pre_pro.mobilenet import MobileNetV3_backbone  # the reference's own trunk
-    except Exception as e:  # pragma: no cover - depends on the checkout
-        raise RuntimeError(
-            "the MobileNetV3 landmark trunk is outside the hot path and is not re-implemented here: run "
-            "inside the reference checkout (face_pre_pro.mobilenet importable) or pass stn=<module "
-            "mapping [B,3,112,112] -> [B,160,h,w]>") from e
-    return MobileNetV3_backbone(mode="large")
+    """The reference's `MobileNetV3_backbone(mode='large')` (ViT_face.py:611,1269): same module tree and
+    checkpoint keys, restated in landmark_trunk.py (stock PyTorch convolutions, outside the hot path)."""
+    from .landmark_trunk import MobileNetV3LargeTrunk
+    return MobileNetV3LargeTrunk()
 
 
 class DropPath(nn.Module):

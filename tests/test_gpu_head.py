@@ -182,3 +182,47 @@ def test_cosface_forward_logits_backward_golden(P, golden):
     ref_gx, ref_gw = T(g["grad_x_hard"]), T(g["grad_w_hard"])
     assert (xg.grad.cpu() - ref_gx).abs().max() <= 2e-2 * ref_gx.abs().max()
     assert (h.weight.grad.cpu() - ref_gw).abs().max() <= 2e-2 * ref_gw.abs().max()
+
+
+def _step_outputs(P, B, C, D, kind, env):
+    """loss, row lse, dE, dW of one fused-loss step under the given kernel-variant switches."""
+    import os
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        torch.manual_seed(1234)
+        x = torch.randn(B, D)
+        w = torch.randn(C, D) * 0.05
+        lab = torch.randint(0, C, (B,))
+        cls = P.CosFace if kind == "cosface" else P.ArcFace
+        h = make_head(P, cls, w)
+        xg = x.cuda().requires_grad_(True)
+        loss = h.forward_loss(xg, lab.cuda())
+        loss.backward()
+        logits = h(x.cuda(), lab.cuda())
+        torch.cuda.synchronize()
+        return float(loss), xg.grad.cpu(), h.weight.grad.cpu(), logits.cpu()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("B,C,D", [(512, 9001, 512), (256, 4099, 256), (130, 3000, 128), (1024, 2500, 512)])
+@pytest.mark.parametrize("kind", ["cosface", "arcface"])
+def test_head_kernel_variants_agree(P, B, C, D, kind):
+    """CTA-pair (cta_group::2) forward/grad GEMMs vs the single-CTA kernel, and the fused dW + Jacobian
+    kernel (E_hat multicast over clusters of 4 / 2 / 1) vs GEMM + normalize_bwd: same math, so the
+    results agree to fp32 accumulation-order noise."""
+    base = _step_outputs(P, B, C, D, kind, {"LAFS_HEAD_1SM": "1", "LAFS_DW_UNFUSED": "1"})
+    for env in ({"LAFS_HEAD_1SM": "0", "LAFS_DW_UNFUSED": "1"},
+                {"LAFS_HEAD_1SM": "1", "LAFS_DW_UNFUSED": "0", "LAFS_DW_CLUSTER": "1"},
+                {"LAFS_HEAD_1SM": "1", "LAFS_DW_UNFUSED": "0", "LAFS_DW_CLUSTER": "2"},
+                {"LAFS_HEAD_1SM": "0", "LAFS_DW_UNFUSED": "0", "LAFS_DW_CLUSTER": "4"}):
+        out = _step_outputs(P, B, C, D, kind, env)
+        assert abs(out[0] - base[0]) <= 1e-5 * abs(base[0]), (env, out[0], base[0])
+        assert (out[3] - base[3]).abs().max() <= 1e-4, (env, float((out[3] - base[3]).abs().max()))
+        for a, b in ((out[1], base[1]), (out[2], base[2])):
+            assert (a - b).abs().max() <= 2e-3 * b.abs().max() + 1e-9, (env, float((a - b).abs().max() / b.abs().max()))

@@ -81,3 +81,32 @@ def test_module_wrappers_keep_state_dict_keys(ref):
         assert set(rs) == set(ms), (sorted(set(rs) ^ set(ms))[:10])
         assert all(rs[k].shape == ms[k].shape for k in rs)
         m.load_state_dict(rs, strict=True)
+
+
+def test_landmark_trunk_matches_reference(ref):
+    """The restated MobileNetV3-large trunk (landmark_trunk.py, outside the hot path) has the
+    reference's checkpoint keys and computes the same function from the same weights."""
+    import contextlib
+    import io
+    from face_pre_pro.mobilenet import MobileNetV3_backbone
+    from lafs_cvpr2024_b200.landmark_trunk import MobileNetV3LargeTrunk
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        r = MobileNetV3_backbone(mode="large")
+    m = MobileNetV3LargeTrunk()
+    rs, ms = r.state_dict(), m.state_dict()
+    assert list(rs) == list(ms)
+    assert all(rs[k].shape == ms[k].shape for k in rs)
+    m.load_state_dict(rs, strict=True)
+    x = torch.randn(2, 3, 112, 112)
+    for mode in ("eval", "train"):
+        getattr(r, mode)(); getattr(m, mode)()
+        torch.manual_seed(1); a = r(x)
+        torch.manual_seed(1); b = m(x)
+        assert a.shape == (2, 160, 4, 4)
+        assert torch.equal(a, b)
+    # same initialisation statistics (mobilenet.py:315-328): conv std = sqrt(2 / fan_out), BN (1, 0)
+    m2 = MobileNetV3LargeTrunk()
+    w = m2.features[0][0].weight
+    assert abs(float(w.std()) - (2.0 / (16 * 9)) ** 0.5) < 0.03
+    assert float(m2.features[1].conv[1].weight.min()) == 1.0 and float(m2.features[1].conv[1].bias.abs().max()) == 0.0
