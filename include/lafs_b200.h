@@ -225,6 +225,17 @@ LAFS_API int lafs_gather_embed_fwd(const void* imgs, int in_dtype, float in_scal
                                    const void* w_perm_bf16, const float* bias, void* out0, void* out1, int out_dtype,
                                    int Bv, int H, int W, int n, int dim, int n_models, lafs_stream_t stream);
 
+/* Backward of patch_to_embedding (the training path of the fused kernel; the reference gets it from
+ * autograd through nn.Linear, ViT_face.py:760-761 / lafs_train.py:544): two tcgen05 GEMMs over the
+ * M = faces*landmarks token rows.  grad_emb [M,dim], tokens [M,192] ('(p1 p2 c)' order), weight
+ * [dim,192] are bf16; grad_w [dim,192] and grad_tokens [M,192] are fp32 (grad_tokens feeds
+ * lafs_gather_bwd with LAFS_LAYOUT_TOKENS).  dim % 8 == 0. */
+LAFS_API size_t lafs_embed_bwd_workspace_bytes(int M, int dim);
+LAFS_API int lafs_embed_bwd_weight(const void* grad_emb_bf16, const void* tokens_bf16, int M, int dim, float* grad_w,
+                                   void* workspace, size_t workspace_bytes, lafs_stream_t stream);
+LAFS_API int lafs_embed_bwd_tokens(const void* grad_emb_bf16, const void* weight_bf16, int M, int dim,
+                                   float* grad_tokens, lafs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

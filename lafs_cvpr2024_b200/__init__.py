@@ -12,9 +12,9 @@ from .dino_loss import DINOLoss  # noqa: F401
 from .ema import EmaPlan, ema_update_  # noqa: F401
 from .margin_head import ArcFace, CosFace, label_to_shard, shard_bounds  # noqa: F401
 from .patches import (PatchEmbedWeights, extract_patches_pytorch_gridsample, extract_tokens,  # noqa: F401
-                      gather_embed, landmark_post)
+                      gather_embed, gather_embed_train, landmark_post)
 
 from .vit_face import ViT_face_landmark_patch8, face_landmark_4simmin_glo_loc  # noqa: F401,E402
 
 __all__ = ["ViT_face_landmark_patch8", "face_landmark_4simmin_glo_loc", "ArcFace", "CosFace", "label_to_shard", "shard_bounds", "DINOLoss", "EmaPlan", "ema_update_", "extract_patches_pytorch_gridsample", "extract_tokens",
-           "landmark_post", "gather_embed", "PatchEmbedWeights"]
+           "landmark_post", "gather_embed", "gather_embed_train", "PatchEmbedWeights"]

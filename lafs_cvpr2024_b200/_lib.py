@@ -49,6 +49,9 @@ SIGNATURES = {
     "lafs_head_bwd_embed": (_i, [_p, C.c_longlong, _p, _i, _i, _i, _p, _p, _z, _p]),
     "lafs_head_bwd_weight": (_i, [_p, C.c_longlong, _p, _p, _p, _i, _i, _i, _p, _p]),
     "lafs_normalize_bwd": (_i, [_p, _p, _p, _i, _i, _p, _p]),
+    "lafs_embed_bwd_workspace_bytes": (_z, [_i, _i]),
+    "lafs_embed_bwd_weight": (_i, [_p, _p, _i, _i, _p, _p, _z, _p]),
+    "lafs_embed_bwd_tokens": (_i, [_p, _p, _i, _i, _p, _p]),
 }
 
 _lib = None

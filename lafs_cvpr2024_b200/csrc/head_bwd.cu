@@ -745,3 +745,73 @@ extern "C" int lafs_normalize_bwd(const float* g, const void* x_hat_bf16, const 
   normalize_bwd_kernel<<<(R + 7) / 8, 256, 0, (cudaStream_t)stream>>>(g, (const __nv_bfloat16*)x_hat_bf16, inv_norm, R, D, out);
   return check_launch("lafs_normalize_bwd");
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Backward of patch_to_embedding = nn.Linear(192, dim) (ViT_face.py:760-761, lafs_train.py:544) on the
+ * same generic tcgen05 GEMM: the training path of the fused gather -> embed kernel.
+ *   grad_w [dim,192]  = grad_emb^T [dim, M] . tokens [M, 192]    (both operands MN-major, split-K over M)
+ *   grad_tok [M,192]  = grad_emb [M, dim] . W [dim, 192]         (K-major A, MN-major B)
+ * M = faces * landmarks token rows; operands bf16, accumulation and outputs fp32. */
+static int embed_bwd_splits(int M, int dim) {
+  const int tiles = (dim + 127) / 128;
+  const int kblocks = (M + 63) / 64;
+  int s = kNumSMs / tiles;
+  if (s < 1) s = 1;
+  if (s > kblocks) s = kblocks;
+  return s;
+}
+
+extern "C" size_t lafs_embed_bwd_workspace_bytes(int M, int dim) {
+  if (M <= 0 || dim <= 0) return 0;
+  return (size_t)embed_bwd_splits(M, dim) * dim * 192 * sizeof(float);
+}
+
+extern "C" int lafs_embed_bwd_weight(const void* grad_emb_bf16, const void* tokens_bf16, int M, int dim, float* grad_w,
+                                     void* workspace, size_t workspace_bytes, lafs_stream_t stream) {
+  if (int brc = lafs::bind_device_of(grad_emb_bf16)) return brc;
+  LAFS_REQUIRE(grad_emb_bf16 && tokens_bf16 && grad_w && workspace, LAFS_ERR_ARG, "lafs_embed_bwd_weight: null pointer");
+  LAFS_REQUIRE(M > 0 && dim > 0 && dim % 8 == 0, LAFS_ERR_ARG, "lafs_embed_bwd_weight: M=%d dim=%d (dim must be a multiple of 8)", M, dim);
+  LAFS_REQUIRE((((uintptr_t)grad_emb_bf16 | (uintptr_t)tokens_bf16 | (uintptr_t)grad_w | (uintptr_t)workspace) & 15u) == 0,
+               LAFS_ERR_ARG, "lafs_embed_bwd_weight: pointers must be 16-byte aligned");
+  const int splits = embed_bwd_splits(M, dim);
+  const size_t need = (size_t)splits * dim * 192 * sizeof(float);
+  LAFS_REQUIRE(workspace_bytes >= need, LAFS_ERR_WORKSPACE, "lafs_embed_bwd_weight: workspace %zu < %zu", workspace_bytes, need);
+  CUtensorMap ta, tb;
+  int rc = encode_bf16_2d(&ta, grad_emb_bf16, (uint64_t)M, (uint64_t)dim, (uint64_t)dim * 2, 64, 64);   // MN-major A: [K=M, dim]
+  if (rc) return rc;
+  rc = encode_bf16_2d(&tb, tokens_bf16, (uint64_t)M, 192, 192 * 2, 64, 64);                             // MN-major B: [K=M, 192]
+  if (rc) return rc;
+  GemmParams p{};
+  p.M = dim; p.N = 192; p.K = M;
+  p.m_tiles = (dim + 127) / 128; p.n_tiles = 1;
+  p.kblocks_total = (M + 63) / 64;
+  p.kblocks_per_split = (p.kblocks_total + splits - 1) / splits;
+  p.splits = (p.kblocks_total + p.kblocks_per_split - 1) / p.kblocks_per_split;
+  p.out = (float*)workspace; p.ldo = 192; p.split_stride = (long long)dim * 192;
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = launch_gemm<true>(ta, tb, p, st);
+  if (rc) return rc;
+  const long long n = (long long)dim * 192;
+  split_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const float*)workspace, p.splits, n, n, grad_w);
+  return check_launch("lafs_embed_bwd_weight");
+}
+
+extern "C" int lafs_embed_bwd_tokens(const void* grad_emb_bf16, const void* weight_bf16, int M, int dim, float* grad_tokens,
+                                     lafs_stream_t stream) {
+  if (int brc = lafs::bind_device_of(grad_emb_bf16)) return brc;
+  LAFS_REQUIRE(grad_emb_bf16 && weight_bf16 && grad_tokens, LAFS_ERR_ARG, "lafs_embed_bwd_tokens: null pointer");
+  LAFS_REQUIRE(M > 0 && dim > 0 && dim % 8 == 0, LAFS_ERR_ARG, "lafs_embed_bwd_tokens: M=%d dim=%d (dim must be a multiple of 8)", M, dim);
+  LAFS_REQUIRE((((uintptr_t)grad_emb_bf16 | (uintptr_t)weight_bf16 | (uintptr_t)grad_tokens) & 15u) == 0, LAFS_ERR_ARG,
+               "lafs_embed_bwd_tokens: pointers must be 16-byte aligned");
+  CUtensorMap ta, tb;
+  int rc = encode_bf16_2d(&ta, grad_emb_bf16, (uint64_t)M, (uint64_t)dim, (uint64_t)dim * 2, 64, 128);  // K-major A: [M, K=dim]
+  if (rc) return rc;
+  rc = encode_bf16_2d(&tb, weight_bf16, (uint64_t)dim, 192, 192 * 2, 64, 64);                           // MN-major B: [K=dim, 192]
+  if (rc) return rc;
+  GemmParams p{};
+  p.M = M; p.N = 192; p.K = dim;
+  p.m_tiles = (M + 127) / 128; p.n_tiles = 1; p.splits = 1;
+  p.kblocks_total = (dim + 63) / 64; p.kblocks_per_split = p.kblocks_total;
+  p.out = grad_tokens; p.ldo = 192; p.split_stride = 0;
+  return launch_gemm<false>(ta, tb, p, (cudaStream_t)stream);
+}

@@ -173,3 +173,68 @@ def gather_embed(imgs, landmarks, weights: PatchEmbedWeights, out_dtype=torch.bf
               outs[1].data_ptr() if m > 1 else None, _lib.dtype_code(outs[0]), Bv, H, W, n, weights.dim, m,
               _lib.stream())
     return outs
+
+
+class _GatherEmbedTrainFn(torch.autograd.Function):
+    """Differentiable gather -> patch_to_embedding for the finetune path (the landmark CNN and the
+    embedding are trained, ViT_face.py:706,760-761).  Forward: the fused tcgen05 kernel (no token
+    tensor in HBM).  Backward: the tokens are re-gathered, then
+        grad_weight = grad_emb^T . tokens,  grad_bias = column sums of grad_emb,
+        grad_tokens = grad_emb . W  ->  lafs_gather_bwd  ->  grad_landmarks (, grad_imgs)
+    on the same tcgen05 GEMM the margin head's backward uses (bf16 operands, fp32 accumulation)."""
+
+    @staticmethod
+    def forward(ctx, imgs, theta, weight, bias):
+        w = PatchEmbedWeights([(weight, bias)])
+        (emb,) = gather_embed(imgs, theta, w, out_dtype=torch.bfloat16)
+        ctx.save_for_backward(imgs, theta, weight)
+        ctx.has_bias = bias is not None
+        return emb
+
+    @staticmethod
+    def backward(ctx, grad_emb):
+        imgs, theta, weight = ctx.saved_tensors
+        need_img, need_th, need_w, need_b = ctx.needs_input_grad
+        x = imgs.detach().float().contiguous()
+        th = theta.detach().float().contiguous()
+        Bv, Cc, H, W = x.shape
+        n = th.shape[1]
+        dim = weight.shape[0]
+        M = Bv * n
+        g = grad_emb.detach().to(torch.bfloat16).contiguous().view(M, dim)
+        dev = g.device
+        gw = gb = gi = gt = None
+        if need_w:
+            tok = torch.empty(Bv, n, 64 * Cc, dtype=torch.float32, device=dev)
+            _lib.call("lafs_gather_fwd", x.data_ptr(), th.data_ptr(), tok.data_ptr(), Bv, Cc, H, W, n,
+                      _lib.LAYOUT_TOKENS, COORD_MODE, _lib.stream())
+            tok16 = tok.view(M, 64 * Cc).to(torch.bfloat16)
+            nbytes = _lib.lib().lafs_embed_bwd_workspace_bytes(M, dim)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            gw = torch.empty(dim, 64 * Cc, dtype=torch.float32, device=dev)
+            _lib.call("lafs_embed_bwd_weight", g.data_ptr(), tok16.data_ptr(), M, dim, gw.data_ptr(), ws.data_ptr(),
+                      nbytes, _lib.stream())
+            gw = gw.to(weight.dtype)
+        if need_b and ctx.has_bias:
+            gb = torch.empty(dim, dtype=torch.float32, device=dev)
+            nb = 32 * dim * 4
+            wsb = torch.empty(nb, dtype=torch.uint8, device=dev)
+            _lib.call("lafs_colsum", g.data_ptr(), M, dim, _lib.BF16, gb.data_ptr(), wsb.data_ptr(), nb, _lib.stream())
+        if need_img or need_th:
+            w16 = weight.detach().to(torch.bfloat16).contiguous()
+            gtok = torch.empty(M, 64 * Cc, dtype=torch.float32, device=dev)
+            _lib.call("lafs_embed_bwd_tokens", g.data_ptr(), w16.data_ptr(), M, dim, gtok.data_ptr(), _lib.stream())
+            gi = torch.zeros_like(x) if need_img else None
+            gt = torch.empty_like(th) if need_th else None
+            _lib.call("lafs_gather_bwd", x.data_ptr(), th.data_ptr(), gtok.data_ptr(), _lib.ptr(gi), _lib.ptr(gt),
+                      Bv, Cc, H, W, n, _lib.LAYOUT_TOKENS, COORD_MODE, _lib.stream())
+        return gi, gt, gw, gb
+
+
+def gather_embed_train(imgs, landmarks, weight, bias=None):
+    """tokens(imgs, landmarks) @ weight^T + bias -> [B, n, dim] bf16, differentiable w.r.t. landmarks,
+    imgs, weight and bias (fp32 [B,3,112,112] images; weight [dim,192], dim % 128 == 0, n <= 208)."""
+    _lib.require_cuda(imgs, landmarks, weight, bias)
+    if imgs.dim() != 4 or imgs.shape[1] != 3 or imgs.dtype == torch.uint8:
+        raise ValueError("gather_embed_train expects fp32 [B,3,H,W] images")
+    return _GatherEmbedTrainFn.apply(imgs, landmarks, weight, bias)

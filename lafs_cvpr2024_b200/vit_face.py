@@ -25,7 +25,7 @@ import torch.nn.functional as F
 
 from . import _lib
 from .margin_head import ArcFace, CosFace
-from .patches import PatchEmbedWeights, extract_tokens, gather_embed, landmark_post
+from .patches import PatchEmbedWeights, extract_tokens, gather_embed, gather_embed_train, landmark_post
 
 MIN_NUM_PATCHES = 15  # ViT_face.py:21
 
@@ -120,11 +120,18 @@ class Transformer(nn.Module):
 
 
 def _tokens_and_embedding(imgs, theta, linear, training_path):
-    """patch tokens -> patch_to_embedding.  With gradients: differentiable fp32 gather kernel +
-    the nn.Linear; without: the fused tcgen05 gather->embed kernel (no token tensor in HBM)."""
+    """patch tokens -> patch_to_embedding on the fused tcgen05 gather->embed kernel (no token tensor in
+    HBM).  With gradients its backward runs on the tcgen05 GEMMs of patches.gather_embed_train; shapes
+    the fused kernel does not cover (dim % 128 != 0, more than 208 landmarks) take the differentiable
+    fp32 gather kernel + nn.Linear."""
+    fused_ok = linear.weight.shape[0] % 128 == 0 and theta.shape[1] <= 208 and imgs.shape[1] == 3
     if training_path:
+        if fused_ok:
+            return gather_embed_train(imgs, theta, linear.weight, linear.bias).to(linear.weight.dtype)
         tok = extract_tokens(imgs, theta)
         return linear(tok.to(linear.weight.dtype))
+    if not fused_ok:
+        return linear(extract_tokens(imgs, theta).to(linear.weight.dtype))
     w = PatchEmbedWeights([(linear.weight, linear.bias)])
     (emb,) = gather_embed(imgs, theta, w, out_dtype=torch.bfloat16)
     return emb.to(linear.weight.dtype)

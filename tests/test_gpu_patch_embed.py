@@ -93,3 +93,33 @@ def test_uint8_images_normalised_in_kernel(P, n):
     # same numbers as the fp32-input kernel up to bf16 token rounding flips
     o_f, _ = P.gather_embed(imgs_f.cuda(), th.cuda(), wts, out_dtype=torch.float32)
     assert (o_f - o_s).abs().max() <= 1e-3 * o_f.abs().max()
+
+
+@pytest.mark.parametrize("B,n,dim", [(6, 196, 768), (9, 36, 256), (150, 196, 128)])
+def test_gather_embed_train_backward_vs_autograd(P, B, n, dim):
+    """Training path of a3: fused forward + tcgen05 backward GEMMs against fp32 autograd through the
+    oracle's differentiable gather + F.linear (bf16 operands: max-norm-relative tolerances)."""
+    torch.manual_seed(B + n + dim)
+    imgs = torch.rand(B, 3, 112, 112) * 2 - 1
+    th = torch.rand(B, n, 2) * 100 + 5
+    lin = torch.nn.Linear(192, dim)
+    gout = torch.randn(B, n, dim)
+    # reference: oracle gather (autograd through grid_sample) + fp32 linear
+    th_r = th.clone().requires_grad_(True)
+    w_r = lin.weight.detach().clone().requires_grad_(True)
+    b_r = lin.bias.detach().clone().requires_grad_(True)
+    tok = O.extract_tokens(imgs, th_r)
+    ref = torch.nn.functional.linear(tok, w_r, b_r)
+    (ref * gout).sum().backward()
+    th_g = th.cuda().requires_grad_(True)
+    w_g = lin.weight.detach().cuda().requires_grad_(True)
+    b_g = lin.bias.detach().cuda().requires_grad_(True)
+    out = P.gather_embed_train(imgs.cuda(), th_g, w_g, b_g)
+    assert out.dtype == torch.bfloat16 and out.shape == (B, n, dim)
+    assert (out.float().cpu() - ref.detach()).abs().max() <= (1e-3 + 2 ** -7) * ref.abs().max()
+    (out.float() * gout.cuda()).sum().backward()
+    for got, want, name in ((w_g.grad, w_r.grad, "weight"), (b_g.grad, b_r.grad, "bias"), (th_g.grad, th_r.grad, "theta")):
+        err = (got.cpu() - want).abs().max() / want.abs().max()
+        assert err <= 2e-2, (name, float(err))
+        cs = torch.nn.functional.cosine_similarity(got.cpu().flatten(), want.flatten(), dim=0)
+        assert cs > 0.999, (name, float(cs))

@@ -115,3 +115,27 @@ def test_landmark_cnn_wrapper_ssl_calls(P):
         th_ref = O.landmark_post(raw, noise, idx)
         assert mos.shape == (3, 3, 48, 48)
         assert torch.equal(th.cpu(), th_ref) and torch.equal(mos.cpu(), O.extract_patches(xa, th_ref, 36))
+
+
+def test_default_landmark_trunk_runs_self_contained():
+    """No reference checkout, no injected stn: the package's own MobileNetV3-large trunk
+    (landmark_trunk.py, reference checkpoint keys) feeds the landmark tail and the gather kernels."""
+    import lafs_cvpr2024_b200 as P
+    torch.manual_seed(0)
+    g = P.face_landmark_4simmin_glo_loc(loss_type="None", GPU_ID=None, num_class=0, image_size=112, patch_size=8,
+                                        dim=64, depth=1, heads=2, mlp_dim=64).cuda().eval()
+    assert any(k.startswith("stn.features.15.conv.8.") for k in g.state_dict())
+    x = torch.rand(4, 3, 112, 112, device="cuda") * 2 - 1
+    with torch.no_grad():
+        theta, patches = g(x, Random_prob=True, return_prob=True)
+    assert theta.shape == (4, 196, 2) and patches.shape == (4, 3, 112, 112)
+    assert torch.isfinite(theta).all() and torch.isfinite(patches).all()
+    m = P.ViT_face_landmark_patch8(loss_type="CosFace", GPU_ID=None, num_class=100, image_size=112, patch_size=8,
+                                   dim=128, depth=1, heads=2, mlp_dim=128, num_patches=196, with_land=True).cuda().train()
+    lab = torch.randint(0, 100, (4,), device="cuda")
+    loss = m.forward_loss(x, lab)                      # fused gather->embed forward, tcgen05 backward GEMMs
+    loss.backward()
+    assert torch.isfinite(loss)
+    for name in ("patch_to_embedding.weight", "output_layer.1.weight", "stn.features.0.0.weight", "loss.weight"):
+        gr = dict(m.named_parameters())[name].grad
+        assert gr is not None and torch.isfinite(gr).all() and float(gr.abs().max()) > 0, name
