@@ -124,9 +124,17 @@ head_gemm_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
       }
       int stage = 0;
       uint32_t phase = 0;
+      // W is read once from HBM (plus L2 hits by the other M tiles): the ring alone (<= 96 KB per SM)
+      // cannot cover HBM latency at the UMMA consumption rate (ncu: the epilogue warps wait on acc_full
+      // for 25 % of the samples), so the producer also pulls the chunk after next into L2
+      const int pf_ahead = 2 * p.nranges;
+      const bool pf_owner = PAIR ? blockIdx.x < 2 : blockIdx.x == 0;   // one prefetch per W tile, not one per M tile
       for (int chunk = range; chunk < p.nchunks; chunk += p.nranges) {
         const int wrow = chunk * BN + (int)rank * kStageRows;
+        const int pf_row = wrow + pf_ahead * BN;
+        const bool pf = pf_owner && chunk + pf_ahead < p.nchunks;
         for (int k = 0; k < p.kch; ++k) {
+          if (pf) tma_prefetch_l2_2d(&tmap_w, k * 64, pf_row);
           mbar_wait(b_empty + stage, phase ^ 1);     // every consumer of this slot (both CTAs' data) is done
           if (leader) mbar_arrive_expect_tx(b_full + stage, (uint32_t)kStageBytes * (PAIR ? 2u : 1u));
           uint8_t* dst = smem_b + (size_t)stage * kStageBytes;

@@ -24,6 +24,7 @@ constexpr int kBM = 128, kBN = 256, kBK = 64;
 constexpr int kStageA = kBM * kBK * 2;      // 16 KB
 constexpr int kStageB = kBN * kBK * 2;      // 32 KB
 constexpr int kStages = 4;
+constexpr int kPrefetch = 8;                             // k blocks of L2 prefetch distance
 constexpr int kThreads = 192;
 constexpr int kPitch = 36;                              // floats per staged row (144 B: 16-byte aligned, conflict-free)
 constexpr int kStageOut = 4 * 32 * kPitch * 4;          // per epilogue warp a [32 x 32] fp32 block: 18,432 B total
@@ -103,6 +104,19 @@ gemm_bwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         const int kb1 = min(kb0 + p.kblocks_per_split, p.kblocks_total);
         for (int kb = kb0; kb < kb1; ++kb, ++cnt) {
           const int st = cnt % kStages;
+          // pull the operands of k block kb + kPrefetch into L2 (once per operand tile: A by the N tile 0
+          // CTAs, B by the M tile 0 CTAs): the 4-stage ring alone does not cover HBM latency
+          if (kb + kPrefetch < kb1) {
+            const int kp = (kb + kPrefetch) * kBK;
+            if (nt == 0) {
+              if (A_MN) { tma_prefetch_l2_2d(&tmap_a, mt * kBM, kp); tma_prefetch_l2_2d(&tmap_a, mt * kBM + 64, kp); }
+              else tma_prefetch_l2_2d(&tmap_a, kp, mt * kBM);
+            }
+            if (mt == 0) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) tma_prefetch_l2_2d(&tmap_b, nt * kBN + q * 64, kp);
+            }
+          }
           mbar_wait(empty + st, ((cnt / kStages) & 1) ^ 1);   // all CL consumers of this slot are done
           mbar_arrive_expect_tx(full + st, kStageA + kStageB);
           uint8_t* da = s_a + st * kStageA;
@@ -216,17 +230,22 @@ gemm_bwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 }
 
 // ---- dW with the F.normalize Jacobian fused into the epilogue ---------------------------------------
-// One CTA owns 128 classes x ALL D columns (D <= 512 = the whole TMEM), so after the K = batch loop a
-// TMEM lane holds a complete row of dW_hat and the Jacobian
+// One CTA owns 128 classes x ALL D columns (D <= 512 = the whole TMEM), so complete rows of dW_hat
+// leave one CTA and the Jacobian
 //     grad_w[c,:] = (dW_hat[c,:] - w_hat[c,:] * <w_hat[c,:], dW_hat[c,:]>) * inv_norm_w[c]
-// is applied on the way out: grad_w is written exactly once (C*D*4 bytes) instead of the
-// write + read + read(w_hat) + write of a GEMM followed by normalize_bwd_kernel.
+// is applied by the same CTA while the rows are still in L2: phase A drains TMEM into grad_w
+// (256 KB per tile), phase B re-reads those lines from L2 one warp per row (coalesced, like
+// normalize_bwd_kernel) and overwrites them in place, while the tensor core already works on the
+// next tile.  HBM sees grad_w once (C*D*4 bytes) instead of the write + read + write of a GEMM
+// followed by normalize_bwd_kernel.  (Applying the Jacobian straight from TMEM -- a lane owns a
+// row there -- needs w_hat with one 16-byte piece per row per load, which is latency bound:
+// measured 139 us against 67 + 77 us for the two-kernel form at B=512, C=93431, D=512.)
 // Every class tile contracts against the SAME E_hat [B, D]; with K = B = 512 a tile moves 128 KB of
 // G and 512 KB of E_hat for 67 MFLOP, i.e. the L2 -> SM fill bounds the kernel.  CL CTAs of a
 // cluster therefore work on CL neighbouring class tiles in lock step and each fetches 1/CL of every
 // E_hat k block, multicast to the whole cluster (E_hat fill traffic / CL).
-// Warps: 0 TMA, 1 UMMA, 2..9 epilogue (two per TMEM lane quarter, half of the columns each; the row
-// dot product is combined through shared memory).
+// Warps: 0 TMA, 1 UMMA, 2..9 epilogue (phase A: two per TMEM lane quarter, half of the columns each;
+// phase B: 16 rows of the tile each).
 namespace dwf {
 constexpr int kBM = 128, kBK = 64;
 constexpr int kThreads = 320;
@@ -289,8 +308,13 @@ dw_fused_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constan
       uint32_t cnt = 0;
       LAFS_DW_TILES {
         const int tile = sup * CL + rank;
+        const int next_tile = (sup + nclusters) * CL + rank;   // its G columns come from HBM: pull them into L2 now
         for (int kb = 0; kb < p.kblocks; ++kb, ++cnt) {
           const int st = cnt % p.stages;
+          if (next_tile < p.m_tiles) {
+            tma_prefetch_l2_2d(&tmap_g, next_tile * kBM, kb * kBK);
+            tma_prefetch_l2_2d(&tmap_g, next_tile * kBM + 64, kb * kBK);
+          }
           mbar_wait(empty + st, ((cnt / p.stages) & 1) ^ 1);
           mbar_arrive_expect_tx(full + st, (uint32_t)stage_bytes);
           uint8_t* da = smem + (size_t)st * stage_bytes;
@@ -336,91 +360,108 @@ dw_fused_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constan
   } else {
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
-    const int ncol = p.D / 2;                   // columns of this warp: [half*ncol, (half+1)*ncol), a multiple of 32
+    const int ew = warp - 2;                    // 0..7
+    const int ncol = p.D / 2;                   // phase A columns of this warp: [half*ncol, (half+1)*ncol)
     const int col_lo = half * ncol;
-    float* stage = s_out + (warp - 2) * (32 * kPitch);
+    float* stage = s_out + ew * (32 * kPitch);
     uint32_t tcnt = 0;
     LAFS_DW_TILES {
       const int tile = sup * CL + rank;
       const int row_base = tile * kBM + quarter * 32;
-      const int grow = row_base + lane;           // the class this lane's TMEM row belongs to
-      const bool ok = grow < p.C;
-      const __nv_bfloat16* wrow = p.w_hat + (size_t)(ok ? grow : 0) * p.D + col_lo;
-      // This lane's half row of w_hat (<= 256 bf16 = 32 x 16 B) is fetched into registers BEFORE the
-      // accumulator is waited for: the loads (one 16-byte piece per row per instruction, i.e. latency
-      // bound) overlap the tile's MMA phase, and both epilogue passes then run from registers + TMEM.
-      uint4 w[kMaxPieces * 4];
-#pragma unroll
-      for (int i = 0; i < kMaxPieces; ++i) {
-        if (i * 32 < ncol) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) w[i * 4 + q] = ld_stream_u4(wrow + i * 32 + q * 8);
-        }
-      }
-      const float inv = ok ? __ldg(p.inv_norm + grow) : 0.f;
       mbar_wait(acc_full, tcnt & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col_lo;
-      // ---- pass 1: <w_hat[c,:], dW_hat[c,:]> ------------------------------------------------------
-      float dot = 0.f;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      // ---- phase A: TMEM -> dW_hat rows in grad_w (transposed through shared memory so that a warp
+      // writes full 128-byte row segments); the lines stay in L2 for phase B ------------------------------
+#pragma unroll 1
+      for (int c0 = col_lo; c0 < col_lo + ncol; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + (uint32_t)c0, v);
+        tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < kMaxPieces; ++i) {
-        if (i * 32 < ncol) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(taddr + (uint32_t)(i * 32), v);
-          tmem_ld_wait();
-          float d0 = 0.f, d1 = 0.f;
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(stage + lane * kPitch + j) =
+              make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                          __uint_as_float(v[j + 3]));
+        __syncwarp();
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t ww[4] = {w[i * 4 + q].x, w[i * 4 + q].y, w[i * 4 + q].z, w[i * 4 + q].w};
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-              d0 = fmaf(__uint_as_float(v[q * 8 + 2 * h]), Half2Ops<__nv_bfloat16>::lo(ww[h]), d0);
-              d1 = fmaf(__uint_as_float(v[q * 8 + 2 * h + 1]), Half2Ops<__nv_bfloat16>::hi(ww[h]), d1);
-            }
-          }
-          dot += d0 + d1;
+        for (int r8 = 0; r8 < 8; ++r8) {
+          const int rr = r8 * 4 + (lane >> 3), part = lane & 7;       // 8 lanes cover one 128-byte row segment
+          const float4 val = *reinterpret_cast<const float4*>(stage + rr * kPitch + part * 4);
+          if (row_base + rr < p.C)
+            *reinterpret_cast<float4*>(p.out + (size_t)(row_base + rr) * p.D + c0 + part * 4) = val;
         }
+        __syncwarp();
       }
-      s_dot[half * 128 + quarter * 32 + lane] = dot;
-      asm volatile("bar.sync 1, 256;" ::: "memory");       // the 8 epilogue warps
-      dot = s_dot[quarter * 32 + lane] + s_dot[128 + quarter * 32 + lane];
-      const float ndot = -dot * inv;
-      // ---- pass 2: Jacobian, transposed through shared memory into full 128-byte row segments -------
-#pragma unroll
-      for (int i = 0; i < kMaxPieces; ++i) {
-        if (i * 32 < ncol) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(taddr + (uint32_t)(i * 32), v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t ww[4] = {w[i * 4 + q].x, w[i * 4 + q].y, w[i * 4 + q].z, w[i * 4 + q].w};
-            float o[8];
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {   // (v - w*dot)*inv
-              o[2 * h] = fmaf(Half2Ops<__nv_bfloat16>::lo(ww[h]), ndot, __uint_as_float(v[q * 8 + 2 * h]) * inv);
-              o[2 * h + 1] = fmaf(Half2Ops<__nv_bfloat16>::hi(ww[h]), ndot, __uint_as_float(v[q * 8 + 2 * h + 1]) * inv);
-            }
-            *reinterpret_cast<float4*>(stage + lane * kPitch + q * 8) = make_float4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<float4*>(stage + lane * kPitch + q * 8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
-          }
-          __syncwarp();
-          const int c0 = col_lo + i * 32;
-#pragma unroll
-          for (int r8 = 0; r8 < 8; ++r8) {
-            const int rr = r8 * 4 + (lane >> 3), part = lane & 7;       // 8 lanes cover one 128-byte row segment
-            const float4 val = *reinterpret_cast<const float4*>(stage + rr * kPitch + part * 4);
-            if (row_base + rr < p.C)
-              st_stream_f4(p.out + (size_t)(row_base + rr) * p.D + c0 + part * 4, val);
-          }
-          __syncwarp();
-        }
-      }
+      // the accumulator is drained: the UMMAs of the next tile run under phase B
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty);
-      asm volatile("bar.sync 1, 256;" ::: "memory");       // s_dot is rewritten by the next tile
+      __threadfence_block();
+      asm volatile("bar.sync 1, 256;" ::: "memory");       // every row of the tile is written (8 epilogue warps)
+      // ---- phase B: F.normalize Jacobian in place, one warp per row (16 rows per warp), the row and
+      // its w_hat row read back coalesced from L2; kRowsInFlight rows in flight per warp (the phase is a
+      // chain of L2 round trips: 2 rows in flight measured 20 % of all stall samples on the first use) --------
+      constexpr int kRowsInFlight = 4;
+      const int tile_row0 = tile * kBM;
+#pragma unroll 1
+      for (int rp = 0; rp < 16; rp += kRowsInFlight) {
+        float4 gv[kRowsInFlight][2][2];
+        uint4 xv[kRowsInFlight][2];
+        int rows[kRowsInFlight];
+#pragma unroll
+        for (int u = 0; u < kRowsInFlight; ++u) {
+          rows[u] = tile_row0 + ew * 16 + rp + u;
+          if (rows[u] < p.C) {
+            const float* grow = p.out + (size_t)rows[u] * p.D;
+            const __nv_bfloat16* xrow = p.w_hat + (size_t)rows[u] * p.D;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const int c = q * 256 + lane * 8;
+              if (c < p.D) {
+                gv[u][q][0] = __ldcg(reinterpret_cast<const float4*>(grow + c));
+                gv[u][q][1] = __ldcg(reinterpret_cast<const float4*>(grow + c + 4));
+                xv[u][q] = ld_stream_u4(xrow + c);
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kRowsInFlight; ++u) {
+          if (rows[u] < p.C) {                                        // warp-uniform
+            float xf[2][8];
+            float dot = 0.f;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const int c = q * 256 + lane * 8;
+              if (c < p.D) {
+                xf[q][0] = Half2Ops<__nv_bfloat16>::lo(xv[u][q].x); xf[q][1] = Half2Ops<__nv_bfloat16>::hi(xv[u][q].x);
+                xf[q][2] = Half2Ops<__nv_bfloat16>::lo(xv[u][q].y); xf[q][3] = Half2Ops<__nv_bfloat16>::hi(xv[u][q].y);
+                xf[q][4] = Half2Ops<__nv_bfloat16>::lo(xv[u][q].z); xf[q][5] = Half2Ops<__nv_bfloat16>::hi(xv[u][q].z);
+                xf[q][6] = Half2Ops<__nv_bfloat16>::lo(xv[u][q].w); xf[q][7] = Half2Ops<__nv_bfloat16>::hi(xv[u][q].w);
+                dot += gv[u][q][0].x * xf[q][0] + gv[u][q][0].y * xf[q][1] + gv[u][q][0].z * xf[q][2] + gv[u][q][0].w * xf[q][3] +
+                       gv[u][q][1].x * xf[q][4] + gv[u][q][1].y * xf[q][5] + gv[u][q][1].z * xf[q][6] + gv[u][q][1].w * xf[q][7];
+              }
+            }
+            dot = warp_sum(dot);
+            const float inv = __ldg(p.inv_norm + rows[u]);
+            float* orow = p.out + (size_t)rows[u] * p.D;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const int c = q * 256 + lane * 8;
+              if (c < p.D) {
+                float4 o0, o1;
+                o0.x = (gv[u][q][0].x - xf[q][0] * dot) * inv; o0.y = (gv[u][q][0].y - xf[q][1] * dot) * inv;
+                o0.z = (gv[u][q][0].z - xf[q][2] * dot) * inv; o0.w = (gv[u][q][0].w - xf[q][3] * dot) * inv;
+                o1.x = (gv[u][q][1].x - xf[q][4] * dot) * inv; o1.y = (gv[u][q][1].y - xf[q][5] * dot) * inv;
+                o1.z = (gv[u][q][1].z - xf[q][6] * dot) * inv; o1.w = (gv[u][q][1].w - xf[q][7] * dot) * inv;
+                st_stream_f4(orow + c, o0);
+                st_stream_f4(orow + c + 4, o1);
+              }
+            }
+          }
+        }
+      }
       ++tcnt;
     }
   }
@@ -477,10 +518,13 @@ static int launch_dw_fused(const CUtensorMap& ta, const CUtensorMap& tb, DwParam
 // D % 64 == 0, D <= 768: a lane holds up to three (float4 x 2) groups.  out may alias g.
 __global__ void __launch_bounds__(256)
 normalize_bwd_kernel(const float* __restrict__ g, const __nv_bfloat16* __restrict__ x_hat,
-                     const float* __restrict__ inv_norm, int R, int D, float* __restrict__ out) {
+                     const float* __restrict__ inv_norm, int R, int D, float* __restrict__ out, int reverse) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r = blockIdx.x * 8 + warp;
+  int r = blockIdx.x * 8 + warp;
   if (r >= R) return;
+  // reverse: start with the rows the producing GEMM wrote LAST -- they are still in L2 (126 MB), so
+  // the first ~100 MB of this pass do not touch HBM
+  if (reverse) r = R - 1 - r;
   const float* grow = g + (size_t)r * D;
   const __nv_bfloat16* xrow = x_hat + (size_t)r * D;
   float4 gv[3][2];
@@ -695,9 +739,13 @@ extern "C" int lafs_head_bwd_weight(const void* grad_bf16, long long ldg, const 
   rc = encode_bf16_2d(&tb, e_hat, (uint64_t)B, (uint64_t)D, (uint64_t)D * 2, 64, 64);                  // MN-major B: [K=B, N=D]
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  // The single-kernel form (dw_fused_kernel) is opt-in: measured on B200 at B=512, C=93431, D=512 it
+  // takes 157 us alone / 374 us per step against 144 us / 357 us for GEMM + reverse-order Jacobian pass
+  // (its in-place phase B is a chain of L2 round trips); at B=1024, C=205990 the two are equal.
+  const char* fused = getenv("LAFS_DW_FUSED");
   const char* unfused = getenv("LAFS_DW_UNFUSED");
-  if (D <= 512 && !(unfused && atoi(unfused) != 0)) {
-    // fused path: full rows in TMEM, Jacobian in the epilogue
+  if (D <= 512 && fused && atoi(fused) != 0 && !(unfused && atoi(unfused) != 0)) {
+    // fused path: full rows in TMEM, Jacobian applied from L2 by the same CTA
     DwParams q{};
     q.C = C_local; q.D = D; q.B = B;
     q.m_tiles = (C_local + 127) / 128;
@@ -710,7 +758,7 @@ extern "C" int lafs_head_bwd_weight(const void* grad_bf16, long long ldg, const 
     LAFS_REQUIRE(q.stages >= 2, LAFS_ERR_ARG, "lafs_head_bwd_weight: D=%d leaves no room for a 2-stage pipeline", D);
     q.w_hat = (const __nv_bfloat16*)w_hat; q.inv_norm = inv_norm_w; q.out = grad_w;
     const int smem = q.stages * stage_bytes + tail;
-    int cl = 4;                                        // E_hat multicast width (LAFS_DW_CLUSTER: 1, 2 or 4)
+    int cl = 1;                                        // E_hat multicast width (LAFS_DW_CLUSTER: 1, 2 or 4)
     if (const char* e = getenv("LAFS_DW_CLUSTER")) cl = atoi(e);
     const int nboxes = D / 64;
     bool launched = false;
@@ -731,7 +779,7 @@ extern "C" int lafs_head_bwd_weight(const void* grad_bf16, long long ldg, const 
   p.out = grad_w; p.ldo = D; p.split_stride = 0;
   rc = launch_gemm<true>(ta, tb, p, st);
   if (rc) return rc;
-  normalize_bwd_kernel<<<(C_local + 7) / 8, 256, 0, st>>>(grad_w, (const __nv_bfloat16*)w_hat, inv_norm_w, C_local, D, grad_w);
+  normalize_bwd_kernel<<<(C_local + 7) / 8, 256, 0, st>>>(grad_w, (const __nv_bfloat16*)w_hat, inv_norm_w, C_local, D, grad_w, 1);
   return check_launch("lafs_head_bwd_weight");
 }
 
@@ -742,7 +790,7 @@ extern "C" int lafs_normalize_bwd(const float* g, const void* x_hat_bf16, const 
   LAFS_REQUIRE(g && x_hat_bf16 && inv_norm && out && R >= 0 && D > 0 && D <= 768, LAFS_ERR_ARG, "lafs_normalize_bwd: bad argument");
   if (R == 0) return LAFS_OK;
   LAFS_REQUIRE(D % 8 == 0, LAFS_ERR_ARG, "lafs_normalize_bwd: D=%d must be a multiple of 8", D);
-  normalize_bwd_kernel<<<(R + 7) / 8, 256, 0, (cudaStream_t)stream>>>(g, (const __nv_bfloat16*)x_hat_bf16, inv_norm, R, D, out);
+  normalize_bwd_kernel<<<(R + 7) / 8, 256, 0, (cudaStream_t)stream>>>(g, (const __nv_bfloat16*)x_hat_bf16, inv_norm, R, D, out, 0);
   return check_launch("lafs_normalize_bwd");
 }
 

@@ -213,14 +213,15 @@ def _step_outputs(P, B, C, D, kind, env):
 @pytest.mark.parametrize("B,C,D", [(512, 9001, 512), (256, 4099, 256), (130, 3000, 128), (1024, 2500, 512)])
 @pytest.mark.parametrize("kind", ["cosface", "arcface"])
 def test_head_kernel_variants_agree(P, B, C, D, kind):
-    """CTA-pair (cta_group::2) forward/grad GEMMs vs the single-CTA kernel, and the fused dW + Jacobian
-    kernel (E_hat multicast over clusters of 4 / 2 / 1) vs GEMM + normalize_bwd: same math, so the
+    """CTA-pair (cta_group::2) forward/grad GEMMs vs the single-CTA kernel, and the opt-in fused dW + Jacobian
+    kernel (E_hat multicast over clusters of 4 / 2 / 1) vs GEMM + normalize_bwd, dE with / without W_hat multicast: same math, so the
     results agree to fp32 accumulation-order noise."""
     base = _step_outputs(P, B, C, D, kind, {"LAFS_HEAD_1SM": "1", "LAFS_DW_UNFUSED": "1"})
     for env in ({"LAFS_HEAD_1SM": "0", "LAFS_DW_UNFUSED": "1"},
-                {"LAFS_HEAD_1SM": "1", "LAFS_DW_UNFUSED": "0", "LAFS_DW_CLUSTER": "1"},
-                {"LAFS_HEAD_1SM": "1", "LAFS_DW_UNFUSED": "0", "LAFS_DW_CLUSTER": "2"},
-                {"LAFS_HEAD_1SM": "0", "LAFS_DW_UNFUSED": "0", "LAFS_DW_CLUSTER": "4"}):
+                {"LAFS_HEAD_1SM": "1", "LAFS_DW_FUSED": "1", "LAFS_DW_UNFUSED": "0", "LAFS_DW_CLUSTER": "1"},
+                {"LAFS_HEAD_1SM": "1", "LAFS_DW_FUSED": "1", "LAFS_DW_UNFUSED": "0", "LAFS_DW_CLUSTER": "2"},
+                {"LAFS_HEAD_1SM": "0", "LAFS_DW_FUSED": "1", "LAFS_DW_UNFUSED": "0", "LAFS_DW_CLUSTER": "4"},
+                {"LAFS_HEAD_1SM": "0", "LAFS_DE_CLUSTER": "1"}, {"LAFS_HEAD_1SM": "0", "LAFS_DE_CLUSTER": "2"}):
         out = _step_outputs(P, B, C, D, kind, env)
         assert abs(out[0] - base[0]) <= 1e-5 * abs(base[0]), (env, out[0], base[0])
         assert (out[3] - base[3]).abs().max() <= 1e-4, (env, float((out[3] - base[3]).abs().max()))

@@ -63,25 +63,70 @@ def main():
         "bwd_weight(dW+jac)": lambda: _lib.call("lafs_head_bwd_weight", G.data_ptr(), ldg, e_hat.data_ptr(), w_hat.data_ptr(),
                                                 inv_w.data_ptr(), B, C, D, dw.data_ptr(), st()),
     }
-    res = {"cfg": name, "B": B, "C": C, "D": D,
-           "env": {k: os.environ.get(k) for k in ("LAFS_HEAD_1SM", "LAFS_DW_UNFUSED", "LAFS_DW_CLUSTER")}}
+    res = {"cfg": name, "B": B, "C": C, "D": D}
     for k, fn in calls.items():
         fn()
     torch.cuda.synchronize()
-    for k, fn in calls.items():
-        res[k + "_us"] = timeit(fn)
-    res["sum_us"] = round(sum(v for k, v in res.items() if k.endswith("_us")), 1)
+    sweeps = {
+        "normalize_w": [{}], "normalize_e": [{}], "loss": [{}],
+        "fwd_stats+merge": [{"LAFS_HEAD_1SM": "0"}, {"LAFS_HEAD_1SM": "1"}],
+        "grad_logits": [{"LAFS_HEAD_1SM": "0"}, {"LAFS_HEAD_1SM": "1"}],
+        "bwd_embed(dE)": [{"LAFS_DE_CLUSTER": "4"}, {"LAFS_DE_CLUSTER": "2"}, {"LAFS_DE_CLUSTER": "1"}],
+        "bwd_weight(dW+jac)": [{"LAFS_DW_CLUSTER": "4"}, {"LAFS_DW_CLUSTER": "2"}, {"LAFS_DW_CLUSTER": "1"},
+                               {"LAFS_DW_UNFUSED": "1"}],
+    }
     fl = 2.0 * B * C * D
-    res["fwd_TFLOPs"] = round(fl / res["fwd_stats+merge_us"] / 1e6, 1)
-    res["grad_TFLOPs"] = round(fl / res["grad_logits_us"] / 1e6, 1)
-    res["dE_TFLOPs"] = round(fl / res["bwd_embed(dE)_us"] / 1e6, 1)
-    res["dW_TFLOPs"] = round(fl / res["bwd_weight(dW+jac)_us"] / 1e6, 1)
+    for k, fn in calls.items():
+        for env in sweeps[k]:
+            os.environ.update(env)
+            fn(); torch.cuda.synchronize()
+            us = timeit(fn)
+            tag = k + ("[" + ",".join(f"{a[5:]}={b}" for a, b in env.items()) + "]" if env else "")
+            res[tag + "_us"] = us
+            if "norm" not in k and k != "loss":
+                res[tag + "_TFLOPs"] = round(fl / us / 1e6, 1)
+            for a in env:
+                os.environ.pop(a, None)
     xg = x.clone().requires_grad_(True)
 
     def step():
         xg.grad = None; h.weight.grad = None
         h.forward_loss(xg, lab).backward()
-    res["step_eager_us"] = timeit(step, warmup=3, iters=10)
+
+    def graph_us(env):
+        os.environ.update(env)
+        try:
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                step()
+            for _ in range(3):
+                g.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            return round(e0.elapsed_time(e1) / 20 * 1e3, 1)
+        finally:
+            for a in env:
+                os.environ.pop(a, None)
+
+    for env in ({}, {"LAFS_DE_CLUSTER": "1"}, {"LAFS_DE_CLUSTER": "2"}, {"LAFS_DW_UNFUSED": "1"}, {"LAFS_DW_CLUSTER": "1"},
+                {"LAFS_DW_CLUSTER": "2"}, {"LAFS_HEAD_1SM": "1"},
+                {"LAFS_HEAD_1SM": "1", "LAFS_DE_CLUSTER": "1", "LAFS_DW_UNFUSED": "1"}):
+        tag = "step_graph[" + ",".join(f"{a[5:]}={b}" for a, b in env.items()) + "]_us"
+        res[tag] = graph_us(env)
     print(json.dumps(res))
 
 
