@@ -301,8 +301,8 @@ head_gemm_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (PAIR && !leader) mbar_arrive_remote(acc_empty_remote + (uint32_t)(buf * 8));
-        else mbar_arrive(acc_empty + buf);
+        if (PAIR && !leader) mbar_arrive_remote_relaxed(acc_empty_remote + (uint32_t)(buf * 8));
+        else mbar_arrive_relaxed(acc_empty + buf);
       }
     }
     if (MODE == HEAD_STATS && row_ok) {

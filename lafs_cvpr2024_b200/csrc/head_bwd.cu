@@ -217,7 +217,7 @@ gemm_bwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty + buf);
+      if (lane == 0) mbar_arrive_relaxed(acc_empty + buf);
     }
   }
   tc_fence_before();
@@ -396,7 +396,7 @@ dw_fused_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constan
       // the accumulator is drained: the UMMAs of the next tile run under phase B
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty);
+      if (lane == 0) mbar_arrive_relaxed(acc_empty);
       __threadfence_block();
       asm volatile("bar.sync 1, 256;" ::: "memory");       // every row of the tile is written (8 epilogue warps)
       // ---- phase B: F.normalize Jacobian in place, one warp per row (16 rows per warp), the row and

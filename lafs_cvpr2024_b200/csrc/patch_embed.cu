@@ -335,7 +335,7 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(acc_empty + buf);
+        if (lane == 0) mbar_arrive_relaxed(acc_empty + buf);   // no release: do not wait for the token stores
       }
     }
   } else if (warp >= kWarpGather0) {

@@ -23,6 +23,13 @@ __device__ __forceinline__ void fence_mbar_init() {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// arrive WITHOUT release semantics: for "this TMEM accumulator has been read" signals, where the only
+// prior work that must be ordered is tcgen05.ld (ordered by tcgen05.wait::ld + fence::before_thread_sync).
+// A releasing arrive compiles to MEMBAR + ERRBAR and makes the warp wait for its outstanding GLOBAL
+// stores (the epilogue's output) before every accumulator hand-back.
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -140,6 +147,9 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t ra
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {   // see mbar_arrive_relaxed
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load into THIS CTA's shared memory whose byte count is credited to an mbarrier that may live in
 // the pair's other CTA (`bar_cluster_addr` is a shared::cluster address)

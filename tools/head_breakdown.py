@@ -72,8 +72,7 @@ def main():
         "fwd_stats+merge": [{"LAFS_HEAD_1SM": "0"}, {"LAFS_HEAD_1SM": "1"}],
         "grad_logits": [{"LAFS_HEAD_1SM": "0"}, {"LAFS_HEAD_1SM": "1"}],
         "bwd_embed(dE)": [{"LAFS_DE_CLUSTER": "4"}, {"LAFS_DE_CLUSTER": "2"}, {"LAFS_DE_CLUSTER": "1"}],
-        "bwd_weight(dW+jac)": [{"LAFS_DW_CLUSTER": "4"}, {"LAFS_DW_CLUSTER": "2"}, {"LAFS_DW_CLUSTER": "1"},
-                               {"LAFS_DW_UNFUSED": "1"}],
+        "bwd_weight(dW+jac)": [{}, {"LAFS_DW_FUSED": "1", "LAFS_DW_CLUSTER": "1"}, {"LAFS_DW_FUSED": "1", "LAFS_DW_CLUSTER": "2"}],
     }
     fl = 2.0 * B * C * D
     for k, fn in calls.items():
@@ -122,9 +121,8 @@ def main():
             for a in env:
                 os.environ.pop(a, None)
 
-    for env in ({}, {"LAFS_DE_CLUSTER": "1"}, {"LAFS_DE_CLUSTER": "2"}, {"LAFS_DW_UNFUSED": "1"}, {"LAFS_DW_CLUSTER": "1"},
-                {"LAFS_DW_CLUSTER": "2"}, {"LAFS_HEAD_1SM": "1"},
-                {"LAFS_HEAD_1SM": "1", "LAFS_DE_CLUSTER": "1", "LAFS_DW_UNFUSED": "1"}):
+    for env in ({}, {"LAFS_HEAD_1SM": "1"}, {"LAFS_DE_CLUSTER": "1"}, {"LAFS_DW_FUSED": "1"},
+                {"LAFS_DW_FUSED": "1", "LAFS_DW_CLUSTER": "2"}):
         tag = "step_graph[" + ",".join(f"{a[5:]}={b}" for a, b in env.items()) + "]_us"
         res[tag] = graph_us(env)
     print(json.dumps(res))
