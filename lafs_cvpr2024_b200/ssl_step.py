@@ -74,7 +74,7 @@ class SSLHotPath:
 
 class GraphedSSLStep:
     """The whole hot-path step captured once into a CUDA graph and replayed with a single launch
-    (15 kernels -> 1 graph launch; the inputs live in static device buffers that the caller
+    (11 kernels -> 1 graph launch; the inputs live in static device buffers that the caller
     refreshes, e.g. with copy_ from pinned host memory on a copy stream).
 
     Static inputs : img_g, img_l (uint8 or fp32), raw_g, raw_l, noise_g, noise_l, idx_l,

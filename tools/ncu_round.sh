@@ -19,8 +19,10 @@ cap dino_bwd dino_bwd_kernel dino 1
 cap pe_global gather_embed_kernel pe_global 1
 cap pe_local gather_embed_kernel pe_local 1
 cap pe_global_u8 gather_embed_kernel pe_global_u8 1
-cap head_fwd head_gemm_kernel head_bwd 2     # launches per repetition: <256,0> (forward), <256,2> (grad logits)
+cap dino_finish dino_finish dino 1
+cap head_fwd head_gemm_kernel head_bwd 2     # launches per repetition: <256,0,pair> (forward), <256,2,pair> (grad logits)
 cap head_grad head_gemm_kernel head_bwd 3
-cap head_de gemm_bwd_kernel head_bwd 2       # <0> (dE, split-K), <1> (dW)
+cap head_de gemm_bwd_kernel head_bwd 2       # <0,4> (dE, split-K, W_hat multicast), <1,1> (dW)
 cap head_dw gemm_bwd_kernel head_bwd 3
+rm -f gpurun_out/head_dwf.ncu-rep gpurun_out/head_dwf.log
 ls -la gpurun_out/*.ncu-rep
