@@ -162,6 +162,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # rank 0 prints exactly ONE line on stdout: keep NCCL's "NCCL version ..." banner off it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     if _lib.lib().lafs_device_ok() != 1:
         raise SystemExit("bench.py needs a compute-capability 10.x device (B200)")
