@@ -236,6 +236,21 @@ LAFS_API int lafs_embed_bwd_weight(const void* grad_emb_bf16, const void* tokens
 LAFS_API int lafs_embed_bwd_tokens(const void* grad_emb_bf16, const void* weight_bf16, int M, int dim,
                                    float* grad_tokens, lafs_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * (4e) Exchange steps of the class-sharded head over NVLink peer memory (one kernel each, instead of
+ *      NCCL all_gather / all_reduce).  The reference has no counterpart (it replicates the head,
+ *      ViT_face.py:56 only chunks the weight for the matmul); the ownership rule is torch.chunk's.
+ * Every rank maps one symmetric buffer of lafs_xchg_bytes(world, B, D, offsets) bytes (same layout on
+ * all ranks, zero-filled once, e.g. torch.distributed._symmetric_memory); peer_base is a DEVICE array
+ * of the `world` base addresses as seen from this rank.  offsets[0..4] = flags, statistics slots,
+ * partial dE_hat [B,D] fp32 (all-reduce input), summed dE_hat [B,D] fp32 (output), error flag (uint32,
+ * non-zero after a peer failed to arrive within the spin bound).  world <= 8, D % 4 == 0.
+ * All ranks must issue the same sequence of lafs_xchg_* calls. */
+LAFS_API size_t lafs_xchg_bytes(int world, int B, int D, size_t* offsets);
+LAFS_API int lafs_xchg_stats(const void* peer_base, int rank, int world, int B, int D, const float* local_stats,
+                             float* merged_stats, lafs_stream_t stream);
+LAFS_API int lafs_xchg_allreduce(const void* peer_base, int rank, int world, int B, int D, lafs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,15 +67,17 @@ def _round8(n):
     return (n + 15) // 16 * 16
 
 
-def _head_backward(G, ldg, e_hat, w_hat, inv_e, inv_w, B, C, D, sharded):
+def _head_backward(G, ldg, e_hat, w_hat, inv_e, inv_w, B, C, D, sharded, xchg=None):
     """dE [B,D], dW [C,D] (fp32) from the bf16 logit gradient G [B, ldg] via two tcgen05 GEMMs."""
     dev = e_hat.device
     nbytes = _lib.lib().lafs_head_bwd_workspace_bytes(B, C, D)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    de_hat = torch.empty(B, D, dtype=torch.float32, device=dev)
+    de_hat = xchg.de_in if (sharded and xchg is not None) else torch.empty(B, D, dtype=torch.float32, device=dev)
     _lib.call("lafs_head_bwd_embed", G.data_ptr(), ldg, w_hat.data_ptr(), B, C, D, de_hat.data_ptr(),
               ws.data_ptr(), nbytes, _lib.stream())
-    if sharded:
+    if sharded and xchg is not None:
+        de_hat = xchg.allreduce_de()                 # sum over the class shards through peer memory
+    elif sharded:
         dist.all_reduce(de_hat)                      # sum over the class shards
     de = torch.empty_like(de_hat)
     _lib.call("lafs_normalize_bwd", de_hat.data_ptr(), e_hat.data_ptr(), inv_e.data_ptr(), B, D, de.data_ptr(),
@@ -106,7 +108,10 @@ class _HeadLossFn(torch.autograd.Function):
                   B, C, D, head.class_lo, float(head.s), float(head.m), head.kind, stats.data_ptr(),
                   ws.data_ptr(), nbytes, _lib.stream())
         sharded = head.shard is not None and head.shard[1] > 1
-        if sharded:
+        xchg = head._exchange(B, D, dev) if sharded else None
+        if sharded and xchg is not None:
+            stats = xchg.merge_stats(stats)          # put / flag / merge through peer memory, one kernel
+        elif sharded:
             parts = torch.empty(head.shard[1], B, 4, dtype=torch.float32, device=dev)
             dist.all_gather_into_tensor(parts, stats)
             stats = torch.empty_like(stats)
@@ -118,6 +123,7 @@ class _HeadLossFn(torch.autograd.Function):
         ctx.save_for_backward(e_hat, w_hat, inv_e, inv_w, la, lb if lb is not None else la, lse2)
         ctx.cfg = (head.class_lo, float(head.s), float(head.m), head.kind, lam, lb is not None, sharded,
                    input.dtype)
+        ctx.xchg = xchg
         return loss
 
     @staticmethod
@@ -132,7 +138,7 @@ class _HeadLossFn(torch.autograd.Function):
         _lib.call("lafs_head_grad_logits", e_hat.data_ptr(), w_hat.data_ptr(), la.data_ptr(),
                   lb.data_ptr() if has_b else None, lam, B, C, D, class_lo, s, m, kind, lse2.data_ptr(),
                   g.data_ptr(), s / B, G.data_ptr(), ldg, _lib.stream())
-        de, dw = _head_backward(G, ldg, e_hat, w_hat, inv_e, inv_w, B, C, D, sharded)
+        de, dw = _head_backward(G, ldg, e_hat, w_hat, inv_e, inv_w, B, C, D, sharded, ctx.xchg)
         return de.to(in_dtype), dw, None, None, None, None
 
 
@@ -193,6 +199,25 @@ class _MarginHead(nn.Module):
         full = torch.empty(out_features, in_features)
         nn.init.xavier_uniform_(full)                     # same init as the reference (ViT_face.py:46-47)
         self.weight = Parameter(full[lo:hi].clone())
+
+    # ---- class-sharded exchange ------------------------------------------------------------------
+    def enable_peer_exchange(self, group=None, enabled=True):
+        """Run the two exchange steps of forward_loss (row statistics, dE sum) as peer-memory kernels over
+        NVLink (csrc/exchange.cu) instead of NCCL all_gather / all_reduce.  All ranks of `group` (one node)
+        must call this; buffers are created lazily per (B, D)."""
+        self._peer = bool(enabled)
+        self._peer_group = group
+        self._xchg = {}
+        return self
+
+    def _exchange(self, B, D, dev):
+        if not getattr(self, "_peer", False):
+            return None
+        key = (B, D)
+        if key not in self._xchg:
+            from .peer_exchange import PeerExchange
+            self._xchg[key] = PeerExchange(self._peer_group, B, D, dev)
+        return self._xchg[key]
 
     # ---- helpers -----------------------------------------------------------------------------
     def _labels(self, label, label_b, lam):

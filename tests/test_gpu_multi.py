@@ -38,6 +38,23 @@ def _worker(rank, world, port, ret):
         assert abs(float(loss) - float(lf)) <= 1e-5 * abs(float(lf)), (float(loss), float(lf))
         assert (xg.grad - xf.grad).abs().max() <= 2e-3 * xf.grad.abs().max()
         assert (h.weight.grad - full.weight.grad[lo:hi]).abs().max() <= 2e-3 * full.weight.grad.abs().max()
+        # the same step with the exchange through NVLink peer memory (csrc/exchange.cu) instead of NCCL
+        h2 = P.CosFace(D, C, None, shard=(rank, world)).cuda().enable_peer_exchange()
+        with torch.no_grad():
+            h2.weight.copy_(w[lo:hi])
+        for it in range(4):                          # several calls: flag epochs, slot parity
+            x2 = x.cuda().requires_grad_(True)
+            h2.weight.grad = None
+            l2 = h2.forward_loss(x2, lab.cuda())
+            l2.backward()
+            assert abs(float(l2) - float(loss)) <= 1e-6 * abs(float(loss)), (it, float(l2), float(loss))
+            assert (x2.grad - xg.grad).abs().max() <= 1e-5 * xg.grad.abs().max()
+            assert (h2.weight.grad - h.weight.grad).abs().max() <= 1e-5 * h.weight.grad.abs().max()
+        # every rank holds bit-identical summed gradients (fixed reduction order)
+        gx_all = [torch.empty_like(x2.grad) for _ in range(world)]
+        dist.all_gather(gx_all, x2.grad.contiguous())
+        assert all(torch.equal(gx_all[0], g) for g in gx_all)
+        h2._xchg[(B, D)].check()
         # DINO centre: every rank ends with the same centre = EMA of the global teacher mean
         K = 4096
         g = torch.Generator().manual_seed(10 + rank)
