@@ -22,7 +22,8 @@
 namespace lafs {
 
 constexpr int kXMaxRanks = 8;      // one NVSwitch domain
-constexpr int kXBlocks = 16;       // CTAs of the all-reduce kernel (all co-resident: they spin on flags)
+constexpr int kXBlocks = 16;       // flag / counter slots per kind (only slot 0 is used by the current kernels)
+constexpr int kXReduceCtas = 64;   // CTAs of the all-reduce data phase
 constexpr int kXThreads = 256;
 constexpr long long kXSpinLimit = 1LL << 24;
 
@@ -120,34 +121,74 @@ xchg_stats_kernel(const uint64_t* __restrict__ peer_base, int rank, int world, i
   if (threadIdx.x == 0) counters[0] = epoch;
 }
 
+// Cross-GPU synchronisation is done by ONE CTA per phase (a system-scope round trip costs microseconds):
+// CTA 0 runs the entry barrier and releases the other CTAs through a local flag; the CTA that finishes
+// its stores last runs the exit barrier.  The data phase is spread over many CTAs with all peer loads
+// of a thread issued before the first use (a peer load is ~2 us of latency).
 __global__ void __launch_bounds__(kXThreads)
 xchg_allreduce_kernel(const uint64_t* __restrict__ peer_base, int rank, int world, XLayout l, int n4) {
   __shared__ unsigned s_epoch;
+  __shared__ int s_last;
   char* my = reinterpret_cast<char*>(peer_base[rank]);
   unsigned* counters = reinterpret_cast<unsigned*>(my + l.off_counters);
-  const int blk = blockIdx.x;
-  if (threadIdx.x == 0) s_epoch = counters[1 + blk] + 1u;
+  unsigned* err = counters + 1 + kXBlocks;
+  unsigned* go = counters + 2;          // local: epoch whose entry barrier has completed
+  unsigned* done = counters + 3;        // local: CTAs that finished their stores in this call
+  if (threadIdx.x == 0) s_epoch = counters[1] + 1u;     // counters[1] is advanced by the last CTA only
   __syncthreads();
   const unsigned epoch = s_epoch;
-  // every rank's partial (written by its preceding kernel) is complete
-  xbarrier(peer_base, l.off_flags, 1, blk, rank, world, epoch, counters + 1 + kXBlocks);
-  // slice of this rank, sub-slice of this CTA
+  if (blockIdx.x == 0) {
+    // every rank's partial (written by its preceding kernel) is complete
+    xbarrier(peer_base, l.off_flags, 1, 0, rank, world, epoch, err);
+    if (threadIdx.x == 0) {
+      __threadfence();
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(go), "r"(epoch) : "memory");
+    }
+  } else {
+    if (threadIdx.x == 0) {
+      unsigned v;
+      long long spins = 0;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(go) : "memory");
+      } while ((int)(v - epoch) < 0 && ++spins < kXSpinLimit);
+    }
+    __syncthreads();
+  }
+  // slice of this rank, spread over the CTAs
   const int per_rank = (n4 + world - 1) / world;
   const int r_lo = rank * per_rank, r_hi = min(n4, r_lo + per_rank);
-  const int per_blk = (per_rank + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int lo = r_lo + blk * per_blk, hi = min(r_hi, lo + per_blk);
-  for (int i = lo + (int)threadIdx.x; i < hi; i += kXThreads) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int q = 0; q < world; ++q) {       // fixed order: bit-identical result on every rank
-      const float4 v = ld_relaxed_sys_f4(reinterpret_cast<const float4*>(peer_base[q] + l.off_in) + i);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  constexpr int U = 4;
+  for (int base = r_lo + ((int)blockIdx.x * kXThreads + (int)threadIdx.x) * U; base < r_hi;
+       base += (int)gridDim.x * kXThreads * U) {
+    float4 v[U][kXMaxRanks];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int q = 0; q < kXMaxRanks; ++q)
+        if (q < world && base + u < r_hi)
+          v[u][q] = ld_relaxed_sys_f4(reinterpret_cast<const float4*>(peer_base[q] + l.off_in) + base + u);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (base + u < r_hi) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < kXMaxRanks; ++q)       // fixed order: bit-identical result on every rank
+          if (q < world) { acc.x += v[u][q].x; acc.y += v[u][q].y; acc.z += v[u][q].z; acc.w += v[u][q].w; }
+        for (int p = 0; p < world; ++p) reinterpret_cast<float4*>(peer_base[p] + l.off_out)[base + u] = acc;
+      }
     }
-    for (int p = 0; p < world; ++p) reinterpret_cast<float4*>(peer_base[p] + l.off_out)[i] = acc;
   }
   __syncthreads();
-  // every rank's slice has landed everywhere
-  xbarrier(peer_base, l.off_flags, 2, blk, rank, world, epoch, counters + 1 + kXBlocks);
-  if (threadIdx.x == 0) counters[1 + blk] = epoch;
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    s_last = atomicAdd(done, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last) {
+    // every CTA of this rank has stored its part; tell the peers and wait until their slices have landed here
+    xbarrier(peer_base, l.off_flags, 2, 0, rank, world, epoch, err);
+    if (threadIdx.x == 0) { *done = 0u; counters[1] = epoch; }
+  }
 }
 
 }  // namespace lafs
@@ -194,7 +235,7 @@ extern "C" int lafs_xchg_allreduce(const void* peer_base, int rank, int world, i
   int rc = xchg_check(peer_base, rank, world, B, D, "lafs_xchg_allreduce");
   if (rc) return rc;
   const long long n4 = (long long)B * D / 4;
-  xchg_allreduce_kernel<<<kXBlocks, kXThreads, 0, (cudaStream_t)stream>>>((const uint64_t*)peer_base, rank, world,
+  xchg_allreduce_kernel<<<kXReduceCtas, kXThreads, 0, (cudaStream_t)stream>>>((const uint64_t*)peer_base, rank, world,
                                                                          xlayout(world, B, D), (int)n4);
   return check_launch("lafs_xchg_allreduce");
 }
