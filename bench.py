@@ -180,6 +180,17 @@ def run_ours(args):
     t_embed = (st["teacher_params"][1], st["teacher_params"][2])
     path = SSLHotPath(OUT_DIM, L, st["teacher_params"], st["student_params"], student_embed=s_embed, teacher_embed=t_embed)
     path.loss.center = torch.randn(1, OUT_DIM, device=dev) * 0.1
+    centre_exchange = "none (single process)"
+    if world > 1:
+        # the path's one collective (teacher column sums, lafs_train.py:675) through the peer-memory kernel;
+        # NCCL all_reduce if symmetric memory cannot be set up on this box
+        try:
+            path.loss.enable_peer_exchange()
+            path.loss._exchange(OUT_DIM, dev)
+            centre_exchange = "peer-memory all-reduce kernel (csrc/exchange.cu)"
+        except Exception as e:
+            path.loss.enable_peer_exchange(enabled=False)
+            centre_exchange = "nccl all_reduce (peer exchange unavailable: %s)" % str(e).splitlines()[0][:80]
     sched = 0.996 + 0.5 * (1 - 0.996) * (1 - np.cos(np.pi * np.arange(100000) / 100000))  # utils.py:187-198
     names = ["landmark+gather_embed", "dino_fwd+center", "dino_bwd", "ema"]
 
@@ -350,7 +361,7 @@ def run_ours(args):
                    "batch_per_gpu": B, "out_dim": K, "ncrops": nc, "ema_params": nparam, "ema_tensors": len(vit_b_param_shapes()),
                    "images": "uint8 decoded pixels, normalised in-kernel (value_fp32_images / e2e_fp32_images: fp32 tensors)",
                    "l2": "inputs larger than L2 (logits 335 MB, tokens out 362 MB, parameters 882 MB per step)",
-                   "parallelism": f"dp{world}"},
+                   "parallelism": f"dp{world}", "centre_exchange": centre_exchange},
         "e2e": {"value": round(faces / (ms_e2e / args.steps / 1e3), 1), "unit": "faces/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 5),
                 "transport": "uint8 pixels + fp32 noise + int64 indices from pinned memory on a copy stream (double "

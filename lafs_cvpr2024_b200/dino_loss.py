@@ -93,6 +93,33 @@ class DINOLoss(nn.Module):
         ))
         self._stash = {}
 
+    def enable_peer_exchange(self, group=None, enabled=True):
+        """Sum the [K] teacher column sums over the ranks with the NVLink peer-memory all-reduce kernel
+        (csrc/exchange.cu) instead of NCCL all_reduce (lafs_train.py:675).  All ranks of `group` (one node)
+        must call this."""
+        self._peer = bool(enabled)
+        self._peer_group = group
+        self._xchg = None
+        return self
+
+    def _exchange(self, K, dev):
+        if not getattr(self, "_peer", False):
+            return None
+        if self._xchg is None:
+            from .peer_exchange import PeerExchange
+            self._xchg = PeerExchange(self._peer_group, 1, K, dev)
+        return self._xchg
+
+    def _allreduce_colsum(self, colsum):
+        """sum of `colsum` [K] over the ranks (every rank gets identical bits)."""
+        xchg = self._exchange(colsum.numel(), colsum.device)
+        if xchg is None:
+            dist.all_reduce(colsum)
+            return colsum
+        if colsum.data_ptr() != xchg.de_in.data_ptr():
+            xchg.de_in.view(-1).copy_(colsum)
+        return xchg.allreduce_de().view(-1)
+
     def forward(self, student_output, teacher_output, epoch):
         temp = self.teacher_temp_schedule[epoch]
         single = not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
@@ -118,14 +145,16 @@ class DINOLoss(nn.Module):
             raise ValueError("shape mismatch between student_output, teacher_output and center")
         loss = torch.empty((), dtype=torch.float32, device=dev)
         row_stats = torch.empty((self.ncrops + 2) * B, dtype=torch.float32, device=dev)
-        colsum = torch.empty(K, dtype=torch.float32, device=dev)
+        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        xchg = self._exchange(K, dev) if world > 1 else None
+        # with the peer exchange the kernel writes the column sums straight into the symmetric buffer
+        colsum = xchg.de_in.view(-1) if xchg is not None else torch.empty(K, dtype=torch.float32, device=dev)
         grad = torch.empty_like(s)
         g = grad_scale if grad_scale is not None else torch.ones((), dtype=torch.float32, device=dev)
         nbytes = _lib.lib().lafs_dino_fused_workspace_bytes(B, K, self.ncrops)
         if nbytes == 0:
             raise ValueError(f"unsupported DINO shape B={B} K={K} ncrops={self.ncrops}")
         ws = _workspace(dev, nbytes)
-        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         new_center = torch.empty(1, K, dtype=torch.float32, device=dev) if world == 1 else None
         m = float(self.center_momentum)
         temp = float(self.teacher_temp_schedule[epoch])
@@ -136,7 +165,7 @@ class DINOLoss(nn.Module):
         if world == 1:
             self.center = new_center
         else:
-            dist.all_reduce(colsum)
+            colsum = self._allreduce_colsum(colsum)
             nc = torch.empty(1, K, dtype=torch.float32, device=dev)
             _lib.call("lafs_center_ema", c.data_ptr(), colsum.data_ptr(), float(2 * B * world), float(np.float32(m)),
                       float(np.float32(1.0 - m)), K, nc.data_ptr(), _lib.stream())
@@ -167,7 +196,7 @@ class DINOLoss(nn.Module):
         if dist.is_available() and dist.is_initialized():
             world = dist.get_world_size()
             if world > 1:
-                dist.all_reduce(colsum)
+                colsum = self._allreduce_colsum(colsum)
         center = self.center.float().contiguous()
         new_center = torch.empty_like(center)
         m = float(self.center_momentum)

@@ -66,6 +66,20 @@ def _worker(rank, world, port, ret):
         dist.all_gather(allt, t)
         ref = torch.cat(allt).sum(0, keepdim=True) / (8 * world) * (1 - 0.9)
         torch.testing.assert_close(crit.center, ref, rtol=1e-5, atol=1e-6)
+        # the same centre update with the column sums all-reduced through peer memory; single-call form too
+        crit2 = P.DINOLoss(K, 4, 0.04, 0.07, 30, 41).cuda().enable_peer_exchange()
+        crit2(s, t, 0)
+        torch.testing.assert_close(crit2.center, crit.center, rtol=1e-6, atol=1e-7)
+        crit3 = P.DINOLoss(K, 4, 0.04, 0.07, 30, 41).cuda().enable_peer_exchange()
+        for _ in range(3):
+            crit3.center = torch.zeros(1, K, device="cuda")
+            l3, g3 = crit3.loss_and_grad(s.bfloat16(), t.bfloat16(), 0)
+        cref = P.DINOLoss(K, 4, 0.04, 0.07, 30, 41).cuda()
+        cref.loss_and_grad(s.bfloat16(), t.bfloat16(), 0)
+        torch.testing.assert_close(crit3.center, cref.center, rtol=1e-6, atol=1e-7)
+        cs = [torch.empty_like(crit3.center) for _ in range(world)]
+        dist.all_gather(cs, crit3.center.contiguous())
+        assert all(torch.equal(cs[0], c) for c in cs)      # identical bits on every rank
         ret[rank] = "ok"
     finally:
         dist.destroy_process_group()
