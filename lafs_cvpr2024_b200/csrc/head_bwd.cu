@@ -250,7 +250,6 @@ namespace dwf {
 constexpr int kBM = 128, kBK = 64;
 constexpr int kThreads = 320;
 constexpr int kStageA = kBM * kBK * 2;                  // 16 KB: two {64 m, 64 k} boxes
-constexpr int kMaxPieces = 8;                           // 32-column pieces per epilogue warp: D / 2 <= 256
 constexpr int kPitch = 36;
 constexpr int kStageOut = 8 * 32 * kPitch * 4;          // 36,864 B: a [32 x 32] fp32 block per epilogue warp
 __host__ __device__ constexpr int stage_b(int D) { return D * kBK * 2; }   // D/64 boxes of 8 KB
@@ -272,8 +271,7 @@ dw_fused_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int stage_bytes = kStageA + stage_b(p.D);
   float* s_out = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes);
-  float* s_dot = s_out + kStageOut / 4;                              // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_dot + 256);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + kStageOut / 4);
   uint64_t* full = bars;                 // stages
   uint64_t* empty = bars + p.stages;     // stages
   uint64_t* acc_full = empty + p.stages; // 1
@@ -752,7 +750,7 @@ extern "C" int lafs_head_bwd_weight(const void* grad_bf16, long long ldg, const 
     q.kblocks = (B + 63) / 64;
     q.tmem_cols = D <= 32 ? 32 : D <= 64 ? 64 : D <= 128 ? 128 : D <= 256 ? 256 : 512;
     const int stage_bytes = dwf::kStageA + dwf::stage_b(D);
-    const int tail = dwf::kStageOut + 1024 /*dots*/ + 1024 /*align*/ + 256 /*barriers*/;
+    const int tail = dwf::kStageOut + 1024 /*align*/ + 256 /*barriers*/;
     q.stages = (227 * 1024 - tail) / stage_bytes;
     if (q.stages > 6) q.stages = 6;
     LAFS_REQUIRE(q.stages >= 2, LAFS_ERR_ARG, "lafs_head_bwd_weight: D=%d leaves no room for a 2-stage pipeline", D);
