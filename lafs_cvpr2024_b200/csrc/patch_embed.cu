@@ -88,10 +88,6 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
                : "memory");
 }
 
-__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {   // bytes % 16 == 0
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes) : "memory");
-}
-
 __device__ __forceinline__ void store_out(float* p, float v) { *p = v; }
 __device__ __forceinline__ void store_out(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
@@ -212,27 +208,13 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
     // ===================== image plane producer =====================
     if (lane == 0) {
       const InT* imgs = reinterpret_cast<const InT*>(p.imgs);
-      // The 2-slot ring keeps ONE plane in flight (12.5 / 50 KB): with many small faces per unit
-      // (36-landmark views: 15 planes per unit, little gather work per plane) the unit becomes a chain
-      // of HBM latencies.  The planes of the unit after this one are therefore pulled into L2 while this
-      // unit is processed, so the ring's loads are L2 hits.
-      // (A prefetch immediately followed by the load of the same bytes fetches them TWICE from DRAM
-      //  -- measured +66 MB on the 36-landmark launch -- so the first face of the first unit, whose
-      //  loads are issued right away, is not prefetched.)
-      auto prefetch_group = [&](int g, int first_face) {
-        const int nf = group_faces(g);
-        for (int ff = first_face; ff < nf; ++ff)
-          bulk_prefetch_l2(imgs + (size_t)(g * p.gfaces + ff) * kC * (kH * kW), (uint32_t)(kC * L::kPlaneBytes));
-      };
-      if (nunits_mine > 0) prefetch_group(unit_group(blockIdx.x), 1);
+      // (An L2 prefetch of the next unit's planes -- cp.async.bulk.prefetch.L2 one work unit ahead of the
+      //  ring's loads -- was measured and removed: the bulk loads did not hit the prefetched lines, DRAM
+      //  reads rose from 155 to 217 MB on the 36-landmark launch and the kernel slowed from 64 to 74 us.)
       uint32_t cnt = 0;
       for (int gi = 0; gi < nunits_mine; ++gi) {
         const int g = unit_group(blockIdx.x + gi * gridDim.x);
         const int nf = group_faces(g);
-        if (gi + 1 < nunits_mine) {
-          const int gn = unit_group(blockIdx.x + (gi + 1) * gridDim.x);
-          if (gn != g) prefetch_group(gn, 0);
-        }
         for (int ff = 0; ff < nf; ++ff) {
           const int f = g * p.gfaces + ff;
           for (int c = 0; c < kC; ++c, ++cnt) {
