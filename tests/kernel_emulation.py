@@ -59,3 +59,40 @@ def gather_tokens(imgs, th, recip=False):
         r = _fma(vne, bc(ne), r); r = _fma(vsw, bc(sw), r); r = _fma(vse, bc(se), r)
         out[b] = np.transpose(r, (1, 2, 3, 0))
     return out
+
+
+def xchg_slices(n4, world, nctas=64, threads=256, unroll=4):
+    """Index sets (in float4 units) that rank r's CTAs cover in xchg_allreduce_kernel (csrc/exchange.cu):
+    rank r owns [r*per, min(n4, (r+1)*per)), per = ceil(n4 / world); a thread starts at
+    r_lo + (cta*threads + tid)*unroll and strides by nctas*threads*unroll."""
+    per = -(-n4 // world)
+    out = []
+    for r in range(world):
+        lo, hi = r * per, min(n4, (r + 1) * per)
+        idx = []
+        for cta in range(nctas):
+            for tid in range(threads):
+                base = lo + (cta * threads + tid) * unroll
+                while base < hi:
+                    idx.extend(i for i in range(base, base + unroll) if i < hi)
+                    base += nctas * threads * unroll
+        out.append(sorted(idx))
+    return out
+
+
+def xchg_allreduce(parts):
+    """Two-shot all-reduce as the kernel performs it: rank r sums slice r of every rank's partial in rank
+    order (fp32, fixed order), every rank receives every slice.  parts: list of equal-shape fp32 arrays
+    whose size is a multiple of 4.  Returns the array every rank ends with."""
+    world = len(parts)
+    flat = [np.asarray(p, dtype=np.float32).reshape(-1, 4) for p in parts]
+    n4 = flat[0].shape[0]
+    out = np.empty_like(flat[0])
+    per = -(-n4 // world)
+    for r in range(world):
+        lo, hi = r * per, min(n4, (r + 1) * per)
+        acc = np.zeros((max(hi - lo, 0), 4), dtype=np.float32)
+        for q in range(world):
+            acc = (acc + flat[q][lo:hi]).astype(np.float32)
+        out[lo:hi] = acc
+    return out.reshape(np.asarray(parts[0]).shape)

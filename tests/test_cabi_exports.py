@@ -49,6 +49,29 @@ def test_argument_errors_without_gpu(lib):
     assert h.lafs_ema_multi(None, 3, 0.9, 0.1, 0, None) == -1
 
 
+def test_host_only_planning_entries(lib):
+    """Sizing / layout entry points are pure host code: callable without a GPU."""
+    import ctypes as C
+    h = lib.lib()
+    offs = (C.c_size_t * 5)()
+    for world, B, D in ((2, 512, 512), (8, 1024, 512), (8, 1, 65536), (1, 7, 64)):
+        total = h.lafs_xchg_bytes(world, B, D, offs)
+        flags, slots, o_in, o_out, err = list(offs)
+        assert flags == 0 and flags < err < slots < o_in < o_out < total
+        assert slots % 256 == 0 and o_in % 256 == 0 and o_out % 256 == 0 and total % 256 == 0
+        assert o_in - slots >= 2 * world * B * 16            # two parities of [world][B] float4 records
+        assert o_out - o_in >= B * D * 4 and total - o_out >= B * D * 4
+    assert h.lafs_xchg_bytes(9, 512, 512, offs) == 0 and h.lafs_xchg_bytes(0, 512, 512, offs) == 0
+    assert h.lafs_xchg_bytes(2, 512, 512, None) > 0
+    assert h.lafs_embed_bwd_workspace_bytes(100352, 768) >= 768 * 192 * 4
+    assert h.lafs_embed_bwd_workspace_bytes(0, 768) == 0
+    assert h.lafs_head_workspace_bytes(512, 93431, 512) > 0 and h.lafs_head_workspace_bytes(512, 93431, 100) == 0
+    assert h.lafs_head_bwd_workspace_bytes(512, 93431, 512) >= 512 * 512 * 4
+    # null pointers are rejected before any CUDA call
+    assert h.lafs_embed_bwd_weight(None, None, 128, 768, None, None, 0, None) == -1
+    assert h.lafs_embed_bwd_tokens(None, None, 128, 768, None, None) == -1
+
+
 def test_no_cpu_fallback():
     import lafs_cvpr2024_b200 as P
     with pytest.raises(RuntimeError, match="no CPU fallback"):
