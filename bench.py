@@ -304,6 +304,9 @@ def run_ours(args):
     ms_e2e, h2d = run_e2e(host)
     ms_e2e_f32, h2d_f32 = run_e2e(host_f32)
     clocks = sampler.stop() if sampler else None    # sampled across every timed region above
+    xc = getattr(path.loss, "_xchg", None)
+    if xc is not None:
+        xc.check()                    # raises if a rank missed the centre exchange's spin bound
 
     # ---- secondary: class-sharded margin head (BASELINE configs[2], configs[3]) -----------------
     del st, path, dev_in
@@ -456,6 +459,9 @@ def bench_head(P, world, rank, dev, dist, args):
         except Exception as e:  # capture not possible on this stack: keep the eager number
             mode = "eager (graph capture failed: %s)" % str(e).splitlines()[0][:80]
             torch.cuda.synchronize()
+        if peer:                      # a peer that missed the kernels' spin bound would have produced garbage
+            for xc in h._xchg.values():
+                xc.check()
         del h, x
         torch.cuda.empty_cache()
         return ms, ms_eager, mode
