@@ -96,3 +96,89 @@ def xchg_allreduce(parts):
             acc = (acc + flat[q][lo:hi]).astype(np.float32)
         out[lo:hi] = acc
     return out.reshape(np.asarray(parts[0]).shape)
+
+
+def dino_sliced_loss(student, teacher, center, ncrops, inv_ts, inv_tt, slice_cols=256):
+    """The DINO forward as the kernels decompose it (csrc/dino.cu), in float64: per (sample, column slice)
+    partial records in the log2 domain -- teacher view iq: (max, Z, A) with A = sum_k e_iq,k * (S_k - s_iq,k),
+    S = sum of the student rows; student crop v: (max, sum) -- then dino_finish's two-pass merge over the
+    slices, the per-sample loss  sum_v n_v*lse(s_v/ts) - (1/ts) * sum_iq A_iq/Z_iq  and the mean over
+    samples / (2*ncrops - 2).  Returns (loss, per-row log2-domain lse [ncrops+2, B], column sums [K])."""
+    s = np.asarray(student, dtype=np.float64)
+    t = np.asarray(teacher, dtype=np.float64)
+    c = np.asarray(center, dtype=np.float64).reshape(-1)
+    K = s.shape[1]
+    B = s.shape[0] // ncrops
+    log2e = 1.4426950408889634
+    a_s, a_t = inv_ts * log2e, inv_tt * log2e
+    nsl = -(-K // slice_cols)
+    rec_t = np.zeros((B, nsl, 2, 3))
+    rec_s = np.zeros((B, nsl, ncrops, 2))
+    colsum = t.sum(0)
+    for b in range(B):
+        for sl in range(nsl):
+            k0, k1 = sl * slice_cols, min(K, (sl + 1) * slice_cols)
+            srows = np.stack([s[v * B + b, k0:k1] for v in range(ncrops)])
+            S = srows.sum(0)
+            for iq in range(2):
+                x = t[iq * B + b, k0:k1] * a_t - c[k0:k1] * a_t
+                mx = x.max()
+                e = np.exp2(x - mx)
+                rec_t[b, sl, iq] = (mx, e.sum(), (e * (S - srows[iq])).sum())
+            for v in range(ncrops):
+                mx = srows[v].max() * a_s
+                rec_s[b, sl, v] = (mx, np.exp2(srows[v] * a_s - mx).sum())
+    stats = np.zeros((ncrops + 2, B))
+    total = 0.0
+    for b in range(B):
+        loss = 0.0
+        for v in range(ncrops):
+            m = rec_s[b, :, v, 0].max()
+            z = (rec_s[b, :, v, 1] * np.exp2(rec_s[b, :, v, 0] - m)).sum()
+            l2 = m + np.log2(z)
+            stats[v, b] = l2
+            loss += (1.0 if v < 2 else 2.0) * l2
+        loss *= 0.6931471805599453
+        for iq in range(2):
+            m = rec_t[b, :, iq, 0].max()
+            f = np.exp2(rec_t[b, :, iq, 0] - m)
+            z, a = (rec_t[b, :, iq, 1] * f).sum(), (rec_t[b, :, iq, 2] * f).sum()
+            stats[ncrops + iq, b] = m + np.log2(z)
+            loss -= inv_ts * (a / z)
+        total += loss
+    return total / ((2 * ncrops - 2) * B), stats, colsum
+
+
+def head_sharded_loss(cos, label, s, m, world, chunk=256):
+    """CosFace + cross-entropy as the head kernels decompose it (csrc/head.cu, exchange.cu), in float64:
+    per (row, rank, class chunk) online-softmax records (max in the log2 domain, sum-exp, target logit),
+    merged per rank, then across ranks in rank order; classes are owned with torch.chunk's rule."""
+    cos = np.asarray(cos, dtype=np.float64)
+    B, C = cos.shape
+    log2e = 1.4426950408889634
+    step = -(-C // world)
+    recs = []
+    for r in range(world):
+        lo, hi = min(r * step, C), min((r + 1) * step, C)
+        mrun = np.full(B, -np.inf); lrun = np.zeros(B); tgt = np.zeros(B)
+        for c0 in range(lo, hi, chunk):
+            c1 = min(hi, c0 + chunk)
+            z = cos[:, c0:c1].copy()
+            for b in range(B):
+                if c0 <= label[b] < c1:
+                    z[b, label[b] - c0] -= m
+                    tgt[b] = s * z[b, label[b] - c0]
+            pm = z.max(1) * s * log2e
+            mn = np.maximum(mrun, pm)
+            lrun = lrun * np.exp2(mrun - mn) + np.exp2(z * s * log2e - mn[:, None]).sum(1)
+            mrun = mn
+        recs.append((mrun, lrun, tgt))
+    M = np.full(B, -np.inf); L = np.zeros(B); T = np.zeros(B)
+    for mr, lr, tg in recs:                      # rank order, as xchg_stats_kernel / head_merge_kernel
+        ok = np.isfinite(mr)
+        mn = np.where(ok, np.maximum(M, mr), M)
+        L = np.where(ok, L * np.exp2(M - mn) + lr * np.exp2(np.where(ok, mr, 0.0) - mn), L)
+        M = mn
+        T += tg
+    lse = (M + np.log2(L)) * 0.6931471805599453
+    return float((lse - T).mean())

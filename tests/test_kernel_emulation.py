@@ -41,3 +41,42 @@ def test_peer_allreduce_emulation_equals_sum():
         for p in parts:                       # same fixed rank order -> identical bits
             ref = (ref + p).astype(np.float32)
         assert np.array_equal(got, ref)
+
+
+def test_dino_slice_records_and_merge_equal_the_reference_loss():
+    """Algorithmic identity behind dino_fwd_partial + dino_finish: per-slice log2-domain records with the
+    S-trick, merged over slices, reproduce DINOLoss.forward (oracle) for ragged K and any crop count."""
+    import numpy as np
+    import torch
+    from oracle import lafs_oracle as O
+    from tests.kernel_emulation import dino_sliced_loss
+    g = torch.Generator().manual_seed(0)
+    for B, K, nc, tt in ((3, 1000, 6, 0.04), (2, 256, 2, 0.07), (4, 777, 10, 0.05)):
+        s = torch.randn(nc * B, K, generator=g, dtype=torch.float64) * 3
+        t = torch.randn(2 * B, K, generator=g, dtype=torch.float64) * 3
+        c = torch.randn(1, K, generator=g, dtype=torch.float64) * 0.3
+        ref = O.dino_loss(s.float(), t.float(), c.float(), nc, tt)
+        loss, stats, colsum = dino_sliced_loss(s.float().numpy(), t.float().numpy(), c.float().numpy(), nc, 10.0, 1.0 / tt)
+        assert abs(loss - float(ref)) <= 2e-6 * abs(float(ref)), (loss, float(ref))
+        lse = torch.logsumexp(s.float().double() * 10.0, dim=1).view(nc, B).numpy()
+        assert np.allclose(stats[:nc] * np.log(2.0), lse, rtol=1e-10, atol=1e-9)
+        assert np.allclose(colsum, t.float().double().sum(0).numpy())
+
+
+def test_head_chunk_and_rank_merge_equal_cross_entropy():
+    """Online-softmax records per class chunk, merged per rank and then across class shards in rank order,
+    give CrossEntropyLoss(CosFace logits) for any shard count (torch.chunk ownership, ragged last shard)."""
+    import numpy as np
+    import torch
+    from oracle import lafs_oracle as O
+    from tests.kernel_emulation import head_sharded_loss
+    torch.manual_seed(1)
+    B, C, D = 9, 1003, 32
+    x, w = torch.randn(B, D), torch.randn(C, D)
+    lab = torch.randint(0, C, (B,))
+    lab[0], lab[1] = 0, C - 1
+    cos = torch.nn.functional.normalize(x) @ torch.nn.functional.normalize(w).t()
+    ref = float(O.cross_entropy(O.cosface_logits(x, w, lab), lab))
+    for world in (1, 2, 4, 8):
+        got = head_sharded_loss(cos.numpy(), lab.numpy(), 64.0, 0.4, world, chunk=100)
+        assert abs(got - ref) <= 1e-5 * abs(ref), (world, got, ref)
