@@ -50,17 +50,25 @@ constexpr int kGatherThreads = kGatherWarps * 32;
 constexpr int kWarpPlane = 0, kWarpW = 1, kWarpMma = 2, kWarpEpi0 = 4, kWarpGather0 = kWarpEpi0 + kEpiWarps;
 constexpr int kThreads = (kWarpGather0 + kGatherWarps) * 32;   // 20 warps
 
-template <typename InT>
+// DEEP (uint8 planes, views with few landmarks): ONE token tile and a 7-slot plane ring instead of two
+// token tiles and a 2-slot ring.  With 36-landmark views a work unit is 15 planes with little gather
+// work each, so the 2-slot ring (one 12.5 KB plane in flight) makes the unit a chain of load latencies;
+// six planes in flight cover it, at the price of not overlapping gather(g+1) with the UMMAs of g (the
+// epilogue of g still overlaps: the accumulators are double buffered in TMEM).
+template <typename InT, bool DEEP = false>
 struct Layout {
+  static_assert(!DEEP || sizeof(InT) == 1, "the deep plane ring is built for uint8 planes");
   static constexpr int kPlaneBytes = kH * kW * (int)sizeof(InT);          // 50,176 (fp32) / 12,544 (u8)
   static constexpr int kPlaneSlot = (kPlaneBytes + 1023) / 1024 * 1024;   // keeps later regions 1024-aligned
-  static constexpr int kTokBufs = sizeof(InT) == 1 ? 2 : 1;
+  static constexpr int kPlaneSlots = DEEP ? 7 : 2;
+  static constexpr int kTokBufs = (sizeof(InT) == 1 && !DEEP) ? 2 : 1;
   static constexpr int kOffPlanes = 0;
-  static constexpr int kOffTok = 2 * kPlaneSlot;
+  static constexpr int kOffTok = kPlaneSlots * kPlaneSlot;
   static constexpr int kOffW = kOffTok + kTokBufs * kTokTileBytes;
   static constexpr int kOffScratch = kOffW + kWStages * kWStageBytes;
   static constexpr int kOffBar = kOffScratch + kEpiWarps * kScratchBytes;
-  static constexpr int kSmemBytes = kOffBar + 256 + 1024;                 // + barriers + alignment slack
+  static constexpr int kBarBytes = DEEP ? 512 : 256;
+  static constexpr int kSmemBytes = kOffBar + kBarBytes + 1024;           // + barriers + alignment slack
   static_assert(kOffTok % 1024 == 0 && kOffW % 1024 == 0, "UMMA tiles need 1024-byte alignment");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
@@ -154,33 +162,35 @@ __device__ __forceinline__ void gather_plane(const InT* __restrict__ plane, uint
 }
 
 // DIM > 0: compile-time embedding width (store offsets become immediates); DIM == 0: runtime p.dim
-template <typename InT, typename OutT, int DIM>
+template <typename InT, typename OutT, int DIM, bool DEEP = false>
 __global__ void __launch_bounds__(pe::kThreads, 1)
 gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParams p) {
   using namespace pe;
-  using L = Layout<InT>;
+  using L = Layout<InT, DEEP>;
   constexpr int NTB = L::kTokBufs;
+  constexpr int NPS = L::kPlaneSlots;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* s_planes = smem + L::kOffPlanes;
   uint8_t* s_tok = smem + L::kOffTok;
   uint8_t* s_w = smem + L::kOffW;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
-  uint64_t* plane_full = bars;            // 2
-  uint64_t* plane_empty = bars + 2;       // 2
-  uint64_t* tok_full = bars + 4;          // NTB * 3
-  uint64_t* tok_empty = bars + 10;        // NTB
-  uint64_t* w_full = bars + 12;           // kWStages (<= 4)
-  uint64_t* w_empty = bars + 16;          // kWStages
-  uint64_t* acc_full = bars + 20;         // 2
-  uint64_t* acc_empty = bars + 22;        // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  uint64_t* plane_full = bars;                   // NPS
+  uint64_t* plane_empty = bars + NPS;            // NPS
+  uint64_t* tok_full = bars + 2 * NPS;           // NTB * 3 (room for 6)
+  uint64_t* tok_empty = bars + 2 * NPS + 6;      // NTB (room for 2)
+  uint64_t* w_full = bars + 2 * NPS + 8;         // kWStages (<= 4)
+  uint64_t* w_empty = bars + 2 * NPS + 12;       // kWStages
+  uint64_t* acc_full = bars + 2 * NPS + 16;      // 2
+  uint64_t* acc_empty = bars + 2 * NPS + 18;     // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NPS + 20);
+  static_assert((2 * NPS + 21) * 8 <= L::kBarBytes, "barrier region");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tmap_w);
-    for (int i = 0; i < 2; ++i) { mbar_init(plane_full + i, 1); mbar_init(plane_empty + i, kGatherWarps); }
+    for (int i = 0; i < NPS; ++i) { mbar_init(plane_full + i, 1); mbar_init(plane_empty + i, kGatherWarps); }
     for (int i = 0; i < NTB * 3; ++i) mbar_init(tok_full + i, kGatherWarps);
     for (int i = 0; i < NTB; ++i) mbar_init(tok_empty + i, 1);
     for (int i = 0; i < kWStages; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
@@ -218,8 +228,8 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
         for (int ff = 0; ff < nf; ++ff) {
           const int f = g * p.gfaces + ff;
           for (int c = 0; c < kC; ++c, ++cnt) {
-            const int slot = cnt & 1;
-            mbar_wait(plane_empty + slot, ((cnt >> 1) & 1) ^ 1);
+            const int slot = cnt % NPS;
+            mbar_wait(plane_empty + slot, ((cnt / NPS) & 1) ^ 1);
             mbar_arrive_expect_tx(plane_full + slot, L::kPlaneBytes);
             bulk_load(s_planes + slot * L::kPlaneSlot, imgs + ((size_t)f * kC + c) * (kH * kW), L::kPlaneBytes,
                       plane_full + slot);
@@ -357,8 +367,8 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
       const int row0 = ff * p.n;                           // first token row of this face inside the tile
       const float* th = p.theta + (size_t)f * p.n * 2;
       for (int c = 0; c < kC; ++c, ++pcnt) {
-        const int slot = pcnt & 1;
-        mbar_wait(plane_full + slot, (pcnt >> 1) & 1);
+        const int slot = pcnt % NPS;
+        mbar_wait(plane_full + slot, (pcnt / NPS) & 1);
         const InT* plane = reinterpret_cast<const InT*>(s_planes + slot * L::kPlaneSlot);
         uint8_t* tok = s_tok + tb * kTokTileBytes + c * kTokChunkBytes;
         // item = (token t, block h of JB output columns j): JB+1 pixel rows -> JB 16-byte stores.
@@ -396,13 +406,13 @@ __global__ void embed_weight_prep_kernel(const float* __restrict__ w, const floa
   out[idx] = __float2bfloat16_rn(w[(size_t)d * pe::kFeat + (i * 8 + j) * 3 + c]);
 }
 
-template <typename InT>
+template <typename InT, bool DEEP>
 static int launch_embed(const CUtensorMap& tw, const EmbedParams& p, int out_dtype, int dim, cudaStream_t st) {
   void (*kern)(const CUtensorMap, const EmbedParams);
-  if (out_dtype == LAFS_F32) kern = dim == 768 ? gather_embed_kernel<InT, float, 768> : gather_embed_kernel<InT, float, 0>;
-  else kern = dim == 768 ? gather_embed_kernel<InT, __nv_bfloat16, 768>
-            : dim == 384 ? gather_embed_kernel<InT, __nv_bfloat16, 384> : gather_embed_kernel<InT, __nv_bfloat16, 0>;
-  constexpr int smem = pe::Layout<InT>::kSmemBytes;
+  if (out_dtype == LAFS_F32) kern = dim == 768 ? gather_embed_kernel<InT, float, 768, DEEP> : gather_embed_kernel<InT, float, 0, DEEP>;
+  else kern = dim == 768 ? gather_embed_kernel<InT, __nv_bfloat16, 768, DEEP>
+            : dim == 384 ? gather_embed_kernel<InT, __nv_bfloat16, 384, DEEP> : gather_embed_kernel<InT, __nv_bfloat16, 0, DEEP>;
+  constexpr int smem = pe::Layout<InT, DEEP>::kSmemBytes;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   LAFS_REQUIRE(e == cudaSuccess, LAFS_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   const int grid = p.nunits < kNumSMs ? p.nunits : kNumSMs;
@@ -479,5 +489,12 @@ extern "C" int lafs_gather_embed_fwd(const void* imgs, int in_dtype, float in_sc
   else { p.in_scale = 1.f; p.in_shift = 0.f; p.pad_raw = 0.f; }
   if (const char* dbg = getenv("LAFS_PE_DEBUG")) p.debug = atoi(dbg);
   cudaStream_t st = (cudaStream_t)stream;
-  return in_dtype == LAFS_U8 ? launch_embed<uint8_t>(tw, p, out_dtype, dim, st) : launch_embed<float>(tw, p, out_dtype, dim, st);
+  // EXPERIMENTAL, not yet measured on hardware (opt-in): 7-slot plane ring + one token tile for uint8 views
+  // with few landmarks (see pe::Layout).  Default = the verified 2-slot / two-tile kernel.
+  if (in_dtype == LAFS_U8 && n <= 64) {
+    const char* deep = getenv("LAFS_PE_DEEP_RING");
+    if (deep && atoi(deep) != 0) return launch_embed<uint8_t, true>(tw, p, out_dtype, dim, st);
+  }
+  return in_dtype == LAFS_U8 ? launch_embed<uint8_t, false>(tw, p, out_dtype, dim, st)
+                             : launch_embed<float, false>(tw, p, out_dtype, dim, st);
 }

@@ -1,5 +1,7 @@
 """GPU parity: fused landmark gather -> patch embedding (tcgen05) against golden vectors and
 the oracle evaluated on bf16-rounded tokens / weights."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -123,3 +125,24 @@ def test_gather_embed_train_backward_vs_autograd(P, B, n, dim):
         assert err <= 2e-2, (name, float(err))
         cs = torch.nn.functional.cosine_similarity(got.cpu().flatten(), want.flatten(), dim=0)
         assert cs > 0.999, (name, float(cs))
+
+
+@pytest.mark.skipif(os.environ.get("LAFS_TEST_EXPERIMENTAL", "0") == "0",
+                    reason="experimental kernel variant, not yet verified on hardware (set LAFS_TEST_EXPERIMENTAL=1)")
+def test_deep_plane_ring_variant_is_bit_identical(P):
+    """LAFS_PE_DEEP_RING=1 (7-slot plane ring, one token tile; uint8 views with <= 64 landmarks) computes
+    exactly what the default kernel computes."""
+    torch.manual_seed(0)
+    B, n, dim = 333, 36, 768
+    u8 = torch.randint(0, 256, (B, 3, 112, 112), dtype=torch.uint8).cuda()
+    th = (torch.rand(B, n, 2) * 111 + torch.randn(B, n, 2) * 5).cuda()
+    lin = torch.nn.Linear(192, dim)
+    wts = P.PatchEmbedWeights([(lin.weight.detach().cuda(), lin.bias.detach().cuda())])
+    (ref,) = P.gather_embed(u8, th, wts)
+    os.environ["LAFS_PE_DEEP_RING"] = "1"
+    try:
+        (got,) = P.gather_embed(u8, th, wts)
+        torch.cuda.synchronize()
+    finally:
+        os.environ.pop("LAFS_PE_DEEP_RING", None)
+    assert torch.equal(got, ref)
