@@ -236,6 +236,20 @@ LAFS_API int lafs_embed_bwd_weight(const void* grad_emb_bf16, const void* tokens
 LAFS_API int lafs_embed_bwd_tokens(const void* grad_emb_bf16, const void* weight_bf16, int M, int dim,
                                    float* grad_tokens, lafs_stream_t stream);
 
+/* EXPERIMENTAL (written after the round's GPU budget was spent; compiled, not yet run on hardware; the Python
+ * wrappers use them only with LAFS_DW_DIAG=1): the F.normalize Jacobian of dW on the tensor core.
+ * lafs_head_grad_logits_t = lafs_head_grad_logits + per-class partial dots tpart[(mtile*4+quarter)*ldt + c]
+ * (sum over a 32-row group of G[b,c]*cos[b,c]; 4*ceil(B/128) rows, ldt a multiple of 32 >= C_local rounded up
+ * to 32, 128-byte aligned).  lafs_head_bwd_weight_t sums the rows (in place, row 0) to t[c] = <w_hat_c, dW_hat_c>
+ * and computes grad_w = inv_norm_w * (G^T.E_hat - diag(t).W_hat) in ONE GEMM (two extra k blocks per tile). */
+LAFS_API int lafs_head_grad_logits_t(const void* e_hat, const void* w_hat, const int64_t* label_a, const int64_t* label_b,
+                                     float lam, int B, int C_local, int D, int class_lo, float s, float m, int kind,
+                                     const float* row_lse2, const float* grad_out, float gscale, void* grad_bf16,
+                                     long long ldg, float* tpart, long long ldt, lafs_stream_t stream);
+LAFS_API int lafs_head_bwd_weight_t(const void* grad_bf16, long long ldg, const void* e_hat, const void* w_hat,
+                                    const float* inv_norm_w, float* tpart, int tparts, long long ldt, int B,
+                                    int C_local, int D, float* grad_w, lafs_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * (4e) Exchange steps of the class-sharded head over NVLink peer memory (one kernel each, instead of
  *      NCCL all_gather / all_reduce).  The reference has no counterpart (it replicates the head,

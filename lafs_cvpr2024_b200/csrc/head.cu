@@ -25,7 +25,7 @@ constexpr int kBM = 128;
 constexpr float kLog2eH = 1.4426950408889634f;
 constexpr float kLn2H = 0.6931471805599453f;
 
-enum : int { HEAD_STATS = 0, HEAD_LOGITS = 1, HEAD_GRAD = 2 };
+enum : int { HEAD_STATS = 0, HEAD_LOGITS = 1, HEAD_GRAD = 2, HEAD_GRAD_T = 3 };   // GRAD_T: GRAD + column dots (experimental)
 
 struct HeadParams {
   int B, C_local, D, class_lo;       // class_lo: global id of local class 0
@@ -47,6 +47,8 @@ struct HeadParams {
   int g256;                          // GRAD: rows are 32-byte aligned -> 256-bit stores
   float gscale;                      // s / B_global
   const float* grad_out;             // device scalar: upstream gradient of the loss
+  // GRAD_T reuses `part` (= tpart [mtiles*4][ldt]: partial column dots sum_b G[b,c]*cos[b,c]) and `ldc` (= ldt),
+  // so that the parameter block -- and with it the code of the measured kernels -- stays exactly as it was
 };
 
 // margin-adjusted cosine (logit / s) of a class whose target weight is t (0 < t <= 1)
@@ -200,7 +202,7 @@ head_gemm_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
     float m_run = -INFINITY, l_run = 0.f, tgt_a = 0.f, tgt_b = 0.f;
     float lse2 = 0.f;
     float gscale = 0.f;
-    if (MODE == HEAD_GRAD && row_ok) { lse2 = p.row_lse2[b]; gscale = p.gscale * __ldg(p.grad_out); }
+    if ((MODE == HEAD_GRAD || MODE == HEAD_GRAD_T) && row_ok) { lse2 = p.row_lse2[b]; gscale = p.gscale * __ldg(p.grad_out); }
     const uint32_t acc_empty_remote = (PAIR && !leader) ? mapa_shared(smem_u32(acc_empty), 0) : 0u;
     int it = 0;
     for (int chunk = range; chunk < p.nchunks; chunk += p.nranges, ++it) {
@@ -260,6 +262,59 @@ head_gemm_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
                 if (cbase + j < p.C_local) dst[j] = p.s * c[j];
             }
           }
+        } else if (MODE == HEAD_GRAD_T) {
+          // HEAD_GRAD plus t[c] = sum_b G[b,c] * cos[b,c] (= <w_hat_c, dW_hat_c>) for the F.normalize Jacobian of
+          // dW: each warp reduces its 32 rows per column with a transposing butterfly (lane L ends with
+          // column L) and stores one coalesced 128-byte partial per piece; rows past B carry gscale = 0.
+          float gv[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) gv[j] = ex2(fmaf(c[j], sk2, -lse2));
+          if (has_a || has_b) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int cc = cbase + j;
+              if (has_a && cc == (int)la) gv[j] = (gv[j] - ta) * margin_dcos(__uint_as_float(raw[j]), p);
+              if (has_b && cc == (int)lb) gv[j] -= tb;
+            }
+          }
+          uint32_t pk32[16];
+          float pr[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            pk32[j >> 1] = Half2Ops<__nv_bfloat16>::pack(gv[j] * gscale, gv[j + 1] * gscale);
+            // the bf16 values the dW GEMM will consume, times the raw cosine
+            pr[j] = Half2Ops<__nv_bfloat16>::lo(pk32[j >> 1]) * __uint_as_float(raw[j]);
+            pr[j + 1] = Half2Ops<__nv_bfloat16>::hi(pk32[j >> 1]) * __uint_as_float(raw[j + 1]);
+          }
+          if (row_ok) {
+            __nv_bfloat16* dst = p.grad + (long long)b * p.ldg + cbase;
+            if (!tail) {
+              if (p.g256) {
+                st_global_256(dst, make_uint4(pk32[0], pk32[1], pk32[2], pk32[3]), make_uint4(pk32[4], pk32[5], pk32[6], pk32[7]));
+                st_global_256(dst + 16, make_uint4(pk32[8], pk32[9], pk32[10], pk32[11]),
+                              make_uint4(pk32[12], pk32[13], pk32[14], pk32[15]));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  *reinterpret_cast<uint4*>(dst + 8 * j) = make_uint4(pk32[4 * j], pk32[4 * j + 1], pk32[4 * j + 2], pk32[4 * j + 3]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (cbase + j < p.C_local) dst[j] = __float2bfloat16_rn(gv[j] * gscale);
+            }
+          }
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1) {
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int i = 0; i < o; ++i) {
+              const float send = up ? pr[i] : pr[i + o];
+              const float keep = up ? pr[i + o] : pr[i];
+              pr[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+          }
+          p.part[(size_t)(mt * 4 + quarter) * (size_t)p.ldc + cbase + lane] = pr[0];   // part = tpart, ldc = ldt >= round32(C_local)
         } else {  // HEAD_GRAD: (softmax - target) * dz/dcos * gscale, bf16; 64 contiguous bytes per row
           if (row_ok) {
             float gv[32];
@@ -666,4 +721,26 @@ extern "C" int lafs_head_grad_logits(const void* e_hat, const void* w_hat, const
   p.g256 = (ldg % 16 == 0 && ((uintptr_t)grad_bf16 & 31u) == 0) ? 1 : 0;
   cudaStream_t st = (cudaStream_t)stream;
   return launch_head_any<HEAD_GRAD>(te, tw, p, hl, st);
+}
+
+/* EXPERIMENTAL (not yet measured on hardware): lafs_head_grad_logits plus the per-class partial dots
+ * tpart[(mtile*4 + quarter)*ldt + c] = sum over that 32-row group of G[b,c]*cos[b,c]; summing the
+ * 4*ceil(B/128) partials of a class gives <w_hat_c, dW_hat_c>, which lafs_head_bwd_weight_t turns into the
+ * F.normalize Jacobian on the tensor core.  ldt >= C_local rounded up to 32; tpart is fully overwritten for
+ * classes < round32(C_local). */
+extern "C" int lafs_head_grad_logits_t(const void* e_hat, const void* w_hat, const int64_t* label_a, const int64_t* label_b,
+                                       float lam, int B, int C_local, int D, int class_lo, float s, float m, int kind,
+                                       const float* row_lse2, const float* grad_out, float gscale, void* grad_bf16,
+                                       long long ldg, float* tpart, long long ldt, lafs_stream_t stream) {
+  if (int brc = lafs::bind_device_of(e_hat)) return brc;
+  HeadParams p; HeadLaunch hl; CUtensorMap te, tw;
+  int rc = head_common<HEAD_GRAD_T>(e_hat, w_hat, label_a, label_b, lam, B, C_local, D, class_lo, s, m, kind, &p, &hl, &te, &tw, "lafs_head_grad_logits_t");
+  if (rc) return rc;
+  LAFS_REQUIRE(row_lse2 && grad_out && grad_bf16 && ldg >= C_local, LAFS_ERR_ARG, "lafs_head_grad_logits_t: bad argument");
+  LAFS_REQUIRE(tpart && ldt >= ((C_local + 31) / 32) * 32 && ((uintptr_t)tpart & 127u) == 0 && ldt % 32 == 0, LAFS_ERR_ARG,
+               "lafs_head_grad_logits_t: tpart must be 128-byte aligned with ldt a multiple of 32 >= round32(C_local)");
+  p.row_lse2 = row_lse2; p.grad = (__nv_bfloat16*)grad_bf16; p.ldg = ldg; p.gscale = gscale; p.grad_out = grad_out;
+  p.g256 = (ldg % 16 == 0 && ((uintptr_t)grad_bf16 & 31u) == 0) ? 1 : 0;
+  p.part = tpart; p.ldc = ldt;
+  return launch_head_any<HEAD_GRAD_T>(te, tw, p, hl, (cudaStream_t)stream);
 }

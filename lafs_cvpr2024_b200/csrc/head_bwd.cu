@@ -511,6 +511,200 @@ static int launch_dw_fused(const CUtensorMap& ta, const CUtensorMap& tb, DwParam
   return check_launch("lafs_head_bwd_weight(fused)");
 }
 
+// ---- EXPERIMENTAL (not yet measured on hardware): dW with the Jacobian's rank-one term on the tensor core ----
+//   grad_w[c,:] = inv_norm_w[c] * ( dW_hat[c,:] - t[c] * w_hat[c,:] ),   t[c] = <w_hat[c,:], dW_hat[c,:]> = sum_b G[b,c]*cos[b,c]
+// t comes from the gradient kernel (HEAD_GRAD_T partials).  Per 128-class tile the correction is the product
+// (-diag(t)) [128 x 128] . W_hat_tile [128 x D]: two extra k blocks of the same GEMM, whose A operand (a
+// diagonal matrix, bf16) is written into the stage by the producer warp in the MN-major / 128-byte-swizzle
+// layout TMA would produce, and whose B operand is the W_hat tile itself, fetched by TMA like E_hat.  The
+// epilogue only scales each row by inv_norm_w: no second pass over dW, no lane-per-row loads of w_hat.
+// (fp32 emulation: 6e-4 max-norm relative error on dW from rounding t to bf16.)
+struct DiagParams {
+  const float* t;           // [M] = sum of the gradient kernel's partial rows (t_reduce_kernel)
+  const float* inv_norm;    // [M]
+};
+
+// t[c] = sum_q tpart[q][c], in place into row 0 (a thread owns a column: no hazard)
+__global__ void t_reduce_kernel(float* __restrict__ tpart, int tparts, long long ldt, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float acc = 0.f;
+  for (int q = 0; q < tparts; ++q) acc += tpart[(size_t)q * ldt + c];
+  tpart[c] = acc;
+}
+
+__global__ void __launch_bounds__(gb::kThreads, 1)
+dw_diag_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_w, const GemmParams p, const DiagParams dp) {
+  using namespace gb;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* s_a = smem;
+  uint8_t* s_b = smem + kStages * kStageA;
+  float* s_out = reinterpret_cast<float*>(s_b + kStages * kStageB);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_b + kStages * kStageB + kStageOut);
+  uint64_t* full = bars;                 // kStages
+  uint64_t* empty = bars + kStages;      // kStages
+  uint64_t* acc_full = bars + 2 * kStages;      // 2
+  uint64_t* acc_empty = acc_full + 2;           // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmap_a);
+    prefetch_tensormap(&tmap_b);
+    prefetch_tensormap(&tmap_w);
+    for (int i = 0; i < kStages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * kBN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int nkb = p.kblocks_total;            // batch k blocks; + 2 diagonal blocks per tile
+
+  if (warp == 0) {
+    uint32_t cnt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+      // this lane's four diagonal entries (classes lane, lane+32 of either 64-class half), fetched before the
+      // batch blocks so that their latency is hidden behind them
+      float tv[2][2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int cls = mt * kBM + e * 64 + lane + 32 * h;
+          tv[e][h] = cls < p.M ? __ldg(dp.t + cls) : 0.f;
+        }
+      if (lane == 0) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          const uint32_t c = cnt + (uint32_t)kb;
+          const int st = c % kStages;
+          mbar_wait(empty + st, ((c / kStages) & 1) ^ 1);
+          mbar_arrive_expect_tx(full + st, kStageA + kStageB);
+          uint8_t* da = s_a + st * kStageA;
+          uint8_t* db = s_b + st * kStageB;
+          tma_load_2d(da, &tmap_a, full + st, mt * kBM, kb * kBK);             // G^T: {64 classes, 64 batch rows}
+          tma_load_2d(da + 8192, &tmap_a, full + st, mt * kBM + 64, kb * kBK);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) tma_load_2d(db + q * 8192, &tmap_b, full + st, nt * kBN + q * 64, kb * kBK);
+        }
+      }
+      cnt += (uint32_t)nkb;
+      __syncwarp();
+      // two diagonal blocks: K index = class within the tile, e*64 .. e*64+63
+      for (int e = 0; e < 2; ++e, ++cnt) {
+        const int st = cnt % kStages;
+        mbar_wait(empty + st, ((cnt / kStages) & 1) ^ 1);      // every lane waits: all of them write the stage
+        uint8_t* da = s_a + st * kStageA;
+        uint8_t* db = s_b + st * kStageB;
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = lane; i < kStageA / 16; i += 32) reinterpret_cast<uint4*>(da)[i] = z;
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int kk = lane + 32 * h;                          // row k = kk of the block, column m' = kk of box e
+          const uint32_t off = (uint32_t)(e * 8192 + kk * 128 + ((((kk >> 3) ^ (kk & 7)) & 7) << 4) + (kk & 7) * 2);
+          *reinterpret_cast<__nv_bfloat16*>(da + off) = __float2bfloat16_rn(-(e == 0 ? tv[0][h] : tv[1][h]));
+        }
+        fence_proxy_async_smem();        // generic-proxy writes -> visible to the UMMA operand reads
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive_expect_tx(full + st, kStageB);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)    // W_hat tile rows as the B operand: {64 d, 64 classes}
+            tma_load_2d(db + q * 8192, &tmap_w, full + st, nt * kBN + q * 64, mt * kBM + e * 64);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBM, kBN, 1, 1);
+      uint32_t cnt = 0, acnt = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acnt) {
+        const int buf = acnt & 1;
+        mbar_wait(acc_empty + buf, ((acnt >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kBN);
+        for (int kb = 0; kb < nkb + 2; ++kb, ++cnt) {
+          const int st = cnt % kStages;
+          mbar_wait(full + st, (cnt / kStages) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(s_a + st * kStageA);
+          const uint32_t b_addr = smem_u32(s_b + st * kStageB);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t da = make_desc_mn_sw128(a_addr + kk * 2048, 8192);
+            const uint64_t db = make_desc_mn_sw128(b_addr + kk * 2048, 8192);
+            mma_f16_ss(d_tmem, da, db, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+          }
+          mma_commit(empty + st);
+        }
+        mma_commit(acc_full + buf);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    uint32_t acnt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acnt) {
+      const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+      const int buf = acnt & 1;
+      const int row_base = mt * kBM + quarter * 32;
+      const float inv = row_base + lane < p.M ? __ldg(dp.inv_norm + row_base + lane) : 0.f;
+      mbar_wait(acc_full + buf, (acnt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(buf * kBN) + ((uint32_t)(quarter * 32) << 16);
+      float* stage = s_out + quarter * (32 * kPitch);
+      float* dst0 = p.out + (size_t)nt * kBN;
+#pragma unroll 1
+      for (int piece = 0; piece < kBN / 32; ++piece) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + (uint32_t)(piece * 32), v);
+        tmem_ld_wait();
+        const int c0 = nt * kBN + piece * 32;
+        if (c0 >= p.N) break;                       // warp-uniform
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(stage + lane * kPitch + j) =
+              make_float4(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv, __uint_as_float(v[j + 2]) * inv,
+                          __uint_as_float(v[j + 3]) * inv);
+        __syncwarp();
+#pragma unroll
+        for (int r8 = 0; r8 < 8; ++r8) {
+          const int rr = r8 * 4 + (lane >> 3), part = lane & 7;       // 8 lanes cover one 128-byte row segment
+          const float4 val = *reinterpret_cast<const float4*>(stage + rr * kPitch + part * 4);
+          const int grow = row_base + rr, gcol = c0 + part * 4;
+          if (grow < p.M) {
+            float* d = dst0 + (size_t)grow * p.ldo + piece * 32 + part * 4;
+            if (gcol + 4 <= p.N) *reinterpret_cast<float4*>(d) = val;
+            else {
+              if (gcol < p.N) d[0] = val.x;
+              if (gcol + 1 < p.N) d[1] = val.y;
+              if (gcol + 2 < p.N) d[2] = val.z;
+            }
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_relaxed(acc_empty + buf);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * kBN);
+  }
+}
+
 // out[r, :] = (g[r, :] - x_hat[r, :] * <x_hat[r, :], g[r, :]>) * inv_norm[r]   (F.normalize backward)
 // one warp per row, 128-bit accesses, all loads of a row issued before the reduction.
 // D % 64 == 0, D <= 768: a lane holds up to three (float4 x 2) groups.  out may alias g.
@@ -860,4 +1054,37 @@ extern "C" int lafs_embed_bwd_tokens(const void* grad_emb_bf16, const void* weig
   p.kblocks_total = (dim + 63) / 64; p.kblocks_per_split = p.kblocks_total;
   p.out = grad_tokens; p.ldo = 192; p.split_stride = 0;
   return launch_gemm<false>(ta, tb, p, (cudaStream_t)stream);
+}
+
+/* EXPERIMENTAL (not yet measured on hardware): lafs_head_bwd_weight with the Jacobian's rank-one term computed on
+ * the tensor core from the per-class dots of lafs_head_grad_logits_t (tpart [tparts][ldt], tparts = 4*ceil(B/128)):
+ * one GEMM, no normalize_bwd pass. */
+extern "C" int lafs_head_bwd_weight_t(const void* grad_bf16, long long ldg, const void* e_hat, const void* w_hat,
+                                      const float* inv_norm_w, float* tpart, int tparts, long long ldt, int B,
+                                      int C_local, int D, float* grad_w, lafs_stream_t stream) {
+  if (int brc = lafs::bind_device_of(grad_bf16)) return brc;
+  LAFS_REQUIRE(grad_bf16 && e_hat && w_hat && inv_norm_w && tpart && grad_w, LAFS_ERR_ARG, "lafs_head_bwd_weight_t: null pointer");
+  LAFS_REQUIRE(B > 0 && C_local > 0 && D > 0 && D % 64 == 0 && D <= 768, LAFS_ERR_ARG, "lafs_head_bwd_weight_t: B=%d C=%d D=%d", B, C_local, D);
+  LAFS_REQUIRE(ldg % 8 == 0 && ldg >= C_local, LAFS_ERR_ARG, "lafs_head_bwd_weight_t: ldg=%lld must be a multiple of 8 and >= C_local", ldg);
+  LAFS_REQUIRE(tparts > 0 && ldt >= C_local, LAFS_ERR_ARG, "lafs_head_bwd_weight_t: tparts=%d ldt=%lld", tparts, ldt);
+  CUtensorMap ta, tb, tw;
+  int rc = encode_bf16_2d(&ta, grad_bf16, (uint64_t)B, (uint64_t)C_local, (uint64_t)ldg * 2, 64, 64);  // MN-major A: [K=B, M=C]
+  if (rc) return rc;
+  rc = encode_bf16_2d(&tb, e_hat, (uint64_t)B, (uint64_t)D, (uint64_t)D * 2, 64, 64);                  // MN-major B: [K=B, N=D]
+  if (rc) return rc;
+  rc = encode_bf16_2d(&tw, w_hat, (uint64_t)C_local, (uint64_t)D, (uint64_t)D * 2, 64, 64);            // MN-major B: [K=classes, N=D]
+  if (rc) return rc;
+  GemmParams p{};
+  p.M = C_local; p.N = D; p.K = B;
+  p.m_tiles = (C_local + 127) / 128; p.n_tiles = (D + 255) / 256; p.splits = 1;
+  p.kblocks_total = (B + 63) / 64; p.kblocks_per_split = p.kblocks_total;
+  p.out = grad_w; p.ldo = D; p.split_stride = 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  t_reduce_kernel<<<(C_local + 255) / 256, 256, 0, st>>>(tpart, tparts, ldt, C_local);   // row 0 <- sum of the rows
+  DiagParams dp{tpart, inv_norm_w};
+  cudaError_t e = cudaFuncSetAttribute(dw_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gb::kSmem);
+  LAFS_REQUIRE(e == cudaSuccess, LAFS_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  const int total = p.m_tiles * p.n_tiles;
+  dw_diag_kernel<<<total < kNumSMs ? total : kNumSMs, gb::kThreads, gb::kSmem, st>>>(ta, tb, tw, p, dp);
+  return check_launch("lafs_head_bwd_weight_t");
 }

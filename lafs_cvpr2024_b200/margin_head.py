@@ -67,7 +67,14 @@ def _round8(n):
     return (n + 15) // 16 * 16
 
 
-def _head_backward(G, ldg, e_hat, w_hat, inv_e, inv_w, B, C, D, sharded, xchg=None):
+def _dw_diag_enabled(D):
+    """EXPERIMENTAL switch (LAFS_DW_DIAG=1): Jacobian of dW on the tensor core (lafs_head_grad_logits_t +
+    lafs_head_bwd_weight_t).  Off by default: written after the round's GPU budget was spent."""
+    import os
+    return os.environ.get("LAFS_DW_DIAG", "0") not in ("", "0") and D % 64 == 0
+
+
+def _head_backward(G, ldg, e_hat, w_hat, inv_e, inv_w, B, C, D, sharded, xchg=None, tpart=None):
     """dE [B,D], dW [C,D] (fp32) from the bf16 logit gradient G [B, ldg] via two tcgen05 GEMMs."""
     dev = e_hat.device
     nbytes = _lib.lib().lafs_head_bwd_workspace_bytes(B, C, D)
@@ -83,8 +90,12 @@ def _head_backward(G, ldg, e_hat, w_hat, inv_e, inv_w, B, C, D, sharded, xchg=No
     _lib.call("lafs_normalize_bwd", de_hat.data_ptr(), e_hat.data_ptr(), inv_e.data_ptr(), B, D, de.data_ptr(),
               _lib.stream())
     dw = torch.empty(C, D, dtype=torch.float32, device=dev)
-    _lib.call("lafs_head_bwd_weight", G.data_ptr(), ldg, e_hat.data_ptr(), w_hat.data_ptr(), inv_w.data_ptr(),
-              B, C, D, dw.data_ptr(), _lib.stream())
+    if tpart is not None:
+        _lib.call("lafs_head_bwd_weight_t", G.data_ptr(), ldg, e_hat.data_ptr(), w_hat.data_ptr(), inv_w.data_ptr(),
+                  tpart.data_ptr(), tpart.shape[0], tpart.shape[1], B, C, D, dw.data_ptr(), _lib.stream())
+    else:
+        _lib.call("lafs_head_bwd_weight", G.data_ptr(), ldg, e_hat.data_ptr(), w_hat.data_ptr(), inv_w.data_ptr(),
+                  B, C, D, dw.data_ptr(), _lib.stream())
     return de, dw
 
 
@@ -135,10 +146,18 @@ class _HeadLossFn(torch.autograd.Function):
         ldg = _round8(C)
         G = torch.empty(B, ldg, dtype=torch.bfloat16, device=e_hat.device)
         g = grad_loss.detach().float().contiguous()
-        _lib.call("lafs_head_grad_logits", e_hat.data_ptr(), w_hat.data_ptr(), la.data_ptr(),
-                  lb.data_ptr() if has_b else None, lam, B, C, D, class_lo, s, m, kind, lse2.data_ptr(),
-                  g.data_ptr(), s / B, G.data_ptr(), ldg, _lib.stream())
-        de, dw = _head_backward(G, ldg, e_hat, w_hat, inv_e, inv_w, B, C, D, sharded, ctx.xchg)
+        tpart = None
+        if _dw_diag_enabled(D):
+            ldt = (C + 31) // 32 * 32
+            tpart = torch.empty(4 * ((B + 127) // 128), ldt, dtype=torch.float32, device=e_hat.device)
+            _lib.call("lafs_head_grad_logits_t", e_hat.data_ptr(), w_hat.data_ptr(), la.data_ptr(),
+                      lb.data_ptr() if has_b else None, lam, B, C, D, class_lo, s, m, kind, lse2.data_ptr(),
+                      g.data_ptr(), s / B, G.data_ptr(), ldg, tpart.data_ptr(), ldt, _lib.stream())
+        else:
+            _lib.call("lafs_head_grad_logits", e_hat.data_ptr(), w_hat.data_ptr(), la.data_ptr(),
+                      lb.data_ptr() if has_b else None, lam, B, C, D, class_lo, s, m, kind, lse2.data_ptr(),
+                      g.data_ptr(), s / B, G.data_ptr(), ldg, _lib.stream())
+        de, dw = _head_backward(G, ldg, e_hat, w_hat, inv_e, inv_w, B, C, D, sharded, ctx.xchg, tpart)
         return de.to(in_dtype), dw, None, None, None, None
 
 

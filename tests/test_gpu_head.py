@@ -227,3 +227,17 @@ def test_head_kernel_variants_agree(P, B, C, D, kind):
         assert (out[3] - base[3]).abs().max() <= 1e-4, (env, float((out[3] - base[3]).abs().max()))
         for a, b in ((out[1], base[1]), (out[2], base[2])):
             assert (a - b).abs().max() <= 2e-3 * b.abs().max() + 1e-9, (env, float((a - b).abs().max() / b.abs().max()))
+
+
+@pytest.mark.skipif(__import__("os").environ.get("LAFS_TEST_EXPERIMENTAL", "0") == "0",
+                    reason="experimental kernel variant, not yet verified on hardware (set LAFS_TEST_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("B,C,D", [(512, 9001, 512), (130, 3000, 128), (300, 4099, 256), (64, 1000, 768)])
+@pytest.mark.parametrize("kind", ["cosface", "arcface"])
+def test_dw_jacobian_on_tensor_core_variant(P, B, C, D, kind):
+    """LAFS_DW_DIAG=1: per-class dots from the gradient kernel + dW = inv * (G^T.E - diag(t).W_hat) in one GEMM,
+    against GEMM + normalize_bwd (t is rounded to bf16: ~6e-4 max-norm relative on dW)."""
+    base = _step_outputs(P, B, C, D, kind, {"LAFS_DW_DIAG": "0"})
+    out = _step_outputs(P, B, C, D, kind, {"LAFS_DW_DIAG": "1"})
+    assert abs(out[0] - base[0]) <= 1e-6 * abs(base[0])
+    assert (out[1] - base[1]).abs().max() <= 1e-5 * base[1].abs().max()            # dE: untouched path
+    assert (out[2] - base[2]).abs().max() <= 5e-3 * base[2].abs().max(), float((out[2] - base[2]).abs().max() / base[2].abs().max())
