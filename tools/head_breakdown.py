@@ -121,8 +121,11 @@ def main():
             for a in env:
                 os.environ.pop(a, None)
 
-    for env in ({}, {"LAFS_HEAD_1SM": "1"}, {"LAFS_DE_CLUSTER": "1"}, {"LAFS_DW_FUSED": "1"},
-                {"LAFS_DW_FUSED": "1", "LAFS_DW_CLUSTER": "2"}):
+    envs = [{}, {"LAFS_HEAD_1SM": "1"}, {"LAFS_DE_CLUSTER": "1"}, {"LAFS_DW_FUSED": "1"},
+            {"LAFS_DW_FUSED": "1", "LAFS_DW_CLUSTER": "2"}]
+    if os.environ.get("LAFS_TEST_EXPERIMENTAL", "0") != "0":
+        envs.append({"LAFS_DW_DIAG": "1"})        # experimental: Jacobian of dW on the tensor core
+    for env in envs:
         tag = "step_graph[" + ",".join(f"{a[5:]}={b}" for a, b in env.items()) + "]_us"
         res[tag] = graph_us(env)
     print(json.dumps(res))
