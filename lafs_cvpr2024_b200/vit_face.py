@@ -137,6 +137,36 @@ def _tokens_and_embedding(imgs, theta, linear, training_path):
     return emb.to(linear.weight.dtype)
 
 
+def image_grid_tokens(x, p):
+    """einops 'b c (h p1) (w p2) -> b (h w) (p1 p2 c)' (ViT_face.py:759) for image input without landmarks."""
+    b, c, H, W = x.shape
+    return x.reshape(b, c, H // p, p, W // p, p).permute(0, 2, 4, 3, 5, 1).reshape(b, (H // p) * (W // p), p * p * c)
+
+
+def standard_grid_tokens(x, num_land, random_prob, shuffle, extract_mosaic):
+    """`use_standcoord=True` of the reference (ViT_face.py:717-746): patches at the fixed grid centres
+    4, 12, ..., (+ randn*3 with Random_prob, re-sampled with replacement with shuffle; both drawn on the CPU
+    default generator in the reference's order), the mosaic transposed (`x.permute(0,1,3,2)`, :746) and
+    re-laid-out as '(h w) (p1 p2 c)' tokens (:759).  `extract_mosaic(imgs, theta)` is the patch extractor
+    (the sm_100a gather kernel in the product; the tests pass the oracle's to check this composition on CPU
+    against the reference).  Returns (theta [b,n,2], tokens [b,n,192])."""
+    b = x.shape[0]
+    rc = torch.arange(0, math.sqrt(num_land)) * 8 + 4              # float32, like the reference's torch.arange(0, np.sqrt(n))
+    cx, cy = torch.meshgrid(rc, rc, indexing="ij")
+    theta = torch.stack((cx, cy), 2).view(1, -1, 2).repeat(b, 1, 1).to(x.device)
+    n = theta.shape[1]
+    if random_prob:
+        theta = theta + (torch.randn(theta.shape) * 3).to(x.device)
+    if shuffle:
+        idx = torch.randint(0, n, (b, n, 1)).to(x.device).repeat(1, 1, 2)
+        theta = torch.gather(theta, 1, idx)
+    theta = theta[:, :num_land]
+    m = extract_mosaic(x, theta).permute(0, 1, 3, 2)                # [b, c, 8r, 8r], height and width swapped
+    c, r = m.shape[1], m.shape[2] // 8
+    tokens = m.reshape(b, c, r, 8, r, 8).permute(0, 2, 4, 3, 5, 1).reshape(b, r * r, 64 * c)
+    return theta, tokens
+
+
 class ViT_face_landmark_patch8(nn.Module):
     def __init__(self, *, loss_type, GPU_ID, num_class, image_size, patch_size, dim, depth, heads, mlp_dim,
                  pool='cls', num_patches=None, channels=3, dim_head=64, dropout=0., emb_dropout=0., fp16=True,
@@ -149,8 +179,10 @@ class ViT_face_landmark_patch8(nn.Module):
         assert pool in {'cls', 'mean'}, 'pool type must be either cls (cls token) or mean (mean pooling)'
         if patch_size != 8:
             raise ValueError("the sm_100a gather kernels implement the reference's 8x8 patches")
-        if use_standcoord:
-            raise NotImplementedError("use_standcoord (fixed grid, unused by LAFS pretrain/finetune) is not built")
+        if use_standcoord and with_land:
+            raise NotImplementedError("with_land and use_standcoord together (the reference would re-extract patches "
+                                      "from the landmark mosaic) is not built")
+        self.use_standcoord = use_standcoord
         self.patch_size = patch_size
         self.fp16 = fp16
         self.num_patches = num_patches
@@ -188,15 +220,32 @@ class ViT_face_landmark_patch8(nn.Module):
         self.theta = theta
         return theta
 
+    def _num_land(self, x):
+        """ViT_face.py:663-677: (H/p)^2 landmarks, except the 144-patch model on 112-pixel faces."""
+        if self.num_patches == 144 and x.shape[-2] == 112:
+            return self.num_patches
+        return (x.shape[-2] // self.patch_size) ** 2
+
     def forward(self, x, label=None, mask=None, visualize=False, save_token=False, opt=None, keep_num=None,
                 glo_diff=False):
         theta = None
-        if x.dim() == 4:
-            if not self.with_land:
-                raise ValueError("4-D image input needs with_land=True (token input is 3-D [B, n, 192])")
+        if x.dim() == 4 and not self.with_land:
+            # images without the landmark CNN (ViT_face.py:717-761): fixed-grid patches (use_standcoord) or the
+            # plain ViT patch grid; stock PyTorch re-layout around the gather kernel
+            num_land = self._num_land(x)
+            if self.use_standcoord:
+                _lib.require_cuda(x)
+                from .patches import extract_patches_pytorch_gridsample
+                theta, tok = standard_grid_tokens(
+                    x.float(), num_land, self.Random_prob, self.shuffle,
+                    lambda im, th: extract_patches_pytorch_gridsample(im, th, self.patch_shape, th.shape[1]))
+            else:
+                tok = image_grid_tokens(x, self.patch_size)
+            x = self.patch_to_embedding(tok.to(self.patch_to_embedding.weight.dtype))
+        elif x.dim() == 4:
             _lib.require_cuda(x)
             theta = self.landmarks(x.float())
-            num_land = (x.shape[-2] // self.patch_size) ** 2
+            num_land = self._num_land(x)
             need_grad = torch.is_grad_enabled() and (theta.requires_grad or x.requires_grad
                                                      or self.patch_to_embedding.weight.requires_grad)
             x = _tokens_and_embedding(x.float(), theta[:, :num_land], self.patch_to_embedding, need_grad)

@@ -110,3 +110,40 @@ def test_landmark_trunk_matches_reference(ref):
     w = m2.features[0][0].weight
     assert abs(float(w.std()) - (2.0 / (16 * 9)) ** 0.5) < 0.03
     assert float(m2.features[1].conv[1].weight.min()) == 1.0 and float(m2.features[1].conv[1].bias.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("random_prob,shuffle", [(False, False), (True, False), (True, True)])
+def test_standard_grid_and_plain_grid_paths_match_reference(ref, random_prob, shuffle):
+    """ViT_face_landmark_patch8 on image input without the landmark CNN: `use_standcoord` (fixed-grid patches,
+    optional jitter / re-sampling drawn on the CPU generator in the reference's order, transposed mosaic) and the
+    plain ViT patch grid.  The wrapper's re-layout logic is run here on CPU with the ORACLE's patch extractor in
+    place of the gather kernel and compared with the unmodified reference module (same weights, same seed)."""
+    import contextlib
+    import io
+    from oracle import lafs_oracle as O
+    from lafs_cvpr2024_b200 import vit_face as V
+    kw = dict(loss_type="None", GPU_ID=None, num_class=0, image_size=112, patch_size=8, dim=32, depth=1, heads=2,
+              mlp_dim=48, num_patches=196)
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        r = ref.VF.ViT_face_landmark_patch8(use_standcoord=True, Random_prob=random_prob, shuffle=shuffle, **kw).eval()
+        m = V.ViT_face_landmark_patch8(use_standcoord=True, Random_prob=random_prob, shuffle=shuffle, **kw).eval()
+    m.load_state_dict(r.state_dict(), strict=True)
+    x = torch.rand(3, 3, 112, 112) * 2 - 1
+    torch.manual_seed(5)
+    with torch.no_grad():
+        want = r(x)
+    # the wrapper's composition with the oracle extractor (the product path substitutes the CUDA gather kernel)
+    torch.manual_seed(5)
+    theta, tok = V.standard_grid_tokens(x, 196, random_prob, shuffle, lambda im, th: O.extract_patches(im, th, th.shape[1]))
+    with torch.no_grad():
+        emb = m(tok)                                   # 3-D token input: patch_to_embedding + transformer
+    assert theta.shape == (3, 196, 2)
+    torch.testing.assert_close(emb, want, rtol=1e-5, atol=1e-6)
+    # plain grid (no landmarks, no standard coordinates): pure PyTorch, runs on CPU through the wrapper itself
+    with contextlib.redirect_stdout(io.StringIO()):
+        r2 = ref.VF.ViT_face_landmark_patch8(**kw).eval()
+        m2 = V.ViT_face_landmark_patch8(**kw).eval()
+    m2.load_state_dict(r2.state_dict(), strict=True)
+    with torch.no_grad():
+        torch.testing.assert_close(m2(x), r2(x), rtol=1e-5, atol=1e-6)
