@@ -1,0 +1,45 @@
+"""CPU: the JSON line of `bench.py --impl reference` (the only arm that runs without a GPU) carries the keys
+the driver reads, and the committed round profiles of our arm do too."""
+import glob
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "e2e", "cpu_baseline"}
+
+
+def test_reference_arm_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0", "--cpu-faces", "4"], capture_output=True, text=True, timeout=600,
+                       env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1                                    # exactly one line on stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and BASE_KEYS <= set(d)
+    assert d["metric"] == "lafs_ssl_hot_path_faces_per_sec" and d["unit"] == "faces/s" and d["higher_is_better"] is True
+    assert d["vs_baseline"] is None and "workload" in d["config"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+
+
+def test_committed_profiles_of_our_arm_follow_the_contract():
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_bench_n*.json")))
+    assert files
+    for f in files:
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+        assert (BASE_KEYS - {"cpu_baseline"}) <= set(d), (f, BASE_KEYS - set(d))
+        assert d["metric"] == "lafs_ssl_hot_path_faces_per_sec" and d["scaling"] == "weak" and d["data"] == "synthetic"
+        assert d["n_gpus"] >= 1 and d["warmup"] >= 3 and d["gpu_launches"] > 0
+        assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
+        assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["value"] != d["value"]
+        rf = d["roofline"]
+        assert rf["bound"] in ("hbm", "tensor") and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-3
+        assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+        assert not ({"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(d["clocks"]["reasons"]))
+        if d["n_gpus"] == 1:
+            assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
