@@ -388,7 +388,7 @@ def run_ours(args):
     for name, h in head.items():
         h["frac_tc"] = round(h["TFLOPs_6BCD"] / pk["tc"], 4)
     line["head"] = head
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:          # the CPU baseline is a rank-0, N = 1 report
         line["cpu_baseline"] = cpu_baseline(sample_faces=args.cpu_faces)
     print(json.dumps(line))
     if world > 1:
