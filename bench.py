@@ -40,19 +40,49 @@ N_LOCAL = 4
 OUT_DIM = 65536
 N_LAND = 196
 KEEP_LOCAL = 36
+DIM = 768
 METRIC = "lafs_ssl_hot_path_faces_per_sec"
+
+# --config: the default is BASELINE.json configs[1] (the configuration the metric is quoted on); the others are
+# the remaining SSL configurations of BASELINE.json / SURVEY 8(d), run by hand and committed under profiles/
+WORKLOADS = {
+    "cfg1": {"B": 256, "L": 4, "vit": "B", "name": "BASELINE configs[1]: LAFS SSL pretrain hot path, ViT-B, 196 landmark "
+             "patches, out_dim 65536, 2 global + 4 local crops, batch 256 per GPU"},
+    "cfg1_L8": {"B": 256, "L": 8, "vit": "B", "name": "configs[1] with the reference's default of 8 local crops "
+                "(lafs_train.py:101), batch 256 per GPU"},
+    "cfg4": {"B": 128, "L": 4, "vit": "B", "name": "BASELINE configs[4]: SSL hot path with teacher EMA + landmark "
+             "augmentations, batch 128 per GPU (1024 over 8 GPUs)"},
+    "cfg0": {"B": 8, "L": 4, "vit": "S", "name": "BASELINE configs[0]: Part-fViT ViT-S (dim 384), batch 8, landmark patch "
+             "sampling + DINOLoss (2 global + 4 local crops)"},
+}
+
+
+def vit_param_shapes(vit="B", out_dim=OUT_DIM):
+    """The parameter tensors EMA'd every step: Part-fViT backbone (incl. the unused CosFace weight
+    [30000,dim]) + DINOHead.  ViT-B (dim 768, 11 heads x 64, mlp 2048: ViT_face.py / lafs_train.py:
+    302-333): 147 tensors, 110,261,248 parameters.  ViT-S (dim 384, 6 heads x 64, mlp 1536)."""
+    dim, inner, mlp = (768, 704, 2048) if vit == "B" else (384, 384, 1536)
+    shapes = [(1, 197, dim), (dim, 192), (dim,), (1, 1, dim)]
+    for _ in range(12):
+        shapes += [(dim,), (dim,), (3 * inner, dim), (dim, inner), (dim,), (dim,), (dim,), (mlp, dim), (mlp,),
+                   (dim, mlp), (dim,)]
+    shapes += [(dim,), (dim,), (30000, dim)]
+    shapes += [(2048, dim), (2048,), (2048, 2048), (2048,), (256, 2048), (256,), (out_dim, 1), (out_dim, 256)]
+    return shapes
 
 
 def vit_b_param_shapes(out_dim=OUT_DIM):
-    """The 147 parameter tensors EMA'd every step: Part-fViT ViT-B backbone (incl. the unused
-    CosFace weight [30000,768]) + DINOHead.  110,261,248 parameters."""
-    shapes = [(1, 197, 768), (768, 192), (768,), (1, 1, 768)]
-    for _ in range(12):
-        shapes += [(768,), (768,), (2112, 768), (768, 704), (768,), (768,), (768,), (2048, 768), (2048,),
-                   (768, 2048), (768,)]
-    shapes += [(768,), (768,), (30000, 768)]
-    shapes += [(2048, 768), (2048,), (2048, 2048), (2048,), (256, 2048), (256,), (out_dim, 1), (out_dim, 256)]
-    return shapes
+    return vit_param_shapes("B", out_dim)
+
+
+def set_workload(name):
+    global B_PER_GPU, N_LOCAL, DIM, VIT, WL_NAME
+    w = WORKLOADS[name]
+    B_PER_GPU, N_LOCAL, VIT, WL_NAME = w["B"], w["L"], w["vit"], w["name"]
+    DIM = 768 if VIT == "B" else 384
+
+
+VIT, WL_NAME = "B", WORKLOADS["cfg1"]["name"]
 
 
 def ncu_traffic(report):
@@ -141,7 +171,7 @@ def make_device_state(B, seed, dev):
         "student_out": torch.randn((L + 2) * B, OUT_DIM, device=dev, generator=g).bfloat16(),
         "teacher_out": torch.randn(2 * B, OUT_DIM, device=dev, generator=g).bfloat16(),
     }
-    shapes = vit_b_param_shapes()
+    shapes = vit_param_shapes(VIT)
     st["student_params"] = [torch.randn(*s, device=dev, generator=g) * 0.02 for s in shapes]
     st["teacher_params"] = [p.clone() for p in st["student_params"]]
     return st
@@ -322,12 +352,12 @@ def run_ours(args):
     ms_step_eager = ms_total / args.steps
     faces = B * world
     K, nc = OUT_DIM, L + 2
-    nparam = sum(int(np.prod(s)) for s in vit_b_param_shapes())
-    tok_out = (2 * 2 * B * 196 + L * B * 36) * 768 * 2
+    nparam = sum(int(np.prod(s)) for s in vit_param_shapes(VIT))
+    tok_out = (2 * 2 * B * 196 + L * B * 36) * DIM * 2
     alg = {
         # images + landmarks in, bf16 tokens of both models out (e_img = 1 byte)
         "landmark+gather_embed": {"bytes": (2 + L) * B * (3 * 112 * 112 * 1) + 2 * B * 196 * 8 + L * B * 36 * 8 + tok_out,
-                                  "flops": 2.0 * 192 * 768 * (2 * 2 * B * 196 + L * B * 36), "write_bytes": tok_out},
+                                  "flops": 2.0 * 192 * DIM * (2 * 2 * B * 196 + L * B * 36), "write_bytes": tok_out},
         "dino_fwd+center": {"bytes": (nc + 2) * B * K * 2 + 8 * K},
         "dino_bwd": {"bytes": (2 * nc + 2) * B * K * 2},
         "ema": {"bytes": 12 * nparam},
@@ -359,9 +389,8 @@ def run_ours(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 5),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 logits+tokens / uint8 images / fp32 params",
         "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1]: LAFS SSL pretrain hot path, ViT-B, 196 landmark patches, "
-                               "out_dim 65536, 2 global + 4 local crops, batch 256 per GPU",
-                   "batch_per_gpu": B, "out_dim": K, "ncrops": nc, "ema_params": nparam, "ema_tensors": len(vit_b_param_shapes()),
+        "config": {"workload": WL_NAME,
+                   "batch_per_gpu": B, "out_dim": K, "ncrops": nc, "ema_params": nparam, "ema_tensors": len(vit_param_shapes(VIT)),
                    "images": "uint8 decoded pixels, normalised in-kernel (value_fp32_images / e2e_fp32_images: fp32 tensors)",
                    "l2": "inputs larger than L2 (logits 335 MB, tokens out 362 MB, parameters 882 MB per step)",
                    "parallelism": f"dp{world}", "centre_exchange": centre_exchange},
@@ -388,8 +417,14 @@ def run_ours(args):
     for name, h in head.items():
         h["frac_tc"] = round(h["TFLOPs_6BCD"] / pk["tc"], 4)
     line["head"] = head
+    if world == 1 and not args.no_ref_gpu and _reference_available():
+        # the unmodified reference modules in eager PyTorch on this same GPU (N = 1 report)
+        line["reference_eager_b200"] = reference_eager_gpu(dev)
+        r = line["reference_eager_b200"].get("ssl_step")
+        if r:
+            line["reference_eager_b200"]["speedup_value_over_reference_eager"] = round(r["ms_per_step"] / ms_step, 1)
     if not args.no_cpu and world == 1:          # the CPU baseline is a rank-0, N = 1 report
-        line["cpu_baseline"] = cpu_baseline(sample_faces=args.cpu_faces)
+        line["cpu_baseline"] = cpu_baseline()
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -462,13 +497,34 @@ def bench_head(P, world, rank, dev, dist, args):
         if peer:                      # a peer that missed the kernels' spin bound would have produced garbage
             for xc in h._xchg.values():
                 xc.check()
+        # ---- N > 1: the sharded step against the unsharded one on the same inputs (every rank checks its
+        # own class slice; the worst relative error over the ranks is reported and gates the bench) ----------
+        parity = None
+        if world > 1:
+            loss_s = step().detach().clone()
+            de_s, dw_s = x.grad.detach().clone(), h.weight.grad.detach().clone()
+            torch.manual_seed(7)
+            hu = cls(D, C, None).to(dev)
+            xu = x.detach().clone().requires_grad_(True)
+            loss_u = hu.forward_loss(xu, lab)
+            loss_u.backward()
+            lo, hi = h.class_lo, h.class_hi
+            dw_u = hu.weight.grad[lo:hi]
+            errs = torch.stack([
+                (loss_s - loss_u.detach()).abs() / loss_u.detach().abs(),
+                (de_s - xu.grad).abs().max() / xu.grad.abs().max(),
+                (dw_s - dw_u).abs().max() / hu.weight.grad.abs().max()]).double()
+            dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+            parity = [float(v) for v in errs.tolist()]
+            del hu, xu, dw_u
         del h, x
         torch.cuda.empty_cache()
-        return ms, ms_eager, mode
+        return ms, ms_eager, mode, parity
 
+    import lafs_cvpr2024_b200 as PK
     out = {}
-    cfgs = [("cosface_ms1mv3", P.CosFace, 512, 93431, 512), ("arcface_webface4m", P.ArcFace, 1024, 205990, 512)]
-    for name, cls, B, C, D in cfgs:
+    for name, B, C, D in HEAD_CFGS:
+        cls = PK.CosFace if name.startswith("cosface") else PK.ArcFace
         res = {}
         for variant in (["nccl", "peer"] if world > 1 else ["single"]):
             try:
@@ -478,7 +534,7 @@ def bench_head(P, world, rank, dev, dist, args):
                 torch.cuda.synchronize()
         timed = {k: v for k, v in res.items() if isinstance(v, tuple)}
         best = min(timed, key=lambda k: timed[k][0])
-        ms, ms_eager, mode = timed[best]
+        ms, ms_eager, mode, _ = timed[best]
         out[name] = {"B_global": B, "classes": C, "D": D, "shards": world, "ms_fwd_bwd": round(ms, 4), "launch": mode,
                      "ms_fwd_bwd_eager": round(ms_eager, 4), "exchange": best,
                      "faces_per_s": round(B / ms * 1e3, 1), "TFLOPs_6BCD": round(6.0 * B * C * D / ms / 1e9 / world, 1),
@@ -486,14 +542,74 @@ def bench_head(P, world, rank, dev, dist, args):
         if world > 1:
             out[name]["ms_by_exchange"] = {k: round(v[0], 4) for k, v in timed.items()}
             out[name].update({k: v for k, v in res.items() if k.endswith("_error")})
+            # sharded vs unsharded on the same inputs: [loss rel, dE max-norm rel, dW-slice max-norm rel], worst rank
+            pm = {k: v[3] for k, v in timed.items() if v[3] is not None}
+            out[name]["parity_vs_unsharded"] = {k: [float("%.3g" % e) for e in v] for k, v in pm.items()}
+            out[name]["parity_max_rel"] = float("%.3g" % max(max(v) for v in pm.values()))
+            if out[name]["parity_max_rel"] > HEAD_PARITY_TOL:
+                raise SystemExit(f"bench.py: sharded head {name} deviates from the unsharded head by "
+                                 f"{out[name]['parity_max_rel']} (> {HEAD_PARITY_TOL}) at world={world}")
     return out
 
 
+HEAD_PARITY_TOL = 2e-3     # max-norm relative; the two runs share operands and lse up to fp32 summation order
+
+
 # ---------------------------------------------------------------------------------------------
-def cpu_step_time(sample_faces, threads, reps=1):
-    """The oracle port of the same step on the host cores: per-face parts on `sample_faces`
-    faces, the (batch-independent) EMA on the full parameter list.  Returns seconds per
-    256-face step, extrapolated linearly in the per-face parts."""
+# Reference arms.  The reference is pure Python/PyTorch: __graft_entry__.build() stages the seven files
+# the path needs, unmodified, in the git-ignored baseline/_ref/ (SURVEY.md section 7 step 1), and
+# oracle/ref_step.py drives those modules through the same hot path.  kind = "reference".  If the copy
+# is missing (build() was not run where /root/reference exists) the oracle port stands in, kind = "port".
+def _reference_available():
+    from oracle import ref_harness
+    return ref_harness.available()
+
+
+def cpu_reference_run(steps, warmup, budget_s=200.0):
+    """The unmodified reference modules on the host cores (fp32, all threads).  Every step is a
+    bounded sample: the per-face regions (extract, embed, dino) run on `faces` <= B faces and are
+    scaled to B, the EMA runs on the full parameter list.  `faces` is chosen after the first warm-up
+    step so that steps + warmup end within `budget_s`.  Returns (seconds per B-face step, info)."""
+    from oracle import ref_step
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B, L = B_PER_GPU, N_LOCAL
+    shapes = vit_param_shapes(VIT)
+    faces = min(B, 64)
+    st = ref_step.SSLReferenceStep("cpu", faces, L, OUT_DIM, DIM, shapes, seed=0)
+
+    def one(it):
+        t = st.step(it)
+        per_face = t["extract"] + t["embed"] + t["dino"]
+        return per_face * (B / faces) + t["ema"], t
+
+    sec, _ = one(0)                                     # first warm-up step doubles as the probe
+    total = max(1, steps + warmup)
+    want = B
+    while want > 8 and sec * (want / faces) * total > budget_s:
+        want //= 2
+    if want != faces:
+        faces = want
+        del st
+        st = ref_step.SSLReferenceStep("cpu", faces, L, OUT_DIM, DIM, shapes, seed=0)
+    for i in range(max(0, warmup - 1)):
+        one(i)
+    secs, parts = [], []
+    for i in range(max(1, steps)):
+        sec, t = one(warmup + i)
+        secs.append(sec)
+        parts.append(t)
+    sec = float(np.median(secs))
+    regions = {k: round(float(np.median([p[k] for p in parts])) * (1.0 if k == "ema" else B / faces) * 1e3, 2)
+               for k in ("extract", "embed", "dino", "ema")}
+    info = {"cores": cores, "kind": "reference", "faces": faces, "ms_by_region": regions,
+            "sample": f"unmodified reference modules (baseline/_ref via oracle/ref_step.py), fp32, {cores} threads: "
+                      f"extract/embed/DINO regions on {faces} of {B} faces scaled x{B / faces:g}, full {len(shapes)}-tensor EMA"}
+    return sec, info
+
+
+def cpu_port_run(sample_faces, threads, reps=1):
+    """Fallback when the reference files are not staged: the oracle port (kind = "port")."""
     from oracle import lafs_oracle as O
     torch.set_num_threads(threads)
     Bs, L = sample_faces, N_LOCAL
@@ -505,8 +621,7 @@ def cpu_step_time(sample_faces, threads, reps=1):
     s = torch.randn((L + 2) * Bs, OUT_DIM, generator=g)
     t = torch.randn(2 * Bs, OUT_DIM, generator=g)
     center = torch.zeros(1, OUT_DIM)
-    shapes = vit_b_param_shapes()
-    q = [torch.randn(*sh, generator=g) for sh in shapes]
+    q = [torch.randn(*sh, generator=g) for sh in vit_param_shapes(VIT)]
     k = [p.clone() for p in q]
     ws, bs, wt, bt = q[1], q[2], k[1], k[2]     # patch_to_embedding of student / teacher
     best_face, best_ema = float("inf"), float("inf")
@@ -523,45 +638,86 @@ def cpu_step_time(sample_faces, threads, reps=1):
         O.ema_update_(k, q, 0.996)
         t2 = time.perf_counter()
         best_face, best_ema = min(best_face, t1 - t0), min(best_ema, t2 - t1)
-    return best_face * (B_PER_GPU / Bs) + best_ema, best_face, best_ema
+    return best_face * (B_PER_GPU / Bs) + best_ema
 
 
-def cpu_baseline(sample_faces=256):
-    cores = os.cpu_count() or 1
-    sec, t_face, t_ema = cpu_step_time(sample_faces, cores, reps=3)
-    return {"value": round(B_PER_GPU / sec, 2), "unit": "faces/s", "cores": cores, "kind": "port",
-            "sample": f"oracle port (torch-CPU fp32, {cores} threads): per-face parts timed on {sample_faces} of 256 faces "
-                      f"({t_face:.2f} s) and scaled x{B_PER_GPU // sample_faces}; full 147-tensor EMA timed once ({t_ema:.2f} s)"}
+def cpu_baseline():
+    """cpu_baseline leg of our own line (rank 0, N = 1): a short run of the reference arm."""
+    if _reference_available():
+        sec, info = cpu_reference_run(steps=2, warmup=1, budget_s=25.0)
+    else:
+        cores = os.cpu_count() or 1
+        sec = cpu_port_run(min(B_PER_GPU, 64), cores)
+        info = {"cores": cores, "kind": "port", "sample": "oracle port (baseline/_ref not staged), 64 faces scaled"}
+    out = {"value": round(B_PER_GPU / sec, 2), "unit": "faces/s"}
+    out.update(info)
+    return out
+
+
+def reference_eager_gpu(dev, steps=3):
+    """The same unmodified reference modules in eager PyTorch on this GPU (fp16 autocast as in
+    lafs_train.py:577): per region and per step -- the practical kernel to beat."""
+    from oracle import ref_step
+    out = {}
+    try:
+        st = ref_step.SSLReferenceStep(dev, B_PER_GPU, N_LOCAL, OUT_DIM, DIM, vit_param_shapes(VIT), seed=0)
+        st.step(0)
+        ts = [st.step(1 + i) for i in range(steps)]
+        reg = {k: float(np.median([t[k] for t in ts])) * 1e3 for k in ("extract", "embed", "dino", "ema")}
+        ms = sum(reg.values())
+        out["ssl_step"] = {"ms_per_step": round(ms, 3), "faces_per_s": round(B_PER_GPU / ms * 1e3, 1),
+                           "ms_by_region": {k: round(v, 3) for k, v in reg.items()},
+                           "note": "reference modules, eager CUDA, fp16 autocast; device-resident inputs; regions timed with "
+                                   "CUDA events, launch overhead included (that is the reference's cost)"}
+        del st
+        torch.cuda.empty_cache()
+    except Exception as e:
+        out["ssl_step_error"] = str(e).splitlines()[0][:160]
+    for name, B, C, D in HEAD_CFGS:
+        if D != 512:
+            continue
+        try:
+            sec, _ = ref_step.head_reference_step(dev, B, C, D, iters=3)
+            out["head_" + name] = {"ms_fwd_bwd": round(sec * 1e3, 3), "faces_per_s": round(B / sec, 1),
+                                   "note": "VF.CosFace + CrossEntropyLoss fwd+bwd, eager CUDA fp32 (CPU one-hot + H2D as in "
+                                           "ViT_face.py:67-82)"}
+        except Exception as e:
+            out["head_" + name + "_error"] = str(e).splitlines()[0][:160]
+        torch.cuda.empty_cache()
+    return out
 
 
 def run_reference(args):
-    """Reference arm: the reference's own CPU implementation of the path.  The reference is
-    Python and cannot travel to the GPU box (no /root/reference there), so this is the oracle
-    port (pinned bit-for-bit to the reference by tests/golden), on all host cores."""
+    """`--impl reference`: the reference's own CPU implementation of the path on the box's host cores,
+    honouring --steps / --warmup.  Rank 0 alone runs; the other ranks exit 0 without work."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    faces = args.cpu_faces
-    cpu_step_time(min(faces, 8), cores, reps=0)     # untimed: thread pool / allocator warm-up
-    secs = []
-    for _ in range(max(1, min(args.steps, 5))):
-        sec, t_face, t_ema = cpu_step_time(faces, cores, reps=1)
-        secs.append(sec)
-    sec = float(np.median(secs))
+    if _reference_available():
+        sec, info = cpu_reference_run(args.steps, args.warmup)
+        steps, warm = max(1, args.steps), args.warmup
+    else:
+        cores = os.cpu_count() or 1
+        secs = [cpu_port_run(min(B_PER_GPU, 64), cores, reps=0) for _ in range(max(1, min(args.steps, 5)))]
+        sec, steps, warm = float(np.median(secs)), len(secs), 0
+        info = {"cores": cores, "kind": "port", "sample": "oracle port (baseline/_ref not staged), 64 faces scaled"}
     val = round(B_PER_GPU / sec, 2)
+    cb = {"value": val, "unit": "faces/s"}
+    cb.update(info)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "faces/s", "n_gpus": args.gpus,
-        "steps": len(secs), "warmup": 1, "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True,
+        "steps": steps, "warmup": warm, "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1] hot path on host cores (bounded sample)", "batch_per_gpu": B_PER_GPU,
+        "config": {"workload": WL_NAME + " -- on host cores (bounded sample)", "batch_per_gpu": B_PER_GPU,
                    "out_dim": OUT_DIM, "ncrops": N_LOCAL + 2},
-        "cpu_baseline": {"value": val, "unit": "faces/s", "cores": cores, "kind": "port",
-                         "sample": f"per-face parts on {faces} of 256 faces scaled x{B_PER_GPU // faces} + full EMA; "
-                                   "oracle port of the reference (Python reference cannot travel to the GPU box)"},
+        "cpu_baseline": cb,
         "e2e": {"value": val, "unit": "faces/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+HEAD_CFGS = [("cosface_ms1mv3", 512, 93431, 512), ("arcface_webface4m", 1024, 205990, 512),
+             ("cosface_ms1mv3_d768", 512, 93431, 768), ("arcface_webface4m_d768", 1024, 205990, 768)]
 
 
 def main():
@@ -570,9 +726,11 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-faces", type=int, default=256, help="faces in the bounded CPU sample (256 = the full step)")
+    ap.add_argument("--config", default="cfg1", choices=sorted(WORKLOADS), help="SSL workload (default: BASELINE configs[1])")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference_eager_b200 report")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
+    set_workload(args.config)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)

@@ -186,7 +186,16 @@ def cosine_scheduler(base_value, final_value, epochs, niter_per_ep):
 # --------------------------------------------------------------------------------------
 # (4) margin heads + cross entropy + class sharding
 # --------------------------------------------------------------------------------------
+def _round_st(v):
+    """bf16 rounding in the forward value, identity in the backward pass (straight-through)."""
+    return v + (v.detach().bfloat16().float() - v.detach())
+
+
 def _cosine(x, weight, pre_normalized):
+    if pre_normalized == "bf16_st":
+        # F.normalize, then the unit rows rounded to bf16 exactly as a bf16 tensor-core path stores them;
+        # gradients still flow through the normalisation Jacobians (SURVEY H4: same operands, fp32 math)
+        return F.linear(_round_st(F.normalize(x)), _round_st(F.normalize(weight)))
     if pre_normalized:   # operands already unit rows (e.g. the bf16-rounded rows a tensor core sees)
         return F.linear(x, weight)
     return F.linear(F.normalize(x), F.normalize(weight))

@@ -1,9 +1,11 @@
 """Import harness for the UNMODIFIED reference (test infrastructure, not product code).
 
-Only usable where /root/reference exists (the build container).  It is used by
-tests/golden/make_golden.py to generate the committed golden vectors and by
-tests that pin oracle/lafs_oracle.py against the real reference.  Nothing in the
-product package imports this file, and nothing on the GPU box needs it.
+It is used by tests/golden/make_golden.py to generate the committed golden vectors, by the
+tests that pin oracle/lafs_oracle.py against the real reference (build container only:
+/root/reference) and by bench.py's reference arms (oracle/ref_step.py), which on the GPU box
+import the git-ignored copy baseline/_ref/ that __graft_entry__.build() makes of the seven
+files the path needs.  Nothing in the product package imports
+this file; the -m gpu tests and smoke() do not use it.
 
 Recipe follows SURVEY.md Appendix A: two import shims (IPython, timm.models.layers)
 and an identity patch for the hard-coded .cuda() calls when no GPU is present.
@@ -14,11 +16,39 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("LAFS_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LOCAL_COPY = os.path.join(_REPO, "baseline", "_ref")
+# the files of the reference the hot path needs
+REF_FILES = ["lafs_train.py", "utils.py", "vision_transformer.py", "face_pre_pro/ViT_face.py",
+             "face_pre_pro/mobilenet.py", "util/__init__.py", "util/mixup_my.py"]
+
+
+def _find_root():
+    for cand in (os.environ.get("LAFS_REFERENCE_ROOT"), "/root/reference", LOCAL_COPY):
+        if cand and os.path.isfile(os.path.join(cand, "lafs_train.py")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 
 
 def available() -> bool:
     return os.path.isfile(os.path.join(REF_ROOT, "lafs_train.py"))
+
+
+def stage_local_copy(src="/root/reference") -> bool:
+    """Copies the seven reference files, byte for byte, into baseline/_ref/ (git-ignored, NOT
+    gpurun-ignored) so that bench.py's reference arms can run the unmodified reference on the GPU
+    box.  No-op when `src` is absent (the GPU box)."""
+    import shutil
+    if not os.path.isfile(os.path.join(src, "lafs_train.py")):
+        return False
+    for rel in REF_FILES:
+        dst = os.path.join(LOCAL_COPY, rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        shutil.copyfile(os.path.join(src, rel), dst)
+    return True
 
 
 _cached = None
@@ -62,6 +92,6 @@ def load():
     if not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29533")
-        dist.init_process_group("gloo", rank=0, world_size=1)
+        dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo", rank=0, world_size=1)
     _cached = types.SimpleNamespace(VF=VF, L=L, vt=vt, dutils=dutils, mixup=mixup_my)
     return _cached

@@ -55,6 +55,23 @@ def test_ema_vit_b_shapes_vs_oracle(P):
     P.ema_update_([], [], 0.5)  # empty list is a no-op
 
 
+def test_ema_full_vit_b_parameter_list_bit_exact(P):
+    """The list bench.py times: 147 tensors / 110,261,248 fp32 parameters (ViT-B backbone incl. the unused
+    CosFace weight + DINOHead), one launch, bit-exact against lafs_train.py:610-613 on the host."""
+    import bench
+    shapes = bench.vit_param_shapes("B")
+    assert len(shapes) == 147 and sum(int(np.prod(s)) for s in shapes) == 110261248
+    g = torch.Generator().manual_seed(1)
+    q = [torch.randn(*s, generator=g) * 0.02 for s in shapes]
+    k = [torch.randn(*s, generator=g) * 0.02 for s in shapes]
+    qg, kg = [a.cuda() for a in q], [a.cuda() for a in k]
+    m = O.cosine_scheduler(0.996, 1, 41, 1000)[777]
+    O.ema_update_(k, q, m)
+    P.ema_update_(kg, qg, m)
+    for i, (a, b) in enumerate(zip(k, kg)):
+        assert torch.equal(a, b.cpu()), (i, shapes[i])
+
+
 def test_ema_idempotent_at_m1_and_copies_at_m0(P):
     k, q = torch.randn(100003, device="cuda"), torch.randn(100003, device="cuda")
     k0 = k.clone()

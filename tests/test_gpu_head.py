@@ -241,3 +241,84 @@ def test_dw_jacobian_on_tensor_core_variant(P, B, C, D, kind):
     assert abs(out[0] - base[0]) <= 1e-6 * abs(base[0])
     assert (out[1] - base[1]).abs().max() <= 1e-5 * base[1].abs().max()            # dE: untouched path
     assert (out[2] - base[2]).abs().max() <= 5e-3 * base[2].abs().max(), float((out[2] - base[2]).abs().max() / base[2].abs().max())
+
+
+# ---- the exact shapes bench.py times (BASELINE configs[2], configs[3]) and their 8-way shard-local sizes ----
+def _bench_case(P, kind, B, C, D, shard=None, seed=3):
+    """One fused-loss step at a bench shape against the oracle on the SAME bf16-rounded unit operands
+    (fp32 math, gradients through the normalisation Jacobians).  shard=(rank, world): only that class
+    slice lives on the GPU (class_lo != 0), the oracle runs the full problem."""
+    torch.manual_seed(seed)
+    x = torch.randn(B, D)
+    w = torch.empty(C, D)
+    torch.nn.init.xavier_uniform_(w)                      # the reference's init (ViT_face.py:46-47)
+    lab = torch.randint(0, C, (B,))
+    lab[0], lab[1] = C - 1, 0
+    cls = P.CosFace if kind == "cosface" else P.ArcFace
+    ref_loss, ref_logits, ref_gx, ref_gw = O.head_loss_and_grads(x, w, lab, kind, pre_normalized="bf16_st")
+    ref_lse = torch.logsumexp(ref_logits, 1)
+    del ref_logits
+    if shard is None:
+        h = make_head(P, cls, w)
+        xg = x.cuda().requires_grad_(True)
+        loss = h.forward_loss(xg, lab.cuda())
+        loss.backward()
+        assert abs(float(loss) - float(ref_loss)) <= 1e-3 * abs(float(ref_loss)), (float(loss), float(ref_loss))
+        gx, gw = xg.grad.cpu(), h.weight.grad.cpu()
+        lo, hi = 0, C
+    else:
+        r, R = shard
+        lo, hi = P.shard_bounds(C, R)[r]
+        h = cls(D, C, None, shard=(r, R)).cuda()
+        assert h.class_lo == lo and h.weight.shape[0] == hi - lo and lo != 0
+        with torch.no_grad():
+            h.weight.copy_(w[lo:hi])
+        # per-row statistics of this shard against the oracle's logits restricted to the shard
+        stats, (la, lb, lam, e_hat, w_hat) = h.forward_stats(x.cuda(), lab.cuda())
+        xs = torch.nn.functional.normalize(x).bfloat16().float()
+        wsl = torch.nn.functional.normalize(w[lo:hi]).bfloat16().float()
+        z = 64.0 * (xs @ wsl.t())
+        own = (lab >= lo) & (lab < hi)
+        logit_fn = O.cosface_logits if kind == "cosface" else O.arcface_logits
+        z[own] = logit_fn(xs[own], wsl, lab[own] - lo, pre_normalized=True)     # margin on the rows this shard owns
+        st = stats.cpu()
+        lse_shard = st[:, 0] * np.log(2.0) + torch.log(st[:, 1])
+        assert (lse_shard - torch.logsumexp(z, 1)).abs().max() <= 1e-3
+        assert (st[own, 2] - z[own, (lab[own] - lo)]).abs().max() <= 2e-3 * 64
+        # gradient of this shard given the FULL row lse (what the merged statistics deliver)
+        from lafs_cvpr2024_b200 import _lib, margin_head as MH
+        lse2 = (ref_lse / np.log(2.0)).float().cuda().contiguous()
+        ldg = MH._round8(hi - lo)
+        G = torch.empty(B, ldg, dtype=torch.bfloat16, device="cuda")
+        one = torch.ones((), device="cuda")
+        _lib.call("lafs_head_grad_logits", e_hat.data_ptr(), w_hat.data_ptr(), la.data_ptr(), None, 1.0, B, hi - lo, D, lo,
+                  float(h.s), float(h.m), h.kind, lse2.data_ptr(), one.data_ptr(), float(h.s) / B, G.data_ptr(), ldg,
+                  _lib.stream())
+        _, inv_e = MH._prep(x.cuda(), want_inv=True)
+        _, inv_w = MH._prep(h.weight, want_inv=True)
+        de_part, gw = MH._head_backward(G, ldg, e_hat, w_hat, inv_e, inv_w, B, hi - lo, D, False)
+        gw = gw.cpu()
+        gx = None      # dE of one shard is a partial sum: checked through dW and the statistics here
+    sl = slice(lo, hi)
+    if gx is not None:
+        err = float((gx - ref_gx).abs().max() / ref_gx.abs().max())
+        assert err <= 5e-3, ("dE", err)
+    # dW: the rows of the target classes (largest entries) plus a sampled 4k-class slice
+    idx = torch.unique(torch.cat([lab[(lab >= lo) & (lab < hi)], torch.randint(lo, hi, (4096,))]))
+    err = float((gw[idx - lo] - ref_gw[idx]).abs().max() / ref_gw[sl].abs().max())
+    assert err <= 5e-3, ("dW", err)
+    cs = torch.nn.functional.cosine_similarity(gw.flatten(), ref_gw[sl].flatten(), dim=0)
+    assert cs > 0.9999, float(cs)
+
+
+@pytest.mark.parametrize("kind,B,C,D", [("cosface", 512, 93431, 512), ("arcface", 1024, 205990, 512),
+                                        ("cosface", 512, 93431, 768)])
+def test_head_bench_shapes_vs_oracle(P, kind, B, C, D):
+    _bench_case(P, kind, B, C, D)
+
+
+@pytest.mark.parametrize("kind,B,C,rank", [("cosface", 512, 93431, 3), ("cosface", 512, 93431, 7),
+                                           ("arcface", 1024, 205990, 5), ("arcface", 1024, 205990, 7)])
+def test_head_bench_shard_local_shapes_vs_oracle(P, kind, B, C, rank):
+    """8-way class shards of the bench shapes: 11,679 / 11,678 and 25,749 / 25,747 local classes, class_lo != 0."""
+    _bench_case(P, kind, B, C, 512, shard=(rank, 8))

@@ -32,3 +32,7 @@ PY
 done
 echo "=== head step, default vs LAFS_DW_DIAG=1 (graph timings at the end of each line)"
 for c in cfg3 cfg4; do $T 300 python tools/head_breakdown.py $c | tail -1 | tee -a gpurun_out/head_breakdown_r02.jsonl; done
+echo "=== write-bandwidth probe (SIMT vs TMA bulk store vs memset)"
+$T 120 tools/_bin/wbw_probe 2>&1 | tee gpurun_out/wbw_probe.txt
+echo "=== full gpu suite (experimental tests on)"
+$T 900 python -m pytest tests -m gpu -q -p no:cacheprovider -x 2>&1 | tail -5
