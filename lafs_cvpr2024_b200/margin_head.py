@@ -238,6 +238,31 @@ class _MarginHead(nn.Module):
             self._xchg[key] = PeerExchange(self._peer_group, B, D, dev)
         return self._xchg[key]
 
+    # ---- checkpoints of a class-sharded head ------------------------------------------------------
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        """A full [C, D] `weight` (a reference / unsharded checkpoint, key `loss.weight`) loads into a sharded
+        head by taking this rank's torch.chunk slice [class_lo, class_hi) (ViT_face.py:56)."""
+        key = prefix + "weight"
+        w = state_dict.get(key)
+        if w is not None and w.dim() == 2 and w.shape[0] == self.out_features and self.weight.shape[0] != self.out_features:
+            state_dict = dict(state_dict)
+            state_dict[key] = w[self.class_lo:self.class_hi]
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
+
+    @torch.no_grad()
+    def full_weight(self, group=None):
+        """The full [C, D] weight on every rank of a sharded head (all-gather of the slices, in torch.chunk
+        order) -- what `state_dict()` of the reference's unsharded CosFace holds; use it to save checkpoints."""
+        if self.shard is None or self.shard[1] == 1:
+            return self.weight.detach().clone()
+        world = self.shard[1]
+        step = -(-self.out_features // world)
+        pad = torch.zeros(step, self.in_features, dtype=self.weight.dtype, device=self.weight.device)
+        pad[: self.weight.shape[0]] = self.weight
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad, group=group)
+        return torch.cat(parts)[: self.out_features].contiguous()
+
     # ---- helpers -----------------------------------------------------------------------------
     def _labels(self, label, label_b, lam):
         if label.dim() > 1:                                # dense [B, C] soft targets (reference API)

@@ -95,13 +95,19 @@ class GraphedSSLStep:
         self.center = path.loss.center.detach().clone().contiguous()
         self.graph = torch.cuda.CUDAGraph()
         self.out = {}
+        # Warm-up outside capture (lazy init, workspaces) must not change training state: it runs with
+        # momentum 1.0 (k*1 + q*0 leaves the teacher bit-identical for finite q) and the centre is put back
+        # afterwards, so constructing the graph is side-effect free whatever the static input buffers hold.
+        # Capture itself executes nothing.  The static inputs must hold valid data before the first replay().
+        center0 = self.center.clone()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):                 # warm-up outside capture (lazy init, workspaces)
+        with torch.cuda.stream(side):
             for _ in range(2):
-                self._body(epoch, momentum)
+                self._body(epoch, 1.0)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        self.center.copy_(center0)
         with torch.cuda.graph(self.graph):
             self._body(epoch, momentum)
 

@@ -93,15 +93,25 @@ class Attention(nn.Module):
         self.scale = dim ** -0.5
         self.to_qkv = nn.Linear(dim, inner * 3, bias=False)
         self.to_out = nn.Sequential(nn.Linear(inner, dim), nn.Dropout(dropout))
+        self.attention_score = 0
 
     def forward(self, x, mask=None):
         b, n, _ = x.shape
         q, k, v = (t.view(b, n, self.heads, -1).transpose(1, 2) for t in self.to_qkv(x).chunk(3, dim=-1))
-        attn_mask = None
-        if mask is not None:
+        if mask is None:
+            out = F.scaled_dot_product_attention(q, k, v, scale=self.scale)
+        else:
+            # the reference's masked form, op for op (ViT_face.py:164-176): masked logits are REPLACED by
+            # -finfo.max, so a fully masked query row attends uniformly and stays finite (a boolean SDPA mask
+            # would give NaN / 0 there); `attention_score` is kept like the reference does
+            dots = torch.einsum('bhid,bhjd->bhij', q, k) * self.scale
             m = F.pad(mask.flatten(1), (1, 0), value=True)
-            attn_mask = (m[:, None, :] * m[:, :, None])[:, None]
-        out = F.scaled_dot_product_attention(q, k, v, attn_mask=attn_mask, scale=self.scale)
+            assert m.shape[-1] == dots.shape[-1], 'mask has incorrect dimensions'
+            m = m[:, None, :] * m[:, :, None]
+            dots = dots.masked_fill(~m[:, None], -torch.finfo(dots.dtype).max)
+            attn = dots.softmax(dim=-1)
+            self.attention_score = attn.detach()
+            out = torch.einsum('bhij,bhjd->bhid', attn, v)
         return self.to_out(out.transpose(1, 2).reshape(b, n, -1))
 
 
@@ -124,7 +134,8 @@ def _tokens_and_embedding(imgs, theta, linear, training_path):
     HBM).  With gradients its backward runs on the tcgen05 GEMMs of patches.gather_embed_train; shapes
     the fused kernel does not cover (dim % 128 != 0, more than 208 landmarks) take the differentiable
     fp32 gather kernel + nn.Linear."""
-    fused_ok = linear.weight.shape[0] % 128 == 0 and theta.shape[1] <= 208 and imgs.shape[1] == 3
+    fused_ok = (linear.weight.shape[0] % 128 == 0 and theta.shape[1] <= 208 and imgs.shape[1] == 3
+                and tuple(imgs.shape[-2:]) == (112, 112))
     if training_path:
         if fused_ok:
             return gather_embed_train(imgs, theta, linear.weight, linear.bias).to(linear.weight.dtype)

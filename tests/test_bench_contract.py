@@ -13,7 +13,7 @@ BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
 
 def test_reference_arm_line():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                        "--warmup", "0", "--cpu-faces", "4"], capture_output=True, text=True, timeout=600,
+                        "--warmup", "1", "--config", "cfg0"], capture_output=True, text=True, timeout=600,
                        env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
     assert r.returncode == 0, r.stderr[-500:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
@@ -25,6 +25,9 @@ def test_reference_arm_line():
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["steps"] == 1 and d["warmup"] == 1               # the arm honours --steps / --warmup
+    if os.path.isfile("/root/reference/lafs_train.py") or os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "lafs_train.py")):
+        assert cb["kind"] == "reference"                      # the unmodified reference modules, not the port
 
 
 def test_committed_profiles_of_our_arm_follow_the_contract():

@@ -85,12 +85,11 @@ def test_graph_replay_equals_eager_over_steps():
         loss, grad_e = path_e.loss_and_grad(dev["student_out"], dev["teacher_out"], 5)   # wave-fused, as in the graph
         path_e.ema_step(0.99)
         losses_e.append(float(loss))
-    # graph: capture (its two warm-up runs + capture must not advance the state we compare)
+    # graph: construction (two warm-up runs + capture) must leave the teacher and the centre untouched
     path_g, _, tpg = fresh()
     g = GraphedSSLStep(path_g, dev, epoch=5, momentum=0.99)
-    g.center.copy_(center0.cuda())
-    for a, b in zip(tpg, tp):
-        a.copy_(b.cuda())
+    assert torch.equal(g.center, center0.cuda())
+    assert all(torch.equal(a.cpu(), b) for a, b in zip(tpg, tp))
     losses_g = [float(g.replay()) for _ in range(3)]
     assert losses_g == losses_e                      # deterministic kernels: bit-identical
     assert torch.equal(g.out["grad_student"], grad_e)

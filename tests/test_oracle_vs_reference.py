@@ -147,3 +147,29 @@ def test_standard_grid_and_plain_grid_paths_match_reference(ref, random_prob, sh
     m2.load_state_dict(r2.state_dict(), strict=True)
     with torch.no_grad():
         torch.testing.assert_close(m2(x), r2(x), rtol=1e-5, atol=1e-6)
+
+
+def test_attention_with_mask_matches_reference(ref):
+    """Masked attention (ViT_face.py:140-182): masked logits are replaced by -finfo.max, a fully masked query
+    row attends uniformly (finite), and `attention_score` is stashed -- same weights, same output (CPU)."""
+    from lafs_cvpr2024_b200 import vit_face as V
+    torch.manual_seed(3)
+    dim, heads, n = 64, 3, 9
+    ra = ref.VF.Attention(dim, heads=heads, dim_head=16)
+    oa = V.Attention(dim, heads=heads, dim_head=16)
+    oa.load_state_dict(ra.state_dict(), strict=True)
+    # the reference broadcasts its [b,n,n] mask against [b,h,n,n] logits without a head axis (ViT_face.py:171-172),
+    # which only works for b == 1 (or b == heads, where it silently masks per HEAD): compare one sample at a time
+    for masked_all in (False, True):
+        x = torch.randn(1, n + 1, dim)
+        mask = torch.rand(1, n) > 0.4
+        if masked_all:
+            mask[0, :] = False              # every patch token masked: their query rows are fully masked
+        out_r = ra(x, mask=mask.clone())
+        out_o = oa(x, mask=mask.clone())
+        assert torch.isfinite(out_o).all()
+        torch.testing.assert_close(out_o, out_r, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(oa.attention_score, ra.attention_score, rtol=1e-5, atol=1e-7)
+    x = torch.randn(2, n + 1, dim)
+    torch.testing.assert_close(oa(x), ra(x), rtol=1e-5, atol=1e-6)     # unmasked path (SDPA) agrees too
+    assert torch.isfinite(oa(x, mask=torch.zeros(2, n, dtype=torch.bool))).all()   # batched masks work here
