@@ -65,6 +65,50 @@ struct Rows {
   uint4 s[NCROPS][U];
 };
 
+constexpr int kChunk = 8;   // samples between two CTA-level pre-merges of the 8 warps' slice records
+
+// Merge the 8 slice records of one sample (one per warp of the CTA, in shared memory) into ONE record of the
+// same format and store it: the finishing kernel then reads 8x fewer records.  Whole warp; lanes l and
+// l + 8k hold record l & 7, the xor butterflies stay inside 8-lane groups, so every lane ends with the result.
+template <int NCROPS>
+__device__ __forceinline__ void merge_cta_records(const float* __restrict__ recs /*[8][REC]*/, float* __restrict__ out,
+                                                  int lane) {
+  constexpr int REC = rec_floats(NCROPS);
+  const float* r = recs + (lane & 7) * REC;
+  float res[REC];
+#pragma unroll
+  for (int iq = 0; iq < 2; ++iq) {
+    const float ml = r[3 * iq];
+    float m = ml;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const float f = ex2(ml - m);                  // empty record: ml = -inf -> 0
+    float z = r[3 * iq + 1] * f, a = r[3 * iq + 2] * f;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      z += __shfl_xor_sync(0xffffffffu, z, o);
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+    }
+    res[3 * iq] = m; res[3 * iq + 1] = z; res[3 * iq + 2] = a;
+  }
+#pragma unroll
+  for (int v = 0; v < NCROPS; ++v) {
+    const float ml = r[6 + 2 * v];
+    float m = ml;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float z = r[7 + 2 * v] * ex2(ml - m);
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+    res[6 + 2 * v] = m; res[7 + 2 * v] = z;
+  }
+  float val = 0.f;
+#pragma unroll
+  for (int j = 0; j < REC; ++j)
+    if (lane == j) val = res[j];
+  if (lane < REC) out[lane] = val;                // one coalesced store of the merged record
+}
+
 // RAGGED: the last K-slice is partially filled (K % (32*VEC) != 0); lanes past K are masked.
 // The common case (K = 65536) compiles without any per-element predication.
 template <typename T, int NCROPS, bool RAGGED>
@@ -76,6 +120,8 @@ dino_fwd_partial(const T* __restrict__ student, const T* __restrict__ teacher,
   constexpr int VEC = VecOf<T>::VEC;
   constexpr int NC = VEC;
   constexpr int REC = rec_floats(NCROPS);
+  // slice records of the current / previous chunk of samples: [buffer][sample in chunk][warp][REC]
+  __shared__ float srec[2][kChunk][kDinoWarps][REC];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // arrival counter of dino_finish (the next kernel on the stream): reset here so that the workspace
   // needs no initialisation by the caller
@@ -84,13 +130,16 @@ dino_fwd_partial(const T* __restrict__ student, const T* __restrict__ teacher,
   // a CTA touches 8 x 512 B = 4 KB contiguous bytes of every row it reads (DRAM page locality: with
   // one 512 B segment per row per CTA the same kernel ran at 40 % of the HBM rate).
   const int slice = blockIdx.x * kDinoWarps + warp, group = blockIdx.y;
-  if (slice >= nslices) return;
+  // a warp past the last slice (K not a multiple of 8 slices) computes nothing but keeps the CTA's barriers
+  // balanced; its records are empty (max = -inf, sums = 0)
+  const bool active = slice < nslices;
+  const int nparts = (int)gridDim.x;              // merged records per sample = CTAs along K
   // this launch covers samples [b_begin, b_begin + b_count) (the whole batch, or one L2-sized wave)
   const int b_lo = b_begin + (int)(((long long)b_count * group) / ngroups);
   const int b_hi = b_begin + (int)(((long long)b_count * (group + 1)) / ngroups);
 
   const int col = slice * (32 * VEC) + lane * VEC;
-  const bool ok = !RAGGED || col < K;            // K % VEC == 0 is checked by the host
+  const bool ok = active && (!RAGGED || col < K);   // K % VEC == 0 is checked by the host
   const int colc = ok ? col : 0;                 // masked lanes read a valid address and ignore it
   float cen[NC], csum[NC];
 #pragma unroll
@@ -114,7 +163,7 @@ dino_fwd_partial(const T* __restrict__ student, const T* __restrict__ teacher,
   auto t_ptr = [&](int iq) { return tbase + (off + (size_t)((unsigned)(iq * B)) * row_bytes); };
   auto s_ptr = [&](int v) { return sbase + (off + (size_t)((unsigned)(v * B)) * row_bytes); };
   uint4 rt[2], rs[NCROPS];
-  if (b < b_hi) {
+  if (active && b < b_hi) {
 #pragma unroll
     for (int iq = 0; iq < 2; ++iq) rt[iq] = ld_stream_u4(t_ptr(iq));
 #pragma unroll
@@ -122,6 +171,11 @@ dino_fwd_partial(const T* __restrict__ student, const T* __restrict__ teacher,
   }
   off += step;   // `off` now addresses the warp's NEXT sample
   for (; b < b_hi; ++b) {
+    const int ci = (b - b_lo) % kChunk, cbuf = ((b - b_lo) / kChunk) & 1;
+    float* dst = &srec[cbuf][ci][warp][0];        // this warp's record of sample b
+   if (!active) {
+    if (lane < REC) dst[lane] = ((lane < 6 ? lane % 3 == 0 : (lane & 1) == 0)) ? -INFINITY : 0.f;
+   } else {
     const bool has_next = b + 1 < b_hi;
     // the register pipeline covers one iteration of latency; pull the sample after next into L2
     if (b + 2 < b_hi) {
@@ -131,8 +185,7 @@ dino_fwd_partial(const T* __restrict__ student, const T* __restrict__ teacher,
       for (int v = 0; v < NCROPS; ++v) prefetch_l2(s_ptr(v) + step);
     }
 
-    // partial record of this (sample, slice); lane 0 stores each entry as soon as it is final
-    float* dst = part + ((size_t)b * nslices + slice) * REC;
+    // partial record of this (sample, slice) in shared memory; lane 0 stores each entry as soon as it is final
     float zpart[2];
     float e[2][NC];  // teacher: first x (log2-domain logits), then exp2(x - max)
     // ---- teacher rows ------------------------------------------------------------------
@@ -212,6 +265,16 @@ dino_fwd_partial(const T* __restrict__ student, const T* __restrict__ teacher,
       if (lane == 16) dst[5] = mine;
     }
     off += step;
+   }
+    // ---- every kChunk samples (and after the last one): merge the 8 warps' records per sample ------------
+    // One barrier per chunk; the buffers alternate, and a buffer is rewritten only after the NEXT chunk's
+    // barrier, which every warp reaches after its merge of this chunk.
+    if (ci == kChunk - 1 || b + 1 == b_hi) {
+      __syncthreads();
+      if (warp <= ci)
+        merge_cta_records<NCROPS>(&srec[cbuf][warp][0][0],
+                                  part + ((size_t)(b - ci + warp) * nparts + blockIdx.x) * REC, lane);
+    }
   }
 
   // ---- column sums of this warp's samples (each warp owns its columns: no cross-warp reduction) ----
@@ -335,6 +398,9 @@ dino_finish(const float* __restrict__ part, int B, int nslices, float inv_ts, fl
   constexpr int REC = rec_floats(NCROPS);
   constexpr int NR = 2 + NCROPS;
   extern __shared__ __align__(16) float fin_smem[];
+  // launched with programmatic stream serialisation: the CTAs are scheduled while the streaming kernel
+  // drains and block here until it has completed and its writes are visible (a no-op for a plain launch)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if ((int)blockIdx.x >= nfin) {
     const int k = (((int)blockIdx.x - nfin) * 64 + (int)threadIdx.x) * 4;
     if (k < K) {                                        // K % 4 == 0 (checked by the host)
@@ -580,9 +646,26 @@ static bool launch_finish(const float* part, int B, int nslices, float inv_ts, f
   const int nfin = (B + 1) / 2;
   const int ncol = (K / 4 + 63) / 64;
   const float inv_norm = 1.f / ((float)(2 * NCROPS - 2) * (float)B);
-  kern<<<nfin + ncol, 64, smem, st>>>(part, B, nslices, inv_ts, row_stats, sample_loss, nfin, inv_norm, loss_out,
-                                      counter, colsum_part, ngroups, K, colsum_out, center, center_out,
-                                      (float)(2 * B), mom, om);
+  // programmatic dependent launch (LAFS_DINO_PDL=0 falls back to a plain launch): removes the launch gap
+  // between the streaming kernel and this short tail
+  static int pdl = -1;
+  if (pdl < 0) { const char* e = getenv("LAFS_DINO_PDL"); pdl = (e && atoi(e) == 0) ? 0 : 1; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nfin + ncol);
+  cfg.blockDim = dim3(64);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  const float count = (float)(2 * B);
+  if (cudaLaunchKernelEx(&cfg, kern, part, B, nslices, inv_ts, row_stats, sample_loss, nfin, inv_norm, loss_out, counter,
+                         colsum_part, ngroups, K, colsum_out, center, center_out, count, mom, om) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
   return true;
 }
 
@@ -604,11 +687,12 @@ static int launch_fwd(const void* student, const void* teacher, const float* cen
     dino_fwd_partial<T, NCROPS, true><<<grid, kDinoThreads, 0, st>>>(
         (const T*)student, (const T*)teacher, center, B, K, inv_ts * kLog2e, inv_tt * kLog2e,
         p.nslices, p.ngroups, part, colsum_part, 0, B, counter);
-  if (launch_finish<NCROPS>(part, B, p.nslices, inv_ts, row_stats, sample_loss, loss_out, counter, colsum_part,
+  const int nparts = (int)grid.x;   // the streaming kernel leaves ONE merged record per (sample, CTA along K)
+  if (launch_finish<NCROPS>(part, B, nparts, inv_ts, row_stats, sample_loss, loss_out, counter, colsum_part,
                             p.ngroups, K, colsum_out, center, center_out, mom, om, st))
     return check_launch("lafs_dino_fwd");
   dino_rows_finalize<NCROPS><<<(B + kFinalizeWarps - 1) / kFinalizeWarps, kFinalizeWarps * 32, 0, st>>>(
-      part, B, p.nslices, inv_ts, row_stats, sample_loss, 0, B);
+      part, B, nparts, inv_ts, row_stats, sample_loss, 0, B);
   const float inv_norm = 1.f / ((float)(2 * NCROPS - 2) * (float)B);
   dino_tail<<<(K + kDinoThreads - 1) / kDinoThreads, kDinoThreads, 0, st>>>(
       sample_loss, B, inv_norm, loss_out, colsum_part, p.ngroups, K, colsum_out, center, center_out,
@@ -702,8 +786,9 @@ static int launch_fused(const void* student, const void* teacher, const float* c
       dino_fwd_partial<T, NCROPS, true><<<grid, kDinoThreads, 0, st>>>(
           (const T*)student, (const T*)teacher, center, B, K, inv_ts * kLog2e, inv_tt * kLog2e,
           p.nslices, p.ngroups, part, cpart, b0, bc, counter);
+    const int nparts = (int)grid.x;
     if (p.nwaves == 1 &&
-        launch_finish<NCROPS>(part, B, p.nslices, inv_ts, row_stats, sample_loss, loss_out, counter, colsum_part,
+        launch_finish<NCROPS>(part, B, nparts, inv_ts, row_stats, sample_loss, loss_out, counter, colsum_part,
                               p.ngroups, K, colsum_out, center, center_out, mom, om, st)) {
       dim3 gb1((K / VEC + kDinoThreads - 1) / kDinoThreads, B);
       dino_bwd_kernel<T, NCROPS><<<gb1, kDinoThreads, 0, st>>>(
@@ -712,7 +797,7 @@ static int launch_fused(const void* student, const void* teacher, const float* c
       return check_launch("lafs_dino_fwd_bwd");
     }
     dino_rows_finalize<NCROPS><<<(bc + kFinalizeWarps - 1) / kFinalizeWarps, kFinalizeWarps * 32, 0, st>>>(
-        part, B, p.nslices, inv_ts, row_stats, sample_loss, b0, bc);
+        part, B, nparts, inv_ts, row_stats, sample_loss, b0, bc);
     dim3 gb((K / VEC + kDinoThreads - 1) / kDinoThreads, bc);
     dino_bwd_kernel<T, NCROPS><<<gb, kDinoThreads, 0, st>>>(
         (const T*)student, (const T*)teacher, center, row_stats, grad_out, B, K, inv_ts * kLog2e,

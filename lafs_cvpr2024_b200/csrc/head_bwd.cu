@@ -229,289 +229,12 @@ gemm_bwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   }
 }
 
-// ---- dW with the F.normalize Jacobian fused into the epilogue ---------------------------------------
-// One CTA owns 128 classes x ALL D columns (D <= 512 = the whole TMEM), so complete rows of dW_hat
-// leave one CTA and the Jacobian
-//     grad_w[c,:] = (dW_hat[c,:] - w_hat[c,:] * <w_hat[c,:], dW_hat[c,:]>) * inv_norm_w[c]
-// is applied by the same CTA while the rows are still in L2: phase A drains TMEM into grad_w
-// (256 KB per tile), phase B re-reads those lines from L2 one warp per row (coalesced, like
-// normalize_bwd_kernel) and overwrites them in place, while the tensor core already works on the
-// next tile.  HBM sees grad_w once (C*D*4 bytes) instead of the write + read + write of a GEMM
-// followed by normalize_bwd_kernel.  (Applying the Jacobian straight from TMEM -- a lane owns a
-// row there -- needs w_hat with one 16-byte piece per row per load, which is latency bound:
-// measured 139 us against 67 + 77 us for the two-kernel form at B=512, C=93431, D=512.)
-// Every class tile contracts against the SAME E_hat [B, D]; with K = B = 512 a tile moves 128 KB of
-// G and 512 KB of E_hat for 67 MFLOP, i.e. the L2 -> SM fill bounds the kernel.  CL CTAs of a
-// cluster therefore work on CL neighbouring class tiles in lock step and each fetches 1/CL of every
-// E_hat k block, multicast to the whole cluster (E_hat fill traffic / CL).
-// Warps: 0 TMA, 1 UMMA, 2..9 epilogue (phase A: two per TMEM lane quarter, half of the columns each;
-// phase B: 16 rows of the tile each).
-namespace dwf {
-constexpr int kBM = 128, kBK = 64;
-constexpr int kThreads = 320;
-constexpr int kStageA = kBM * kBK * 2;                  // 16 KB: two {64 m, 64 k} boxes
-constexpr int kPitch = 36;
-constexpr int kStageOut = 8 * 32 * kPitch * 4;          // 36,864 B: a [32 x 32] fp32 block per epilogue warp
-__host__ __device__ constexpr int stage_b(int D) { return D * kBK * 2; }   // D/64 boxes of 8 KB
-}  // namespace dwf
+// (A single-kernel dW with the F.normalize Jacobian applied in place from L2 by the same CTA -- full 128 x 512 rows
+//  in TMEM, optional E_hat multicast over clusters -- was built and measured in rounds 1-2 and removed: 157.8 us
+//  against 138.2 us for GEMM + reverse-order Jacobian pass at B=512, C=93431, D=512; its in-place phase is a chain of
+//  L2 round trips.  The form that won is dw_diag_kernel below.)
 
-struct DwParams {
-  int C, D, B;               // M = classes, N = D, K = batch
-  int m_tiles, kblocks, stages, tmem_cols, super_tiles;
-  const __nv_bfloat16* w_hat;
-  const float* inv_norm;
-  float* out;                // [C][D] fp32
-};
-
-template <int CL>
-__global__ void __launch_bounds__(dwf::kThreads, 1)
-dw_fused_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_e, const DwParams p) {
-  using namespace dwf;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int stage_bytes = kStageA + stage_b(p.D);
-  float* s_out = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + kStageOut / 4);
-  uint64_t* full = bars;                 // stages
-  uint64_t* empty = bars + p.stages;     // stages
-  uint64_t* acc_full = empty + p.stages; // 1
-  uint64_t* acc_empty = acc_full + 1;    // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    prefetch_tensormap(&tmap_g);
-    prefetch_tensormap(&tmap_e);
-    // a stage is refilled by every CTA of the cluster, so all CL consumers must have released it
-    for (int i = 0; i < p.stages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, CL); }
-    mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 8);
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-  tc_fence_before();
-  if (CL > 1) cluster_sync_all();
-  else __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const int nboxes = p.D / 64;
-  const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
-  const int cluster_id = blockIdx.x / CL, nclusters = gridDim.x / CL;
-  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
-  // lock step: every CTA of a cluster runs the same number of tiles (tiles past the end are all-zero)
-#define LAFS_DW_TILES for (int sup = cluster_id; sup < p.super_tiles; sup += nclusters)
-
-  if (warp == 0) {
-    if (lane == 0) {
-      uint32_t cnt = 0;
-      LAFS_DW_TILES {
-        const int tile = sup * CL + rank;
-        const int next_tile = (sup + nclusters) * CL + rank;   // its G columns come from HBM: pull them into L2 now
-        for (int kb = 0; kb < p.kblocks; ++kb, ++cnt) {
-          const int st = cnt % p.stages;
-          if (next_tile < p.m_tiles) {
-            tma_prefetch_l2_2d(&tmap_g, next_tile * kBM, kb * kBK);
-            tma_prefetch_l2_2d(&tmap_g, next_tile * kBM + 64, kb * kBK);
-          }
-          mbar_wait(empty + st, ((cnt / p.stages) & 1) ^ 1);
-          mbar_arrive_expect_tx(full + st, (uint32_t)stage_bytes);
-          uint8_t* da = smem + (size_t)st * stage_bytes;
-          uint8_t* db = da + kStageA;
-          tma_load_2d(da, &tmap_g, full + st, tile * kBM, kb * kBK);            // G^T: {64 classes, 64 batch rows}
-          tma_load_2d(da + 8192, &tmap_g, full + st, tile * kBM + 64, kb * kBK);
-          for (int q = rank; q < nboxes; q += CL) {                              // E_hat: {64 d, 64 batch rows}
-            if (CL > 1) tma_load_2d_mc(db + q * 8192, &tmap_e, full + st, q * 64, kb * kBK, kMask);
-            else tma_load_2d(db + q * 8192, &tmap_e, full + st, q * 64, kb * kBK);
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      uint32_t cnt = 0, tcnt = 0;
-      LAFS_DW_TILES {
-        mbar_wait(acc_empty, (tcnt & 1) ^ 1);      // the epilogue has drained the previous tile
-        tc_fence_after();
-        for (int kb = 0; kb < p.kblocks; ++kb, ++cnt) {
-          const int st = cnt % p.stages;
-          mbar_wait(full + st, (cnt / p.stages) & 1);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + (size_t)st * stage_bytes);
-          const uint32_t b_addr = a_addr + kStageA;
-          for (int n0 = 0; n0 < p.D; n0 += 256) {
-            const int nsub = p.D - n0 < 256 ? p.D - n0 : 256;
-            const uint32_t idesc = make_idesc_bf16(kBM, nsub, 1, 1);
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t da = make_desc_mn_sw128(a_addr + kk * 2048, 8192);
-              const uint64_t db = make_desc_mn_sw128(b_addr + (n0 / 64) * 8192 + kk * 2048, 8192);
-              mma_f16_ss(tmem_base + (uint32_t)n0, da, db, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
-            }
-          }
-          if (CL > 1) mma_commit_mc(empty + st, kMask);
-          else mma_commit(empty + st);
-        }
-        mma_commit(acc_full);
-        ++tcnt;
-      }
-    }
-  } else {
-    const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int ew = warp - 2;                    // 0..7
-    const int ncol = p.D / 2;                   // phase A columns of this warp: [half*ncol, (half+1)*ncol)
-    const int col_lo = half * ncol;
-    float* stage = s_out + ew * (32 * kPitch);
-    uint32_t tcnt = 0;
-    LAFS_DW_TILES {
-      const int tile = sup * CL + rank;
-      const int row_base = tile * kBM + quarter * 32;
-      mbar_wait(acc_full, tcnt & 1);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-      // ---- phase A: TMEM -> dW_hat rows in grad_w (transposed through shared memory so that a warp
-      // writes full 128-byte row segments); the lines stay in L2 for phase B ------------------------------
-#pragma unroll 1
-      for (int c0 = col_lo; c0 < col_lo + ncol; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(taddr + (uint32_t)c0, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(stage + lane * kPitch + j) =
-              make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                          __uint_as_float(v[j + 3]));
-        __syncwarp();
-#pragma unroll
-        for (int r8 = 0; r8 < 8; ++r8) {
-          const int rr = r8 * 4 + (lane >> 3), part = lane & 7;       // 8 lanes cover one 128-byte row segment
-          const float4 val = *reinterpret_cast<const float4*>(stage + rr * kPitch + part * 4);
-          if (row_base + rr < p.C)
-            *reinterpret_cast<float4*>(p.out + (size_t)(row_base + rr) * p.D + c0 + part * 4) = val;
-        }
-        __syncwarp();
-      }
-      // the accumulator is drained: the UMMAs of the next tile run under phase B
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_relaxed(acc_empty);
-      __threadfence_block();
-      asm volatile("bar.sync 1, 256;" ::: "memory");       // every row of the tile is written (8 epilogue warps)
-      // ---- phase B: F.normalize Jacobian in place, one warp per row (16 rows per warp), the row and
-      // its w_hat row read back coalesced from L2; kRowsInFlight rows in flight per warp (the phase is a
-      // chain of L2 round trips: 2 rows in flight measured 20 % of all stall samples on the first use) --------
-      constexpr int kRowsInFlight = 4;
-      const int tile_row0 = tile * kBM;
-#pragma unroll 1
-      for (int rp = 0; rp < 16; rp += kRowsInFlight) {
-        float4 gv[kRowsInFlight][2][2];
-        uint4 xv[kRowsInFlight][2];
-        int rows[kRowsInFlight];
-#pragma unroll
-        for (int u = 0; u < kRowsInFlight; ++u) {
-          rows[u] = tile_row0 + ew * 16 + rp + u;
-          if (rows[u] < p.C) {
-            const float* grow = p.out + (size_t)rows[u] * p.D;
-            const __nv_bfloat16* xrow = p.w_hat + (size_t)rows[u] * p.D;
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              const int c = q * 256 + lane * 8;
-              if (c < p.D) {
-                gv[u][q][0] = __ldcg(reinterpret_cast<const float4*>(grow + c));
-                gv[u][q][1] = __ldcg(reinterpret_cast<const float4*>(grow + c + 4));
-                xv[u][q] = ld_stream_u4(xrow + c);
-              }
-            }
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < kRowsInFlight; ++u) {
-          if (rows[u] < p.C) {                                        // warp-uniform
-            float xf[2][8];
-            float dot = 0.f;
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              const int c = q * 256 + lane * 8;
-              if (c < p.D) {
-                xf[q][0] = Half2Ops<__nv_bfloat16>::lo(xv[u][q].x); xf[q][1] = Half2Ops<__nv_bfloat16>::hi(xv[u][q].x);
-                xf[q][2] = Half2Ops<__nv_bfloat16>::lo(xv[u][q].y); xf[q][3] = Half2Ops<__nv_bfloat16>::hi(xv[u][q].y);
-                xf[q][4] = Half2Ops<__nv_bfloat16>::lo(xv[u][q].z); xf[q][5] = Half2Ops<__nv_bfloat16>::hi(xv[u][q].z);
-                xf[q][6] = Half2Ops<__nv_bfloat16>::lo(xv[u][q].w); xf[q][7] = Half2Ops<__nv_bfloat16>::hi(xv[u][q].w);
-                dot += gv[u][q][0].x * xf[q][0] + gv[u][q][0].y * xf[q][1] + gv[u][q][0].z * xf[q][2] + gv[u][q][0].w * xf[q][3] +
-                       gv[u][q][1].x * xf[q][4] + gv[u][q][1].y * xf[q][5] + gv[u][q][1].z * xf[q][6] + gv[u][q][1].w * xf[q][7];
-              }
-            }
-            dot = warp_sum(dot);
-            const float inv = __ldg(p.inv_norm + rows[u]);
-            float* orow = p.out + (size_t)rows[u] * p.D;
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              const int c = q * 256 + lane * 8;
-              if (c < p.D) {
-                float4 o0, o1;
-                o0.x = (gv[u][q][0].x - xf[q][0] * dot) * inv; o0.y = (gv[u][q][0].y - xf[q][1] * dot) * inv;
-                o0.z = (gv[u][q][0].z - xf[q][2] * dot) * inv; o0.w = (gv[u][q][0].w - xf[q][3] * dot) * inv;
-                o1.x = (gv[u][q][1].x - xf[q][4] * dot) * inv; o1.y = (gv[u][q][1].y - xf[q][5] * dot) * inv;
-                o1.z = (gv[u][q][1].z - xf[q][6] * dot) * inv; o1.w = (gv[u][q][1].w - xf[q][7] * dot) * inv;
-                st_stream_f4(orow + c, o0);
-                st_stream_f4(orow + c + 4, o1);
-              }
-            }
-          }
-        }
-      }
-      ++tcnt;
-    }
-  }
-#undef LAFS_DW_TILES
-  tc_fence_before();
-  if (CL > 1) cluster_sync_all();    // peers may still multicast into / arrive on this CTA's shared memory
-  else __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
-  }
-}
-
-template <int CL>
-static int launch_dw_fused(const CUtensorMap& ta, const CUtensorMap& tb, DwParams q, int smem, cudaStream_t st,
-                           bool* launched) {
-  *launched = false;
-  auto kern = dw_fused_kernel<CL>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  LAFS_REQUIRE(e == cudaSuccess, LAFS_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  q.super_tiles = (q.m_tiles + CL - 1) / CL;
-  cudaLaunchConfig_t cfg = {};
-  cfg.blockDim = dim3(dwf::kThreads);
-  cfg.dynamicSmemBytes = (size_t)smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  int nclusters = kNumSMs;
-  if (CL > 1) {
-    static int cached = -1, cached_smem = -1;           // once per process (see max_clusters)
-    if (cached < 0 || cached_smem != smem) {
-      cfg.gridDim = dim3(CL);
-      int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
-      cached = n; cached_smem = smem;
-    }
-    nclusters = cached;
-    if (nclusters < 1) return LAFS_OK;      // not launched: the caller falls back to a smaller cluster
-    if (nclusters * CL < (kNumSMs * 3) / 4) return LAFS_OK;   // too many SMs left idle by the cluster shape
-    if (nclusters * CL > kNumSMs) nclusters = kNumSMs / CL;
-  }
-  if (nclusters > q.super_tiles) nclusters = q.super_tiles;
-  cfg.gridDim = dim3(nclusters * CL);
-  e = cudaLaunchKernelEx(&cfg, kern, ta, tb, q);
-  LAFS_REQUIRE(e == cudaSuccess, LAFS_ERR_CUDA, "dw_fused_kernel launch: %s", cudaGetErrorString(e));
-  *launched = true;
-  return check_launch("lafs_head_bwd_weight(fused)");
-}
-
-// ---- EXPERIMENTAL (not yet measured on hardware): dW with the Jacobian's rank-one term on the tensor core ----
+// ---- dW with the Jacobian's rank-one term on the tensor core (the default dW path) ---------------------------------
 //   grad_w[c,:] = inv_norm_w[c] * ( dW_hat[c,:] - t[c] * w_hat[c,:] ),   t[c] = <w_hat[c,:], dW_hat[c,:]> = sum_b G[b,c]*cos[b,c]
 // t comes from the gradient kernel (HEAD_GRAD_T partials).  Per 128-class tile the correction is the product
 // (-diag(t)) [128 x 128] . W_hat_tile [128 x D]: two extra k blocks of the same GEMM, whose A operand (a
@@ -931,39 +654,6 @@ extern "C" int lafs_head_bwd_weight(const void* grad_bf16, long long ldg, const 
   rc = encode_bf16_2d(&tb, e_hat, (uint64_t)B, (uint64_t)D, (uint64_t)D * 2, 64, 64);                  // MN-major B: [K=B, N=D]
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  // The single-kernel form (dw_fused_kernel) is opt-in: measured on B200 at B=512, C=93431, D=512 it
-  // takes 157 us alone / 374 us per step against 144 us / 357 us for GEMM + reverse-order Jacobian pass
-  // (its in-place phase B is a chain of L2 round trips); at B=1024, C=205990 the two are equal.
-  const char* fused = getenv("LAFS_DW_FUSED");
-  const char* unfused = getenv("LAFS_DW_UNFUSED");
-  if (D <= 512 && fused && atoi(fused) != 0 && !(unfused && atoi(unfused) != 0)) {
-    // fused path: full rows in TMEM, Jacobian applied from L2 by the same CTA
-    DwParams q{};
-    q.C = C_local; q.D = D; q.B = B;
-    q.m_tiles = (C_local + 127) / 128;
-    q.kblocks = (B + 63) / 64;
-    q.tmem_cols = D <= 32 ? 32 : D <= 64 ? 64 : D <= 128 ? 128 : D <= 256 ? 256 : 512;
-    const int stage_bytes = dwf::kStageA + dwf::stage_b(D);
-    const int tail = dwf::kStageOut + 1024 /*align*/ + 256 /*barriers*/;
-    q.stages = (227 * 1024 - tail) / stage_bytes;
-    if (q.stages > 6) q.stages = 6;
-    LAFS_REQUIRE(q.stages >= 2, LAFS_ERR_ARG, "lafs_head_bwd_weight: D=%d leaves no room for a 2-stage pipeline", D);
-    q.w_hat = (const __nv_bfloat16*)w_hat; q.inv_norm = inv_norm_w; q.out = grad_w;
-    const int smem = q.stages * stage_bytes + tail;
-    int cl = 1;                                        // E_hat multicast width (LAFS_DW_CLUSTER: 1, 2 or 4)
-    if (const char* e = getenv("LAFS_DW_CLUSTER")) cl = atoi(e);
-    const int nboxes = D / 64;
-    bool launched = false;
-    if (cl >= 4 && nboxes % 4 == 0 && q.m_tiles >= 4) {
-      rc = launch_dw_fused<4>(ta, tb, q, smem, st, &launched);
-      if (rc || launched) return rc;
-    }
-    if (cl >= 2 && nboxes % 2 == 0 && q.m_tiles >= 2) {
-      rc = launch_dw_fused<2>(ta, tb, q, smem, st, &launched);
-      if (rc || launched) return rc;
-    }
-    return launch_dw_fused<1>(ta, tb, q, smem, st, &launched);
-  }
   GemmParams p{};
   p.M = C_local; p.N = D; p.K = B;
   p.m_tiles = (C_local + 127) / 128; p.n_tiles = (D + 255) / 256; p.splits = 1;
@@ -1056,7 +746,7 @@ extern "C" int lafs_embed_bwd_tokens(const void* grad_emb_bf16, const void* weig
   return launch_gemm<false>(ta, tb, p, (cudaStream_t)stream);
 }
 
-/* EXPERIMENTAL (not yet measured on hardware): lafs_head_bwd_weight with the Jacobian's rank-one term computed on
+/* lafs_head_bwd_weight with the Jacobian's rank-one term computed on
  * the tensor core from the per-class dots of lafs_head_grad_logits_t (tpart [tparts][ldt], tparts = 4*ceil(B/128)):
  * one GEMM, no normalize_bwd pass. */
 extern "C" int lafs_head_bwd_weight_t(const void* grad_bf16, long long ldg, const void* e_hat, const void* w_hat,

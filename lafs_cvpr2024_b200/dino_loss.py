@@ -155,22 +155,55 @@ class DINOLoss(nn.Module):
         if nbytes == 0:
             raise ValueError(f"unsupported DINO shape B={B} K={K} ncrops={self.ncrops}")
         ws = _workspace(dev, nbytes)
-        new_center = torch.empty(1, K, dtype=torch.float32, device=dev) if world == 1 else None
         m = float(self.center_momentum)
         temp = float(self.teacher_temp_schedule[epoch])
-        _lib.call("lafs_dino_fwd_bwd", s.data_ptr(), t.data_ptr(), c.data_ptr(), g.data_ptr(), B, K, self.ncrops,
-                  1.0 / self.student_temp, 1.0 / temp, _lib.dtype_code(s), loss.data_ptr(), row_stats.data_ptr(),
-                  colsum.data_ptr(), grad.data_ptr(), ws.data_ptr(), nbytes, _lib.ptr(new_center),
-                  float(np.float32(m)), float(np.float32(1.0 - m)), _lib.stream())
+        main = torch.cuda.current_stream()
+        ev = getattr(self, "_center_event", None)
+        if ev is not None:                       # the previous step's centre exchange (side stream) must have landed
+            main.wait_event(ev)
+            self._center_event = None
         if world == 1:
+            new_center = torch.empty(1, K, dtype=torch.float32, device=dev)
+            _lib.call("lafs_dino_fwd_bwd", s.data_ptr(), t.data_ptr(), c.data_ptr(), g.data_ptr(), B, K, self.ncrops,
+                      1.0 / self.student_temp, 1.0 / temp, _lib.dtype_code(s), loss.data_ptr(), row_stats.data_ptr(),
+                      colsum.data_ptr(), grad.data_ptr(), ws.data_ptr(), nbytes, _lib.ptr(new_center),
+                      float(np.float32(m)), float(np.float32(1.0 - m)), _lib.stream())
             self.center = new_center
-        else:
-            colsum = self._allreduce_colsum(colsum)
-            nc = torch.empty(1, K, dtype=torch.float32, device=dev)
-            _lib.call("lafs_center_ema", c.data_ptr(), colsum.data_ptr(), float(2 * B * world), float(np.float32(m)),
+            return loss, grad
+        # Several ranks: forward (+ column sums), then the centre exchange -- all-reduce of the [K] column sums
+        # (lafs_train.py:675) + centre EMA -- runs on a high-priority SIDE stream while the gradient pass (and
+        # whatever the caller enqueues next, e.g. the teacher EMA) runs on the main stream.  Nothing in this step
+        # needs the new centre (the loss and its gradient use the old one): the next forward waits on
+        # `_center_event`; a caller that reads `self.center` from another stream must do the same.
+        # (the fused entry point's workspace is at least as large as the forward-only one)
+        _lib.call("lafs_dino_fwd", s.data_ptr(), t.data_ptr(), c.data_ptr(), B, K, self.ncrops,
+                  1.0 / self.student_temp, 1.0 / temp, _lib.dtype_code(s), loss.data_ptr(), row_stats.data_ptr(),
+                  colsum.data_ptr(), ws.data_ptr(), nbytes, None, 0.0, 0.0, _lib.stream())
+        side = getattr(self, "_side", None)
+        if side is None or side.device != dev:
+            side = self._side = torch.cuda.Stream(device=dev, priority=-1)
+        side.wait_stream(main)
+        nc = torch.empty(1, K, dtype=torch.float32, device=dev)
+        with torch.cuda.stream(side):
+            summed = self._allreduce_colsum(colsum)
+            _lib.call("lafs_center_ema", c.data_ptr(), summed.data_ptr(), float(2 * B * world), float(np.float32(m)),
                       float(np.float32(1.0 - m)), K, nc.data_ptr(), _lib.stream())
-            self.center = nc
+            done = torch.cuda.Event()
+            done.record(side)
+        for tns in (c, colsum, nc, ws):
+            tns.record_stream(side)
+        _lib.call("lafs_dino_bwd", s.data_ptr(), t.data_ptr(), c.data_ptr(), row_stats.data_ptr(), g.data_ptr(), B, K,
+                  self.ncrops, 1.0 / self.student_temp, 1.0 / temp, _lib.dtype_code(s), grad.data_ptr(), _lib.stream())
+        self.center = nc
+        self._center_event = done
         return loss, grad
+
+    def join_center(self):
+        """Make the current stream wait for a centre exchange still running on the side stream."""
+        ev = getattr(self, "_center_event", None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+            self._center_event = None
 
     @torch.no_grad()
     def update_center(self, teacher_output):

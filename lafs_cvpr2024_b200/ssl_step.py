@@ -82,7 +82,8 @@ class GraphedSSLStep:
     embedded-token tensors.  The DINO centre is kept in a static buffer and updated in place at the
     end of the graph (the loss and its backward inside the graph still see the old centre, Q7)."""
 
-    def __init__(self, path: SSLHotPath, static_inputs: dict, epoch: int, momentum: float, overlap_ema=False, ema_ctas=444, fused_loss=True):
+    def __init__(self, path: SSLHotPath, static_inputs: dict, epoch: int, momentum: float, overlap_ema=False, ema_ctas=444,
+                 fused_loss=True, center=None):
         """overlap_ema: put the teacher EMA (as `ema_ctas` persistent CTAs) on a second captured stream
         so that it runs concurrently with the gather->embed / DINO kernels.  Measured on B200: between
         -3 % and +17 % step time depending on the box (the persistent CTAs halve the occupancy of the
@@ -92,7 +93,9 @@ class GraphedSSLStep:
         self.fused_loss = fused_loss
         self.ema_ctas = ema_ctas
         self.side = torch.cuda.Stream()
-        self.center = path.loss.center.detach().clone().contiguous()
+        # `center`: an existing static centre buffer to share (several graphs over different input buffers --
+        # e.g. the two halves of a double-buffered loader hand-off -- that advance ONE training state)
+        self.center = center if center is not None else path.loss.center.detach().clone().contiguous()
         self.graph = torch.cuda.CUDAGraph()
         self.out = {}
         # Warm-up outside capture (lazy init, workspaces) must not change training state: it runs with
@@ -126,12 +129,26 @@ class GraphedSSLStep:
         s_g, t_g, s_l = p.landmarks_and_embeddings(i["raw_g"], i["noise_g"], i["img_g"], i["raw_l"], i["noise_l"],
                                                    i["idx_l"], i["img_l"], refresh=not self.overlap_ema)
         loss, grad = p.loss_and_grad(i["student_out"], i["teacher_out"], epoch, fused=self.fused_loss)
-        self.center.copy_(p.loss.center)              # static centre buffer <- re-bound new centre
+        cside = getattr(p.loss, "_side", None) if getattr(p.loss, "_center_event", None) is not None else None
+        if cside is not None:
+            # several ranks: the centre exchange is running on the loss's side stream.  The static centre buffer
+            # is refreshed there too, but only after the gradient pass (which still reads the OLD centre from it)
+            # has finished on the main stream; the teacher EMA overlaps both.
+            after_bwd = torch.cuda.Event()
+            after_bwd.record(main)
+            with torch.cuda.stream(cside):
+                cside.wait_event(after_bwd)
+                self.center.copy_(p.loss.center)
+            p.loss._center_event = None
+        else:
+            self.center.copy_(p.loss.center)          # static centre buffer <- re-bound new centre
         p.loss.center = self.center
         if self.overlap_ema:
             main.wait_stream(self.side)
         else:
             p.ema_step(momentum)
+        if cside is not None:
+            main.wait_stream(cside)
         self.out = {"loss": loss.detach(), "grad_student": grad, "s_g": s_g, "t_g": t_g, "s_l": s_l}
 
     def replay(self):

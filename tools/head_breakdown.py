@@ -44,8 +44,11 @@ def main():
     nb = L.lafs_head_workspace_bytes(B, C, D)
     ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
     loss = torch.empty((), device="cuda"); lse2 = torch.empty(B, device="cuda"); go = torch.ones((), device="cuda")
-    ldg = (C + 7) // 8 * 8
+    from lafs_cvpr2024_b200.margin_head import _round8
+    ldg = _round8(C)
     G = torch.empty(B, ldg, dtype=torch.bfloat16, device="cuda")
+    ldt = (C + 31) // 32 * 32
+    tpart = torch.empty(4 * ((B + 127) // 128), ldt, device="cuda")
     nbb = L.lafs_head_bwd_workspace_bytes(B, C, D)
     wsb = torch.empty(nbb, dtype=torch.uint8, device="cuda")
     de = torch.empty(B, D, device="cuda"); dw = torch.empty(C, D, device="cuda")
@@ -58,6 +61,12 @@ def main():
         "loss": lambda: _lib.call("lafs_head_loss", stats.data_ptr(), lab.data_ptr(), None, 1.0, B, lse2.data_ptr(), loss.data_ptr(), st()),
         "grad_logits": lambda: _lib.call("lafs_head_grad_logits", e_hat.data_ptr(), w_hat.data_ptr(), lab.data_ptr(), None, 1.0, B, C, D, 0,
                                          64.0, 0.4, 0, lse2.data_ptr(), go.data_ptr(), 64.0 / B, G.data_ptr(), ldg, st()),
+        "grad_logits_t": lambda: _lib.call("lafs_head_grad_logits_t", e_hat.data_ptr(), w_hat.data_ptr(), lab.data_ptr(), None, 1.0, B, C, D,
+                                           0, 64.0, 0.4, 0, lse2.data_ptr(), go.data_ptr(), 64.0 / B, G.data_ptr(), ldg,
+                                           tpart.data_ptr(), ldt, st()),
+        "bwd_weight_t(dW, jac on TC)": lambda: _lib.call("lafs_head_bwd_weight_t", G.data_ptr(), ldg, e_hat.data_ptr(), w_hat.data_ptr(),
+                                                         inv_w.data_ptr(), tpart.data_ptr(), tpart.shape[0], ldt, B, C, D,
+                                                         dw.data_ptr(), st()),
         "bwd_embed(dE)": lambda: _lib.call("lafs_head_bwd_embed", G.data_ptr(), ldg, w_hat.data_ptr(), B, C, D, de.data_ptr(),
                                            wsb.data_ptr(), nbb, st()),
         "bwd_weight(dW+jac)": lambda: _lib.call("lafs_head_bwd_weight", G.data_ptr(), ldg, e_hat.data_ptr(), w_hat.data_ptr(),
@@ -70,9 +79,11 @@ def main():
     sweeps = {
         "normalize_w": [{}], "normalize_e": [{}], "loss": [{}],
         "fwd_stats+merge": [{"LAFS_HEAD_1SM": "0"}, {"LAFS_HEAD_1SM": "1"}],
-        "grad_logits": [{"LAFS_HEAD_1SM": "0"}, {"LAFS_HEAD_1SM": "1"}],
+        "grad_logits": [{"LAFS_HEAD_1SM": "0"}, {"LAFS_HEAD_1SM": "1"}, {"LAFS_HEAD_DEBUG": "1"}],
         "bwd_embed(dE)": [{"LAFS_DE_CLUSTER": "4"}, {"LAFS_DE_CLUSTER": "2"}, {"LAFS_DE_CLUSTER": "1"}],
-        "bwd_weight(dW+jac)": [{}, {"LAFS_DW_FUSED": "1", "LAFS_DW_CLUSTER": "1"}, {"LAFS_DW_FUSED": "1", "LAFS_DW_CLUSTER": "2"}],
+        "bwd_weight(dW+jac)": [{}],
+        "grad_logits_t": [{}, {"LAFS_HEAD_DEBUG": "1"}],          # DEBUG=1: G stores skipped (what do the stores cost?)
+        "bwd_weight_t(dW, jac on TC)": [{}],
     }
     fl = 2.0 * B * C * D
     for k, fn in calls.items():
@@ -121,10 +132,7 @@ def main():
             for a in env:
                 os.environ.pop(a, None)
 
-    envs = [{}, {"LAFS_HEAD_1SM": "1"}, {"LAFS_DE_CLUSTER": "1"}, {"LAFS_DW_FUSED": "1"},
-            {"LAFS_DW_FUSED": "1", "LAFS_DW_CLUSTER": "2"}]
-    if os.environ.get("LAFS_TEST_EXPERIMENTAL", "0") != "0":
-        envs.append({"LAFS_DW_DIAG": "1"})        # experimental: Jacobian of dW on the tensor core
+    envs = [{}, {"LAFS_HEAD_1SM": "1"}, {"LAFS_DW_DIAG": "0"}]
     for env in envs:
         tag = "step_graph[" + ",".join(f"{a[5:]}={b}" for a, b in env.items()) + "]_us"
         res[tag] = graph_us(env)
