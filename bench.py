@@ -76,13 +76,15 @@ def vit_b_param_shapes(out_dim=OUT_DIM):
 
 
 def set_workload(name):
-    global B_PER_GPU, N_LOCAL, DIM, VIT, WL_NAME
+    global B_PER_GPU, N_LOCAL, DIM, VIT, WL_NAME, WL_KEY
+    WL_KEY = name
     w = WORKLOADS[name]
     B_PER_GPU, N_LOCAL, VIT, WL_NAME = w["B"], w["L"], w["vit"], w["name"]
     DIM = 768 if VIT == "B" else 384
 
 
-VIT, WL_NAME = "B", WORKLOADS["cfg1"]["name"]
+VIT, WL_NAME, WL_KEY = "B", WORKLOADS["cfg1"]["name"], "cfg1"
+_ORIG_AFFINITY = os.sched_getaffinity(0)
 
 
 def ncu_traffic(report):
@@ -141,6 +143,29 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local):
+    """Pins this process (and hence the first-touch placement of the pinned host buffers allocated next) to
+    the CPUs of the NUMA node the GPU hangs off: with several ranks per box the H2D copies then read local
+    memory instead of crossing the socket interconnect.  Returns a short description for the JSON line."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        addr = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{addr}/numa_node").read().strip())
+        if node < 0:
+            return f"gpu {addr}: no NUMA node reported"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"gpu {addr}: node {node} has no CPU this process may use"
+        os.sched_setaffinity(0, cpus)
+        return f"gpu {addr} -> NUMA node {node} ({len(cpus)} cpus)"
+    except Exception as e:
+        return "unbound (%s)" % str(e).splitlines()[0][:60]
+
+
 def make_host_inputs(B, seed, uint8):
     """Per-step host-side inputs: the data loader's augmented views and the CPU-generator noise /
     indices (ViT_face.py:1361,1366).  Pinned.
@@ -170,6 +195,9 @@ def make_device_state(B, seed, dev):
         "raw_l": torch.randn(L * B, 2 * N_LAND, device=dev, generator=g),
         "student_out": torch.randn((L + 2) * B, OUT_DIM, device=dev, generator=g).bfloat16(),
         "teacher_out": torch.randn(2 * B, OUT_DIM, device=dev, generator=g).bfloat16(),
+        # gradients of the student's embedded tokens, as the (out-of-path) transformer backward would deliver them
+        "grad_s_g": (torch.randn(2 * B, N_LAND, DIM, device=dev, generator=g) * 0.01).bfloat16(),
+        "grad_s_l": (torch.randn(L * B, KEEP_LOCAL, DIM, device=dev, generator=g) * 0.01).bfloat16(),
     }
     shapes = vit_param_shapes(VIT)
     st["student_params"] = [torch.randn(*s, device=dev, generator=g) * 0.02 for s in shapes]
@@ -199,6 +227,7 @@ def run_ours(args):
     if _lib.lib().lafs_device_ok() != 1:
         raise SystemExit("bench.py needs a compute-capability 10.x device (B200)")
 
+    numa = bind_to_gpu_numa_node(local)
     B, L = B_PER_GPU, N_LOCAL
     host = make_host_inputs(B, 1000 + rank, uint8=True)
     host_f32 = make_host_inputs(B, 1000 + rank, uint8=False)
@@ -222,7 +251,7 @@ def run_ours(args):
             path.loss.enable_peer_exchange(enabled=False)
             centre_exchange = "nccl all_reduce (peer exchange unavailable: %s)" % str(e).splitlines()[0][:80]
     sched = 0.996 + 0.5 * (1 - 0.996) * (1 - np.cos(np.pi * np.arange(100000) / 100000))  # utils.py:187-198
-    names = ["landmark+gather_embed", "dino_fwd+center", "dino_bwd", "ema"]
+    names = ["landmark+gather_embed", "patch_embed_bwd(student)", "dino_fwd+center", "dino_bwd", "ema"]
 
     def step(inp, it, evs=None):
         def mark(i):
@@ -230,16 +259,18 @@ def run_ours(args):
                 evs[i].record()
         mark(0)
         path.landmarks_and_embeddings(st["raw_g"], inp["noise_g"], inp["img_g"], st["raw_l"], inp["noise_l"],
-                                      inp["idx_l"], inp["img_l"])
+                                      inp["idx_l"], inp["img_l"], keep_tokens=True)
         mark(1)
+        path.student_embed_backward(st["grad_s_g"], st["grad_s_l"])
+        mark(2)
         s = st["student_out"].requires_grad_(True)
         s.grad = None
         loss = path.loss(s, st["teacher_out"], it % 41)
-        mark(2)
-        loss.backward()
         mark(3)
-        path.ema_step(sched[it])
+        loss.backward()
         mark(4)
+        path.ema_step(sched[it])
+        mark(5)
         return loss
 
     def barrier():
@@ -249,7 +280,7 @@ def run_ours(args):
 
     def timed(fn, steps, per_kernel=False):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(steps)] if per_kernel else None
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(steps)] if per_kernel else None
         barrier()
         e0.record()
         for i in range(steps):
@@ -262,7 +293,7 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         parts = None
         if per_kernel:
-            parts = [float(np.mean([evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(steps)])) for j in range(4)]
+            parts = [float(np.mean([evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(steps)])) for j in range(5)]
         return float(t.item()), parts
 
     # ---- device-resident arm --------------------------------------------------------------
@@ -274,7 +305,8 @@ def run_ours(args):
     ms_total, parts = timed(lambda i, ev: step(dev_in, args.warmup + i, ev), args.steps, per_kernel=True)
     # the same 11-kernel step captured into ONE CUDA graph and replayed (static device buffers):
     # this is the device-resident headline `value`; the eager run above gives the per-kernel split
-    ginp = dict(dev_in, raw_g=st["raw_g"], raw_l=st["raw_l"], student_out=st["student_out"], teacher_out=st["teacher_out"])
+    ginp = dict(dev_in, raw_g=st["raw_g"], raw_l=st["raw_l"], student_out=st["student_out"], teacher_out=st["teacher_out"],
+                grad_s_g=st["grad_s_g"], grad_s_l=st["grad_s_l"])
     graphed = GraphedSSLStep(path, ginp, epoch=3, momentum=float(sched[1000]))
     for _ in range(3):
         graphed.replay()
@@ -291,11 +323,23 @@ def run_ours(args):
     # region (copy stream, double-buffered, like the reference's pin_memory + non_blocking loader
     # hand-off, lafs_train.py:521) and the loss is read back to the host every step ------------------
     def run_e2e(hbuf):
+        """Per step: the HOST inputs are copied from pinned memory on a copy stream into one of two static device
+        input sets (double buffered, like the reference's pin_memory + non_blocking loader hand-off,
+        lafs_train.py:521), the step's CUDA graph over that set is replayed (GraphedSSLStep: the public call), and
+        the loss is copied back to pinned host memory; the host inspects the loss of step i-2 (the reference's
+        isfinite check, lafs_train.py:585, lagging two steps) so that it never drains the pipeline."""
         h2d = sum(v.numel() * v.element_size() for v in hbuf.values())
-        bufs = [{k: torch.empty_like(v, device=dev) for k, v in hbuf.items()} for _ in range(2)]
+        shared = dict(raw_g=st["raw_g"], raw_l=st["raw_l"], student_out=st["student_out"], teacher_out=st["teacher_out"],
+                      grad_s_g=st["grad_s_g"], grad_s_l=st["grad_s_l"])
+        bufs = [dict({k: v.to(dev) for k, v in hbuf.items()}, **shared) for _ in range(2)]
+        center = path.loss.center.detach().clone().contiguous()
+        graphs = [GraphedSSLStep(path, bufs[b], epoch=3, momentum=float(sched[1000]), center=center) for b in range(2)]
         copy_stream = torch.cuda.Stream(device=dev)
         ready = [torch.cuda.Event() for _ in range(2)]
         free = [torch.cuda.Event() for _ in range(2)]
+        ring = 4
+        loss_host = torch.zeros(ring, dtype=torch.float32).pin_memory()
+        loss_ev = [torch.cuda.Event() for _ in range(ring)]
 
         def upload(i):
             b = i & 1
@@ -306,18 +350,24 @@ def run_ours(args):
                 ready[b].record(copy_stream)
 
         def loop(nsteps):
+            main = torch.cuda.current_stream()
             for b in range(2):
                 free[b].record()
             upload(0)
-            last = 0.0
             for i in range(nsteps):
                 if i + 1 < nsteps:
                     upload(i + 1)
-                torch.cuda.current_stream().wait_event(ready[i & 1])
-                loss = step(bufs[i & 1], args.warmup + i)
+                main.wait_event(ready[i & 1])
+                loss = graphs[i & 1].replay()
                 free[i & 1].record()
-                last = float(loss.item())          # device -> host read of the step's result
-            return last
+                loss_host[i % ring].copy_(loss, non_blocking=True)      # device -> host read of the step's result
+                loss_ev[i % ring].record()
+                if i >= 2:
+                    loss_ev[(i - 2) % ring].synchronize()
+                    if not np.isfinite(float(loss_host[(i - 2) % ring])):
+                        raise SystemExit("bench.py: non-finite loss in the end-to-end loop")
+            torch.cuda.synchronize()
+            return float(loss_host[(nsteps - 1) % ring])
 
         loop(3)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -329,6 +379,9 @@ def run_ours(args):
         t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        path.loss.center = center.clone()
+        del graphs, bufs
+        torch.cuda.empty_cache()
         return float(t.item()), h2d
 
     ms_e2e, h2d = run_e2e(host)
@@ -356,8 +409,12 @@ def run_ours(args):
     tok_out = (2 * 2 * B * 196 + L * B * 36) * DIM * 2
     alg = {
         # images + landmarks in, bf16 tokens of both models out (e_img = 1 byte)
-        "landmark+gather_embed": {"bytes": (2 + L) * B * (3 * 112 * 112 * 1) + 2 * B * 196 * 8 + L * B * 36 * 8 + tok_out,
+        "landmark+gather_embed": {"bytes": (2 + L) * B * (3 * 112 * 112 * 1) + 2 * B * 196 * 8 + L * B * 36 * 8 + tok_out
+                                  + (2 * B * 196 + L * B * 36) * 192 * 2,       # + the bf16 tokens kept for the backward
                                   "flops": 2.0 * 192 * DIM * (2 * 2 * B * 196 + L * B * 36), "write_bytes": tok_out},
+        # student weight/bias gradient: read dY (bf16) and the kept bf16 tokens once, 2*M*193*dim flops
+        "patch_embed_bwd(student)": {"bytes": (2 * B * 196 + L * B * 36) * (DIM * 2 + 192 * 2) + DIM * 193 * 4,
+                                     "flops": 2.0 * 193 * DIM * (2 * B * 196 + L * B * 36)},
         "dino_fwd+center": {"bytes": (nc + 2) * B * K * 2 + 8 * K},
         "dino_bwd": {"bytes": (2 * nc + 2) * B * K * 2},
         "ema": {"bytes": 12 * nparam},
@@ -375,9 +432,8 @@ def run_ours(args):
     kernels["landmark+gather_embed(fp32 images)"] = {
         "ms": round(parts_f32[0], 5), "alg_bytes": b32, "GBps": round(b32 / parts_f32[0] / 1e6, 1),
         "frac_hbm": round(b32 / parts_f32[0] / 1e6 / pk["hbm"], 4)}
-    kernels["landmark+gather_embed"]["note"] = ("write-dominated: %.0f MB of bf16 tokens out; a pure-write stream on this "
-                                                "part measures 3.9 TB/s (tools/bw_probe.py), i.e. >= %.3f ms"
-                                                % (tok_out / 1e6, tok_out / 3.9e9))
+    kernels["landmark+gather_embed"]["note"] = ("bound = max(HBM, TC): %.0f MB of bf16 tokens out; pure-write streams on this part "
+                                                "measure 6.2-6.9 TB/s (tools/wbw_probe.cu, profiles/r02_wbw_probe.txt)" % (tok_out / 1e6))
     # the DINO loss as a whole (north star: ">= 70 % HBM roofline on the DINO loss"): forward + centre + backward
     dms = kernels["dino_fwd+center"]["ms"] + kernels["dino_bwd"]["ms"]
     dby = alg["dino_fwd+center"]["bytes"] + alg["dino_bwd"]["bytes"]
@@ -396,16 +452,19 @@ def run_ours(args):
                    "parallelism": f"dp{world}", "centre_exchange": centre_exchange},
         "e2e": {"value": round(faces / (ms_e2e / args.steps / 1e3), 1), "unit": "faces/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 5),
-                "transport": "uint8 pixels + fp32 noise + int64 indices from pinned memory on a copy stream (double "
-                             "buffered); ToTensor/Normalize fused into the gather kernel"},
+                "transport": "uint8 pixels + fp32 noise + int64 indices from pinned memory on a copy stream into two static "
+                             "input sets; one CUDA-graph replay per step (GraphedSSLStep); loss copied to pinned host memory "
+                             "every step and checked two steps later; ToTensor/Normalize fused into the gather kernel",
+                "host_numa": numa},
         "e2e_fp32_images": {"value": round(faces / (ms_e2e_f32 / args.steps / 1e3), 1), "unit": "faces/s",
-                            "h2d_bytes_per_step": h2d_f32, "ms_per_step": round(ms_e2e_f32 / args.steps, 5),
+                            "h2d_bytes_per_step": h2d_f32, "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e_f32 / args.steps, 5),
                             "transport": "the reference's fp32 normalised image tensors (PCIe-bound)"},
         "value_fp32_images": round(faces / (ms_total_f32 / args.steps / 1e3), 1),
         "value_eager_launches": round(faces / (ms_step_eager / 1e3), 1),
-        "launch": "value: the step's 11 kernels replayed as one CUDA graph (lafs_cvpr2024_b200.ssl_step.GraphedSSLStep); "
+        "launch": "value: the step's 15 kernels replayed as one CUDA graph (lafs_cvpr2024_b200.ssl_step.GraphedSSLStep); "
                   "value_eager_launches / kernels / e2e: the same kernels launched one by one from Python",
-        "gpu_launches": 11,   # 2 landmark, 3 weight prep, 2 gather-embed, 2 dino fwd (+centre), 1 dino bwd, 1 ema
+        # 2 landmark, 3 weight prep, 2 gather-embed, 2 x (dW GEMM + reduce/un-permute), 2 dino fwd (+centre), 1 dino bwd, 1 ema
+        "gpu_launches": 15,
         "clocks": clocks,
         "roofline": {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["GBps"], "peak": pk["hbm"], "unit": "GB/s",
                      "frac": kernels[dom]["frac_hbm"], "alg_bytes": kernels[dom]["alg_bytes"],
@@ -642,7 +701,16 @@ def cpu_port_run(sample_faces, threads, reps=1):
 
 
 def cpu_baseline():
-    """cpu_baseline leg of our own line (rank 0, N = 1): a short run of the reference arm."""
+    """cpu_baseline leg of our own line (rank 0, N = 1): a short run of the reference arm, in a fresh process
+    with the original CPU affinity (this process is pinned to the GPU's NUMA node for the end-to-end loop)."""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                            "--config", WL_KEY], capture_output=True, text=True, timeout=900,
+                           preexec_fn=lambda: os.sched_setaffinity(0, _ORIG_AFFINITY),
+                           env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+        return json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])["cpu_baseline"]
+    except Exception:
+        pass                                  # fall through: run it here
     if _reference_available():
         sec, info = cpu_reference_run(steps=2, warmup=1, budget_s=25.0)
     else:

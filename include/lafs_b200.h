@@ -224,6 +224,13 @@ LAFS_API int lafs_embed_weight_prep(const float* weight, const float* bias, int 
 LAFS_API int lafs_gather_embed_fwd(const void* imgs, int in_dtype, float in_scale, float in_shift, const float* theta,
                                    const void* w_perm_bf16, const float* bias, void* out0, void* out1, int out_dtype,
                                    int Bv, int H, int W, int n, int dim, int n_models, lafs_stream_t stream);
+/* Training form: additionally keeps the gathered tokens for the weight gradient, bf16 [Bv*n, 208] in the kernel's K
+ * order (k = c*64 + j*8 + i); the kernel writes columns 0..191 only -- the caller sets column 192 to 1 and columns
+ * 193..207 to 0 ONCE (the ones column yields the bias gradient in the same GEMM).  tokens_perm_out may be NULL. */
+LAFS_API int lafs_gather_embed_fwd_save(const void* imgs, int in_dtype, float in_scale, float in_shift, const float* theta,
+                                        const void* w_perm_bf16, const float* bias, void* out0, void* out1, int out_dtype,
+                                        int Bv, int H, int W, int n, int dim, int n_models, void* tokens_perm_out,
+                                        lafs_stream_t stream);
 
 /* Backward of patch_to_embedding (the training path of the fused kernel; the reference gets it from
  * autograd through nn.Linear, ViT_face.py:760-761 / lafs_train.py:544): two tcgen05 GEMMs over the
@@ -233,6 +240,13 @@ LAFS_API int lafs_gather_embed_fwd(const void* imgs, int in_dtype, float in_scal
 LAFS_API size_t lafs_embed_bwd_workspace_bytes(int M, int dim);
 LAFS_API int lafs_embed_bwd_weight(const void* grad_emb_bf16, const void* tokens_bf16, int M, int dim, float* grad_w,
                                    void* workspace, size_t workspace_bytes, lafs_stream_t stream);
+/* grad_w [dim,192] ('(p1 p2 c)' order) and grad_b [dim] (may be NULL) of patch_to_embedding from the tokens
+ * lafs_gather_embed_fwd_save kept ([M,208], ones column included): ONE split-K tcgen05 GEMM grad_emb^T . tokens plus a
+ * [dim,193] reduce / un-permute kernel -- no re-gather, no fp32 token tensor, no separate column-sum pass for the
+ * bias (lafs_train.py:600 through ViT_face.py:761).  accumulate != 0 adds to grad_w / grad_b (several view groups). */
+LAFS_API int lafs_embed_bwd_weight_perm(const void* grad_emb_bf16, const void* tokens_perm_bf16, int M, int dim, float* grad_w,
+                                        float* grad_b, int accumulate, void* workspace, size_t workspace_bytes,
+                                        lafs_stream_t stream);
 LAFS_API int lafs_embed_bwd_tokens(const void* grad_emb_bf16, const void* weight_bf16, int M, int dim,
                                    float* grad_tokens, lafs_stream_t stream);
 

@@ -16,6 +16,7 @@ F32, BF16, F16, U8 = 0, 1, 2, 3
 LAYOUT_MOSAIC, LAYOUT_TOKENS = 0, 1
 COORD_DIV, COORD_RECIP = 0, 1
 EMA_CHUNK = 16384
+TOK_LD = 208          # row pitch of the saved-token tensor (lafs_gather_embed_fwd_save)
 
 _p, _i, _f, _z, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_int64
 
@@ -38,6 +39,8 @@ SIGNATURES = {
     "lafs_gather_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "lafs_embed_weight_prep": (_i, [_p, _p, _i, _p, _p, _p]),
     "lafs_gather_embed_fwd": (_i, [_p, _i, _f, _f, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "lafs_gather_embed_fwd_save": (_i, [_p, _i, _f, _f, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "lafs_embed_bwd_weight_perm": (_i, [_p, _p, _i, _i, _p, _p, _i, _p, _z, _p]),
     "lafs_normalize_rows": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "lafs_head_workspace_bytes": (_z, [_i, _i, _i]),
     "lafs_head_fwd": (_i, [_p, _p, _p, _p, _f, _i, _i, _i, _i, _f, _f, _i, _p, _p, _z, _p]),

@@ -691,9 +691,61 @@ static int embed_bwd_splits(int M, int dim) {
   return s;
 }
 
+constexpr int kTokLd = 208;   // row pitch of the saved-token tensor (patch_embed.cu): 192 features, a ones column, 15 zeros
+
 extern "C" size_t lafs_embed_bwd_workspace_bytes(int M, int dim) {
   if (M <= 0 || dim <= 0) return 0;
-  return (size_t)embed_bwd_splits(M, dim) * dim * 192 * sizeof(float);
+  return (size_t)embed_bwd_splits(M, dim) * dim * kTokLd * sizeof(float);
+}
+
+// sum of the split-K partials [splits][dim][208] -> grad_w [dim][192] in the reference's feature order
+// ((i*8+j)*3 + c  <-  kernel order c*64 + j*8 + i) and grad_b [dim] (the ones column, k = 192)
+__global__ void embed_dw_unpermute_kernel(const float* __restrict__ part, int splits, int dim, float* __restrict__ grad_w,
+                                          float* __restrict__ grad_b, int accumulate) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= dim * 193) return;
+  const int d = idx / 193, k = idx - d * 193;
+  float acc = 0.f;
+  for (int s = 0; s < splits; ++s) acc += part[((size_t)s * dim + d) * kTokLd + k];
+  if (k == 192) {
+    if (grad_b != nullptr) grad_b[d] = accumulate ? grad_b[d] + acc : acc;
+    return;
+  }
+  const int c = k >> 6, j = (k >> 3) & 7, i = k & 7;
+  float* o = grad_w + (size_t)d * 192 + (i * 8 + j) * 3 + c;
+  *o = accumulate ? *o + acc : acc;
+}
+
+extern "C" int lafs_embed_bwd_weight_perm(const void* grad_emb_bf16, const void* tokens_perm_bf16, int M, int dim, float* grad_w,
+                                          float* grad_b, int accumulate, void* workspace, size_t workspace_bytes,
+                                          lafs_stream_t stream) {
+  if (int brc = lafs::bind_device_of(grad_emb_bf16)) return brc;
+  LAFS_REQUIRE(grad_emb_bf16 && tokens_perm_bf16 && grad_w && workspace, LAFS_ERR_ARG, "lafs_embed_bwd_weight_perm: null pointer");
+  LAFS_REQUIRE(M > 0 && dim > 0 && dim % 8 == 0, LAFS_ERR_ARG, "lafs_embed_bwd_weight_perm: M=%d dim=%d (dim must be a multiple of 8)", M, dim);
+  LAFS_REQUIRE((((uintptr_t)grad_emb_bf16 | (uintptr_t)tokens_perm_bf16 | (uintptr_t)workspace) & 15u) == 0, LAFS_ERR_ARG,
+               "lafs_embed_bwd_weight_perm: pointers must be 16-byte aligned");
+  const int splits = embed_bwd_splits(M, dim);
+  const size_t need = (size_t)splits * dim * kTokLd * sizeof(float);
+  LAFS_REQUIRE(workspace_bytes >= need, LAFS_ERR_WORKSPACE, "lafs_embed_bwd_weight_perm: workspace %zu < %zu", workspace_bytes, need);
+  CUtensorMap ta, tb;
+  int rc = encode_bf16_2d(&ta, grad_emb_bf16, (uint64_t)M, (uint64_t)dim, (uint64_t)dim * 2, 64, 64);     // MN-major A: [K=M, dim]
+  if (rc) return rc;
+  rc = encode_bf16_2d(&tb, tokens_perm_bf16, (uint64_t)M, kTokLd, kTokLd * 2, 64, 64);                    // MN-major B: [K=M, 208]
+  if (rc) return rc;
+  GemmParams p{};
+  p.M = dim; p.N = kTokLd; p.K = M;
+  p.m_tiles = (dim + 127) / 128; p.n_tiles = 1;
+  p.kblocks_total = (M + 63) / 64;
+  p.kblocks_per_split = (p.kblocks_total + splits - 1) / splits;
+  p.splits = (p.kblocks_total + p.kblocks_per_split - 1) / p.kblocks_per_split;
+  p.out = (float*)workspace; p.ldo = kTokLd; p.split_stride = (long long)dim * kTokLd;
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = launch_gemm<true>(ta, tb, p, st);
+  if (rc) return rc;
+  const int total = dim * 193;
+  embed_dw_unpermute_kernel<<<(total + 255) / 256, 256, 0, st>>>((const float*)workspace, p.splits, dim, grad_w, grad_b,
+                                                                  accumulate ? 1 : 0);
+  return check_launch("lafs_embed_bwd_weight_perm");
 }
 
 extern "C" int lafs_embed_bwd_weight(const void* grad_emb_bf16, const void* tokens_bf16, int M, int dim, float* grad_w,

@@ -34,6 +34,8 @@ using namespace umma;
 namespace pe {
 constexpr int kH = 112, kW = 112, kC = 3;
 constexpr int kFeat = 192;                         // 3 * 8 * 8
+constexpr int kTokLd = 208;                        // row pitch of the saved-token tensor: 192 features + a ones column
+                                                   // (bias gradient) + 15 zero columns (16-byte row alignment)
 constexpr int kMaxTok = 208;                       // largest UMMA N (196 landmarks -> N_pad 208)
 constexpr int kTokRows = 200;                      // token rows owned per chunk (25 x 8); a UMMA with
                                                    // N_pad = 208 also reads 8 rows of the NEXT region:
@@ -75,6 +77,8 @@ struct EmbedParams {
   const float* theta;       // [Bv, n, 2]
   const float* bias;        // [n_models * dim]
   void* out[2];             // per model: [Bv, n, dim] bf16 or fp32
+  __nv_bfloat16* tok_out;   // optional: the gathered tokens, bf16 [Bv*n, kTokLd] in the kernel's K order (c*64+j*8+i),
+                            //   kept for the weight-gradient GEMM of the training path (columns >= 192 are the caller's)
   int Bv, n, n_pad, dim, n_models;
   int gfaces;               // faces whose tokens share one tile / one pass over the weights (G*n <= 200)
   int ngroups;              // ceil(Bv / gfaces)
@@ -102,7 +106,7 @@ __device__ __forceinline__ float raw_pixel(const uint8_t* plane, int idx) { retu
 template <typename InT, int JB>
 __device__ __forceinline__ void gather_plane(const InT* __restrict__ plane, uint8_t* __restrict__ tok,
                                              const float* __restrict__ th, int n, int row0, int gt, float a_in,
-                                             float b_in, float pad, int debug) {
+                                             float b_in, float pad, int debug, __nv_bfloat16* __restrict__ tok_g) {
   using namespace pe;
   constexpr int NB = 8 / JB;                               // items per token
   for (int item = gt; item < ((debug & 2) ? 0 : NB * n); item += kGatherThreads) {
@@ -165,6 +169,8 @@ __device__ __forceinline__ void gather_plane(const InT* __restrict__ plane, uint
         pk.z = Half2Ops<__nv_bfloat16>::pack(o[4], o[5]);
         pk.w = Half2Ops<__nv_bfloat16>::pack(o[6], o[7]);
         *reinterpret_cast<uint4*>(tok + sw128_offset(row0 + t, j * 8)) = pk;
+        // training path: the same 8 features also go to HBM (14 % of the output bytes) for the dW GEMM
+        if (tok_g != nullptr) *reinterpret_cast<uint4*>(tok_g + (size_t)t * kTokLd + j * 8) = pk;
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) hprev[i] = hcur[i];
@@ -477,8 +483,9 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
         // item = (token t, block h of JB output columns j): JB+1 pixel rows -> JB 16-byte stores.
         // JB = 4 (two items per token) keeps row reuse high when there are many tokens; with few
         // tokens per plane (36-landmark views) JB = 1 spreads the work over all gather threads.
-        if (p.n > 64) gather_plane<InT, 4>(plane, tok, th, p.n, row0, gt, a_in, b_in, pad, p.debug);
-        else          gather_plane<InT, 1>(plane, tok, th, p.n, row0, gt, a_in, b_in, pad, p.debug);
+        __nv_bfloat16* tok_g = p.tok_out != nullptr ? p.tok_out + (size_t)f * p.n * kTokLd + c * 64 : nullptr;
+        if (p.n > 64) gather_plane<InT, 4>(plane, tok, th, p.n, row0, gt, a_in, b_in, pad, p.debug, tok_g);
+        else          gather_plane<InT, 1>(plane, tok, th, p.n, row0, gt, a_in, b_in, pad, p.debug, tok_g);
         fence_proxy_async_smem();      // token stores -> visible to the UMMA (async proxy) reads
         __syncwarp();
         if (lane == 0) {
@@ -539,6 +546,14 @@ extern "C" int lafs_embed_weight_prep(const float* weight, const float* bias, in
 extern "C" int lafs_gather_embed_fwd(const void* imgs, int in_dtype, float in_scale, float in_shift, const float* theta,
                                      const void* w_perm_bf16, const float* bias, void* out0, void* out1, int out_dtype,
                                      int Bv, int H, int W, int n, int dim, int n_models, lafs_stream_t stream) {
+  return lafs_gather_embed_fwd_save(imgs, in_dtype, in_scale, in_shift, theta, w_perm_bf16, bias, out0, out1, out_dtype, Bv, H, W, n,
+                                    dim, n_models, nullptr, stream);
+}
+
+extern "C" int lafs_gather_embed_fwd_save(const void* imgs, int in_dtype, float in_scale, float in_shift, const float* theta,
+                                          const void* w_perm_bf16, const float* bias, void* out0, void* out1, int out_dtype,
+                                          int Bv, int H, int W, int n, int dim, int n_models, void* tokens_perm_out,
+                                          lafs_stream_t stream) {
   if (int brc = lafs::bind_device_of(imgs)) return brc;
   if (Bv == 0) return LAFS_OK;
   LAFS_REQUIRE(imgs && theta && w_perm_bf16 && bias && out0, LAFS_ERR_ARG, "lafs_gather_embed_fwd: null pointer");
@@ -557,6 +572,8 @@ extern "C" int lafs_gather_embed_fwd(const void* imgs, int in_dtype, float in_sc
   EmbedParams p{};
   p.imgs = imgs; p.theta = theta; p.bias = bias;
   p.out[0] = out0; p.out[1] = out1;
+  LAFS_REQUIRE(((uintptr_t)tokens_perm_out & 15u) == 0, LAFS_ERR_ARG, "lafs_gather_embed_fwd_save: tokens_perm_out misaligned");
+  p.tok_out = (__nv_bfloat16*)tokens_perm_out;
   p.Bv = Bv; p.n = n; p.n_pad = (n + 15) & ~15; p.dim = dim; p.n_models = n_models;
   p.mchunks = n_models * dim / 128;
   // faces per group: as many as fit the tile, traded against load balance over the 148 CTAs.

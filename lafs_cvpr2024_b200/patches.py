@@ -145,15 +145,48 @@ class PatchEmbedWeights:
                       self.bias.data_ptr() + i * self.dim * 4, _lib.stream())
 
 
+def new_token_buffer(rows, device):
+    """bf16 [rows, 208] buffer for the tokens `gather_embed(..., save_tokens=buf)` keeps for the weight gradient:
+    columns 0..191 are written by the kernel on every call, column 192 is the ones column (bias gradient) and
+    columns 193..207 stay zero -- set here once, so the buffer can be reused step after step."""
+    buf = torch.empty(rows, _lib.TOK_LD, dtype=torch.bfloat16, device=device)
+    buf[:, 192:] = 0
+    buf[:, 192] = 1
+    return buf
+
+
 @torch.no_grad()
-def gather_embed(imgs, landmarks, weights: PatchEmbedWeights, out_dtype=torch.bfloat16, mean=0.5, std=0.5):
+def embed_backward_weight(grad_emb, tokens_perm, grad_w=None, grad_b=None, accumulate=False):
+    """grad of patch_to_embedding's weight [dim,192] and bias [dim] (fp32) from grad_emb [.., dim] (bf16) and the
+    tokens the forward kept (new_token_buffer + gather_embed(save_tokens=)): one tcgen05 split-K GEMM."""
+    _lib.require_cuda(grad_emb, tokens_perm)
+    dim = grad_emb.shape[-1]
+    g = grad_emb.detach().to(torch.bfloat16).contiguous().view(-1, dim)
+    M = g.shape[0]
+    if tokens_perm.shape != (M, _lib.TOK_LD) or tokens_perm.dtype != torch.bfloat16 or not tokens_perm.is_contiguous():
+        raise ValueError(f"tokens_perm must be a contiguous bf16 [{M}, {_lib.TOK_LD}] buffer")
+    dev = g.device
+    if grad_w is None:
+        grad_w, accumulate = torch.empty(dim, 192, dtype=torch.float32, device=dev), False
+    if grad_b is None:
+        grad_b = torch.empty(dim, dtype=torch.float32, device=dev) if not accumulate else None
+    nbytes = _lib.lib().lafs_embed_bwd_workspace_bytes(M, dim)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    _lib.call("lafs_embed_bwd_weight_perm", g.data_ptr(), tokens_perm.data_ptr(), M, dim, grad_w.data_ptr(), _lib.ptr(grad_b),
+              1 if accumulate else 0, ws.data_ptr(), nbytes, _lib.stream())
+    return grad_w, grad_b
+
+
+@torch.no_grad()
+def gather_embed(imgs, landmarks, weights: PatchEmbedWeights, out_dtype=torch.bfloat16, mean=0.5, std=0.5, save_tokens=None):
     """tokens(imgs, landmarks) @ W^T + b for every model in `weights`, without materialising the
     patches: list of [B, n, dim] tensors.  Forward only (the SSL landmark CNN is frozen and
     the teacher has no gradient).
 
     imgs: fp32 [B,3,112,112] already normalised (the reference's tensors), or uint8 decoded pixels;
     for uint8 the reference's ToTensor + Normalize(mean, std) (lafs_train.py:800-803) runs inside
-    the kernel, which quarters the image bytes moved over PCIe / read from HBM."""
+    the kernel, which quarters the image bytes moved over PCIe / read from HBM.
+    save_tokens: a new_token_buffer(B*n) the kernel also fills with the gathered bf16 tokens (training path)."""
     _lib.require_cuda(imgs, landmarks)
     if imgs.dtype == torch.uint8:
         x = imgs.detach().contiguous()
@@ -168,10 +201,13 @@ def gather_embed(imgs, landmarks, weights: PatchEmbedWeights, out_dtype=torch.bf
     n = th.shape[1]
     m = len(weights.linears)
     outs = [torch.empty(Bv, n, weights.dim, dtype=out_dtype, device=x.device) for _ in range(m)]
-    _lib.call("lafs_gather_embed_fwd", x.data_ptr(), in_dtype, scale, shift, th.data_ptr(),
+    if save_tokens is not None and (save_tokens.shape != (Bv * n, _lib.TOK_LD) or save_tokens.dtype != torch.bfloat16
+                                    or not save_tokens.is_contiguous()):
+        raise ValueError(f"save_tokens must be a contiguous bf16 [{Bv * n}, {_lib.TOK_LD}] buffer (new_token_buffer)")
+    _lib.call("lafs_gather_embed_fwd_save", x.data_ptr(), in_dtype, scale, shift, th.data_ptr(),
               weights.w_perm.data_ptr(), weights.bias.data_ptr(), outs[0].data_ptr(),
               outs[1].data_ptr() if m > 1 else None, _lib.dtype_code(outs[0]), Bv, H, W, n, weights.dim, m,
-              _lib.stream())
+              _lib.ptr(save_tokens), _lib.stream())
     return outs
 
 
@@ -204,22 +240,10 @@ class _GatherEmbedTrainFn(torch.autograd.Function):
         g = grad_emb.detach().to(torch.bfloat16).contiguous().view(M, dim)
         dev = g.device
         gw = gb = gi = gt = None
-        if need_w:
-            tok = torch.empty(Bv, n, 64 * Cc, dtype=torch.float32, device=dev)
-            _lib.call("lafs_gather_fwd", x.data_ptr(), th.data_ptr(), tok.data_ptr(), Bv, Cc, H, W, n,
-                      _lib.LAYOUT_TOKENS, COORD_MODE, _lib.stream())
-            tok16 = tok.view(M, 64 * Cc).to(torch.bfloat16)
-            nbytes = _lib.lib().lafs_embed_bwd_workspace_bytes(M, dim)
-            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            gw = torch.empty(dim, 64 * Cc, dtype=torch.float32, device=dev)
-            _lib.call("lafs_embed_bwd_weight", g.data_ptr(), tok16.data_ptr(), M, dim, gw.data_ptr(), ws.data_ptr(),
-                      nbytes, _lib.stream())
-            gw = gw.to(weight.dtype)
-        if need_b and ctx.has_bias:
-            gb = torch.empty(dim, dtype=torch.float32, device=dev)
-            nb = 32 * dim * 4
-            wsb = torch.empty(nb, dtype=torch.uint8, device=dev)
-            _lib.call("lafs_colsum", g.data_ptr(), M, dim, _lib.BF16, gb.data_ptr(), wsb.data_ptr(), nb, _lib.stream())
+        if (need_w or need_b) and ctx.tok is not None:
+            gw, gb = embed_backward_weight(g, ctx.tok)
+            gw = gw.to(weight.dtype) if need_w else None
+            gb = gb if (need_b and ctx.has_bias) else None
         if need_img or need_th:
             w16 = weight.detach().to(torch.bfloat16).contiguous()
             gtok = torch.empty(M, 64 * Cc, dtype=torch.float32, device=dev)

@@ -15,7 +15,8 @@ import torch
 from . import _lib
 from .dino_loss import DINOLoss
 from .ema import EmaPlan
-from .patches import PatchEmbedWeights, extract_tokens, gather_embed, landmark_post
+from .patches import (PatchEmbedWeights, embed_backward_weight, extract_tokens, gather_embed, landmark_post,
+                      new_token_buffer)
 
 
 class SSLHotPath:
@@ -45,18 +46,34 @@ class SSLHotPath:
         tok_l = extract_tokens(img_l, theta_l)
         return theta_g, tok_g, theta_l, tok_l
 
-    def landmarks_and_embeddings(self, raw_g, noise_g, img_g, raw_l, noise_l, idx_l, img_l, refresh=True):
+    def landmarks_and_embeddings(self, raw_g, noise_g, img_g, raw_l, noise_l, idx_l, img_l, refresh=True, keep_tokens=False):
         """Fused form: landmark tail, then gather -> patch_to_embedding on the tensor cores.
         Returns (student_global, teacher_global, student_local) embedded tokens (bf16); the
-        patch mosaics / token tensors of the reference are never materialised."""
+        patch mosaics / fp32 token tensors of the reference are never materialised.
+        keep_tokens: also keep the gathered bf16 tokens (persistent buffers) for student_embed_backward."""
         if refresh:
             self.embed_global.refresh()    # weights moved by the optimizer / EMA since last step
             self.embed_local.refresh()
+        tg = tl = None
+        if keep_tokens:
+            ng, nl = noise_g.shape[0] * noise_g.shape[1], idx_l.shape[0] * idx_l.shape[1]
+            if getattr(self, "_tok_g", None) is None or self._tok_g.shape[0] != ng or self._tok_l.shape[0] != nl:
+                self._tok_g, self._tok_l = new_token_buffer(ng, raw_g.device), new_token_buffer(nl, raw_g.device)
+            tg, tl = self._tok_g, self._tok_l
         theta_g = landmark_post(raw_g, noise_g)
-        s_g, t_g = gather_embed(img_g, theta_g, self.embed_global)
+        s_g, t_g = gather_embed(img_g, theta_g, self.embed_global, save_tokens=tg)
         theta_l = landmark_post(raw_l, noise_l, idx_l)
-        (s_l,) = gather_embed(img_l, theta_l, self.embed_local)
+        (s_l,) = gather_embed(img_l, theta_l, self.embed_local, save_tokens=tl)
         return s_g, t_g, s_l
+
+    def student_embed_backward(self, grad_s_g, grad_s_l):
+        """Weight / bias gradient of the STUDENT's patch_to_embedding (lafs_train.py:600 through ViT_face.py:761)
+        from the gradients of its embedded tokens (global [2B,196,dim], local [LB,36,dim], bf16) and the tokens kept
+        by landmarks_and_embeddings(keep_tokens=True): two split-K tcgen05 GEMMs accumulating into one
+        [dim,192] + [dim] result.  (The landmark CNN is frozen in the SSL stage, lafs_train.py:146-150: there is no
+        gradient w.r.t. the landmarks or the images.)"""
+        gw, gb = embed_backward_weight(grad_s_g, self._tok_g)
+        return embed_backward_weight(grad_s_l, self._tok_l, grad_w=gw, grad_b=gb, accumulate=True)
 
     def loss_and_grad(self, student_out, teacher_out, epoch, fused=True):
         """DINO loss, its gradient w.r.t. the student logits, and the centre update.  fused=True uses
@@ -78,8 +95,9 @@ class GraphedSSLStep:
     refreshes, e.g. with copy_ from pinned host memory on a copy stream).
 
     Static inputs : img_g, img_l (uint8 or fp32), raw_g, raw_l, noise_g, noise_l, idx_l,
-                    student_out, teacher_out.   Outputs: loss (0-dim), grad_student, the three
-    embedded-token tensors.  The DINO centre is kept in a static buffer and updated in place at the
+                    student_out, teacher_out, optionally grad_s_g / grad_s_l (gradients of the student's embedded
+                    tokens: adds the patch_to_embedding weight/bias gradient to the step).
+    Outputs: loss (0-dim), grad_student, the three embedded-token tensors, grad_embed_w / grad_embed_b.  The DINO centre is kept in a static buffer and updated in place at the
     end of the graph (the loss and its backward inside the graph still see the old centre, Q7)."""
 
     def __init__(self, path: SSLHotPath, static_inputs: dict, epoch: int, momentum: float, overlap_ema=False, ema_ctas=444,
@@ -126,8 +144,12 @@ class GraphedSSLStep:
             self.side.wait_stream(main)
             with torch.cuda.stream(self.side):
                 p.ema_step(momentum, max_ctas=self.ema_ctas)
+        with_bwd = "grad_s_g" in i          # synthetic gradients of the student's embedded tokens (static inputs)
         s_g, t_g, s_l = p.landmarks_and_embeddings(i["raw_g"], i["noise_g"], i["img_g"], i["raw_l"], i["noise_l"],
-                                                   i["idx_l"], i["img_l"], refresh=not self.overlap_ema)
+                                                   i["idx_l"], i["img_l"], refresh=not self.overlap_ema, keep_tokens=with_bwd)
+        gw = gb = None
+        if with_bwd:                         # student patch_to_embedding backward (lafs_train.py:600 / ViT_face.py:761)
+            gw, gb = p.student_embed_backward(i["grad_s_g"], i["grad_s_l"])
         loss, grad = p.loss_and_grad(i["student_out"], i["teacher_out"], epoch, fused=self.fused_loss)
         cside = getattr(p.loss, "_side", None) if getattr(p.loss, "_center_event", None) is not None else None
         if cside is not None:
@@ -149,7 +171,8 @@ class GraphedSSLStep:
             p.ema_step(momentum)
         if cside is not None:
             main.wait_stream(cside)
-        self.out = {"loss": loss.detach(), "grad_student": grad, "s_g": s_g, "t_g": t_g, "s_l": s_l}
+        self.out = {"loss": loss.detach(), "grad_student": grad, "s_g": s_g, "t_g": t_g, "s_l": s_l,
+                    "grad_embed_w": gw, "grad_embed_b": gb}
 
     def replay(self):
         self.graph.replay()

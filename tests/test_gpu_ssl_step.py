@@ -96,3 +96,35 @@ def test_graph_replay_equals_eager_over_steps():
     assert torch.equal(g.center, path_e.loss.center)
     diffs = [float((a - b).abs().max()) for a, b in zip(tpg, tpe)]
     assert all(d == 0.0 for d in diffs), diffs
+
+
+def test_student_embed_backward_matches_oracle_autograd():
+    """patch_to_embedding weight/bias gradient of the student from the tokens the fused forward kept (uint8 views,
+    two view groups accumulated) against fp32 autograd through the oracle's gather + F.linear on bf16-rounded
+    tokens and gradients (the operands of the tensor-core GEMM)."""
+    P, SSLHotPath, host, sp, tp = build(B=7, L=3, dim=256, seed=2)
+    B, L, K, dim = 7, 3, 2048, 256
+    dev = {k: v.cuda() for k, v in host.items()}
+    spg, tpg = [p.cuda() for p in sp], [p.cuda() for p in tp]
+    path = SSLHotPath(K, L, tpg, spg, student_embed=(spg[1], spg[2]), teacher_embed=(tpg[1], tpg[2]))
+    path.landmarks_and_embeddings(dev["raw_g"], dev["noise_g"], dev["img_g"], dev["raw_l"], dev["noise_l"], dev["idx_l"],
+                                  dev["img_l"], keep_tokens=True)
+    g = torch.Generator().manual_seed(9)
+    dy_g = (torch.randn(2 * B, 196, dim, generator=g) * 0.05).bfloat16()
+    dy_l = (torch.randn(L * B, 36, dim, generator=g) * 0.05).bfloat16()
+    for _ in range(2):          # the token buffers are persistent: a second call must give the same result
+        gw, gb = path.student_embed_backward(dy_g.cuda(), dy_l.cuda())
+    img_g = (host["img_g"].float() / 255 - 0.5) / 0.5
+    img_l = (host["img_l"].float() / 255 - 0.5) / 0.5
+    th_g = O.landmark_post(host["raw_g"], host["noise_g"])
+    th_l = O.landmark_post(host["raw_l"], host["noise_l"], host["idx_l"])
+    w = sp[1].clone().requires_grad_(True)
+    b = sp[2].clone().requires_grad_(True)
+    out = 0.0
+    for img, th, dy in ((img_g, th_g, dy_g), (img_l, th_l, dy_l)):
+        tok = O.extract_tokens(img, th).bfloat16().float()
+        out = out + (torch.nn.functional.linear(tok, w, b) * dy.float()).sum()
+    out.backward()
+    assert gw.shape == (dim, 192) and gb.shape == (dim,)
+    assert (gw.cpu() - w.grad).abs().max() <= 1e-3 * w.grad.abs().max(), float((gw.cpu() - w.grad).abs().max() / w.grad.abs().max())
+    assert (gb.cpu() - b.grad).abs().max() <= 1e-3 * b.grad.abs().max()
