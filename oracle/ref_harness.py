@@ -92,6 +92,7 @@ def load():
     if not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29533")
-        dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo", rank=0, world_size=1)
+        # both device types: the CPU arm all-reduces a CPU tensor, the eager-GPU report a CUDA one (lafs_train.py:675)
+        dist.init_process_group("cpu:gloo,cuda:nccl" if torch.cuda.is_available() else "gloo", rank=0, world_size=1)
     _cached = types.SimpleNamespace(VF=VF, L=L, vt=vt, dutils=dutils, mixup=mixup_my)
     return _cached
