@@ -391,6 +391,25 @@ def run_ours(args):
     if xc is not None:
         xc.check()                    # raises if a rank missed the centre exchange's spin bound
 
+    # ---- secondary: clip + AdamW + teacher EMA as one multi-tensor update ------------------
+    extras = {}
+    try:
+        upd = P.StudentUpdate(st["student_params"], st["teacher_params"], regularized=[p.dim() > 1 for p in st["student_params"]])
+        ugr = [torch.randn_like(p) * 0.01 for p in st["student_params"]]
+        for _ in range(3):
+            upd.step(ugr, 5e-4, 0.04, 3.0, 0.996)
+        ms_upd, _ = timed(lambda i, ev: upd.step(ugr, 5e-4, 0.04, 3.0, 0.996), max(5, min(args.steps, 20)))
+        ms_upd /= max(5, min(args.steps, 20))
+        npar = sum(p.numel() for p in st["student_params"])
+        extras["student_update(clip+adamw+ema)"] = {
+            "ms": round(ms_upd, 5), "alg_bytes": 40 * npar, "GBps": round(40 * npar / ms_upd / 1e6, 1),
+            "note": "per-tensor clip (read g) + AdamW + EMA fold (read p,g,m,v,k; write p,m,v,k): 40 B/param; "
+                    "replaces utils.clip_gradients + AdamW.step + the EMA loop (utils.py:132-141, lafs_train.py:601-613)"}
+        del upd, ugr
+    except Exception as e:
+        extras["student_update_error"] = str(e).splitlines()[0][:160]
+    torch.cuda.empty_cache()
+
     # ---- secondary: class-sharded margin head (BASELINE configs[2], configs[3]) -----------------
     del st, path, dev_in
     torch.cuda.empty_cache()
@@ -476,6 +495,10 @@ def run_ours(args):
     for name, h in head.items():
         h["frac_tc"] = round(h["TFLOPs_6BCD"] / pk["tc"], 4)
     line["head"] = head
+    for k, v in extras.items():
+        if isinstance(v, dict) and "GBps" in v:
+            v["frac_hbm"] = round(v["GBps"] / pk["hbm"], 4)
+    line["extras"] = extras
     if world == 1 and not args.no_ref_gpu and _reference_available():
         # the unmodified reference modules in eager PyTorch on this same GPU (N = 1 report)
         line["reference_eager_b200"] = reference_eager_gpu(dev)
@@ -745,6 +768,12 @@ def reference_eager_gpu(dev, steps=3):
         torch.cuda.empty_cache()
     except Exception as e:
         out["ssl_step_error"] = str(e).splitlines()[0][:160]
+    try:
+        sec = ref_step.student_update_reference_step(dev, vit_param_shapes(VIT), iters=3)
+        out["student_update"] = {"ms": round(sec * 1e3, 3), "note": "utils.clip_gradients + torch.optim.AdamW.step + EMA loop, eager CUDA"}
+    except Exception as e:
+        out["student_update_error"] = str(e).splitlines()[0][:160]
+    torch.cuda.empty_cache()
     for name, B, C, D in HEAD_CFGS:
         if D != 512:
             continue

@@ -279,6 +279,24 @@ LAFS_API int lafs_xchg_stats(const void* peer_base, int rank, int world, int B, 
                              float* merged_stats, lafs_stream_t stream);
 LAFS_API int lafs_xchg_allreduce(const void* peer_base, int rank, int world, int B, int D, lafs_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * (f3) Student update: per-tensor gradient clipping + AdamW + teacher EMA as one multi-tensor call
+ *      replaces utils.clip_gradients (utils.py:132-141: a norm kernel, a .item() host sync and a mul_ per tensor),
+ *      utils.cancel_gradients_last_layer (utils.py:144-149), torch.optim.AdamW.step (lafs_train.py:400,601-609)
+ *      and the teacher EMA loop (lafs_train.py:610-613).
+ * table: device array of nchunks records {float* p; const float* g; float* m; float* v; float* k; int32 n; int32 tensor}
+ *      (48 bytes; runs of <= LAFS_EMA_CHUNK elements; g == NULL: the tensor has no gradient this step, only its EMA
+ *      runs; k == NULL: no EMA).  first_chunk [ntensors+1] (int32): the chunks of tensor t are
+ *      [first_chunk[t], first_chunk[t+1]).  regularized [ntensors] (uint8): weight decay applies (utils.py:662-673).
+ * hyper: DEVICE array of 10 floats, refreshed by the host every step (so a captured graph can be replayed):
+ *      {1 - lr*wd, lr/(1-b1^t), sqrt(1-b2^t), eps, 1-b1, b2, 1-b2, ema_m, 1-ema_m, clip (<= 0: off)}.
+ * Outputs: grad_norms [ntensors] (what clip_gradients returns, left on the device), clip_coef [ntensors].
+ * Arithmetic = torch.optim.AdamW's single-tensor formulas in fp32; the EMA uses the NEW parameter value. */
+LAFS_API size_t lafs_optim_workspace_bytes(int nchunks, int ntensors);
+LAFS_API int lafs_adamw_ema_multi(const void* table, int nchunks, const int* first_chunk, const unsigned char* regularized,
+                                  int ntensors, const float* hyper, float* grad_norms, float* clip_coef, void* workspace,
+                                  size_t workspace_bytes, lafs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

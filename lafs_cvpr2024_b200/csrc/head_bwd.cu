@@ -137,10 +137,12 @@ gemm_bwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBM, kBN, A_MN ? 1 : 0, 1);
       uint32_t cnt = 0, acnt = 0;
       for (int tile = first; tile < total_tiles; tile += stride, ++acnt) {
         const int split = tile % p.splits;
+        // UMMA N = the valid columns of this N tile rounded up to 16 (a [*, 208] problem issues N = 208, not 256)
+        const int n_left = p.N - ((tile / p.splits) % p.n_tiles) * kBN;
+        const uint32_t idesc = make_idesc_bf16(kBM, n_left >= kBN ? kBN : ((n_left + 15) & ~15), A_MN ? 1 : 0, 1);
         const int kb0 = split * p.kblocks_per_split;
         const int kb1 = min(kb0 + p.kblocks_per_split, p.kblocks_total);
         const int buf = acnt & 1;

@@ -179,17 +179,13 @@ __device__ __forceinline__ void gather_plane(const InT* __restrict__ plane, uint
 }
 
 // DIM > 0: compile-time embedding width (store offsets become immediates); DIM == 0: runtime p.dim
-// TOKM ("tokens on the M side", the default): D[128 tokens x 128 dims] += Tok[128 x 192] * Wchunk[128 x 192]^T.
-//   A TMEM lane is a TOKEN and its registers are 32 consecutive DIMS, so an epilogue thread packs them to bf16
-//   and writes 64 contiguous bytes of the output row with two 256-bit stores -- 16x fewer store instructions
-//   than the dims-on-lanes form (one 2-byte store per element), whose store stream, not HBM (a pure-write
-//   stream measures 6.2-6.9 TB/s on this part, tools/wbw_probe.cu), bounded the kernel.  Tokens beyond 128 go
-//   to a second M tile (rows 128..255 of the token tile; rows past the tile's 200 read whatever follows in
-//   shared memory -- garbage accumulator ROWS that are never stored).  Shared-memory layout, producers and the
-//   gather are identical in both forms; only the UMMA operand roles and the epilogue differ.
-// !TOKM: D[128 dims x N tokens], tokens on the N side (N = 208 for 196 landmarks): kept for A/B measurements
-//   (LAFS_PE_TOKN=1).
-template <typename InT, typename OutT, int DIM, bool TOKM>
+// Orientation: D[128 dims x N tokens], tokens on the UMMA N side (N = 208 for 196 landmarks: no 128-row padding).
+// The transposed form (tokens on the M side, a TMEM lane = a token, 64 contiguous output bytes per thread and
+// 16x fewer store instructions) was built and measured on B200 in round 2 and removed: 137.6 us against 98.9 us
+// (512 x 196 uint8 views, two models) -- 196 tokens need two M tiles (23 % more UMMA work), and the ablations
+// (profiles/r02_pe_ablate.txt) show the store STREAM (308 MB: ~50 us at the part's write rate), not the store
+// instruction count, is what the epilogue costs.
+template <typename InT, typename OutT, int DIM>
 __global__ void __launch_bounds__(pe::kThreads, 1)
 gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParams p) {
   using namespace pe;
@@ -288,10 +284,8 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
         const int u = blockIdx.x + fi * gridDim.x;
         const int tb = fi % NTB;
         const uint32_t tuse = (uint32_t)(fi / NTB);
-        const int ntok_g = group_ntok(unit_group(u));
-        const int npad_g = (ntok_g + 15) & ~15;
-        const int nmt = (ntok_g + 127) >> 7;                       // TOKM: M tiles of 128 tokens (1 or 2)
-        const uint32_t idesc = TOKM ? make_idesc_bf16(128, 128) : make_idesc_bf16(128, npad_g);
+        const int npad_g = (group_ntok(unit_group(u)) + 15) & ~15;
+        const uint32_t idesc = make_idesc_bf16(128, npad_g);
         const int mc0 = unit_mc0(u), mc1 = mc0 + unit_mcn(u);
         for (int mc = mc0; mc < mc1; ++mc, ++acnt) {
           const int buf = acnt & 1;
@@ -306,21 +300,10 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
             const uint64_t dw = make_desc_k_sw128(smem_u32(s_w + st * kWStageBytes));
             const uint32_t tok_addr = smem_u32(s_tok + tb * kTokTileBytes + c * kTokChunkBytes);
             if (!(p.debug & 4)) {
-              if (TOKM) {
-                // the weight stage serves every M tile before it is released
-                for (int mt = 0; mt < nmt; ++mt) {
-                  const uint64_t dt = make_desc_k_sw128(tok_addr + (uint32_t)mt * (128 * 128));
+              const uint64_t dt = make_desc_k_sw128(tok_addr);
 #pragma unroll
-                  for (int kk = 0; kk < 4; ++kk)
-                    mma_f16_ss(d_tmem + (uint32_t)(mt * 128), desc_advance_k(dt, kk * 16), desc_advance_k(dw, kk * 16), idesc,
-                               (c | kk) != 0);
-                }
-              } else {
-                const uint64_t dt = make_desc_k_sw128(tok_addr);
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                  mma_f16_ss(d_tmem, desc_advance_k(dw, kk * 16), desc_advance_k(dt, kk * 16), idesc, (c | kk) != 0);
-              }
+              for (int kk = 0; kk < 4; ++kk)
+                mma_f16_ss(d_tmem, desc_advance_k(dw, kk * 16), desc_advance_k(dt, kk * 16), idesc, (c | kk) != 0);
             }
             mma_commit(w_empty + st);
           }
@@ -335,73 +318,6 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
     const int half = (warp - kWarpEpi0) >> 2;
     const int dim = DIM > 0 ? DIM : p.dim;
     uint32_t acnt = 0;
-   if (TOKM) {
-    // lane = token (TMEM lane), registers = 32 consecutive dims: + bias, bf16 pack, 64 contiguous bytes per
-    // thread and piece (two 256-bit stores).  The two warps of a lane quarter take the two 64-dim halves.
-    const bool st256 = (((uintptr_t)p.out[0] | (uintptr_t)p.out[1]) & 31u) == 0 && (dim % 16) == 0;
-    for (int fi = 0; fi < nunits_mine; ++fi) {
-      const int u = blockIdx.x + fi * gridDim.x;
-      const int g = unit_group(u);
-      const int f = g * p.gfaces;                          // first face: the group's tokens are contiguous in `out`
-      const int ntok = group_ntok(g);
-      const int nmt = (ntok + 127) >> 7;
-      const int mc0 = unit_mc0(u), mc1 = mc0 + unit_mcn(u);
-      for (int mc = mc0; mc < mc1; ++mc, ++acnt) {
-        const int buf = acnt & 1;
-        mbar_wait(acc_full + buf, (acnt >> 1) & 1);
-        tc_fence_after();
-        for (int mt = 0; mt < nmt; ++mt) {
-          const int row0 = mt * 128 + quarter * 32;
-          if (row0 >= ntok) break;                         // warp-uniform: no valid token in this lane quarter
-          const int row = row0 + lane;
-          const bool row_ok = row < ntok;
-#pragma unroll 1
-          for (int piece = 0; piece < 2; ++piece) {
-            const int col = half * 64 + piece * 32;        // column inside the 128-dim chunk
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(tmem_base + (uint32_t)(buf * 256 + mt * 128 + col) + ((uint32_t)(quarter * 32) << 16), v);
-            tmem_ld_wait();
-            if ((p.debug & 1) || !row_ok) continue;
-            const int d = mc * 128 + col;                  // row of the stacked [n_models*dim] weight; 32 | dim
-            const int model = d >= dim ? 1 : 0, dd = d - model * dim;
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + d);   // uniform address: broadcast loads
-            float o[32];
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = __ldg(bp + (j >> 2));
-              o[j] = __uint_as_float(v[j]) + b4.x; o[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
-              o[j + 2] = __uint_as_float(v[j + 2]) + b4.z; o[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
-            }
-            OutT* dst = reinterpret_cast<OutT*>(model == 0 ? p.out[0] : p.out[1]) + ((size_t)f * p.n + row) * dim + dd;
-            if constexpr (sizeof(OutT) == 2) {
-              uint4 pk[4];
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                pk[j >> 3].x = Half2Ops<__nv_bfloat16>::pack(o[j], o[j + 1]);
-                pk[j >> 3].y = Half2Ops<__nv_bfloat16>::pack(o[j + 2], o[j + 3]);
-                pk[j >> 3].z = Half2Ops<__nv_bfloat16>::pack(o[j + 4], o[j + 5]);
-                pk[j >> 3].w = Half2Ops<__nv_bfloat16>::pack(o[j + 6], o[j + 7]);
-              }
-              if (st256) {
-                st_global_256(dst, pk[0], pk[1]);
-                st_global_256(dst + 16, pk[2], pk[3]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(dst + 8 * j) = pk[j];
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-            }
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_relaxed(acc_empty + buf);   // no release: do not wait for the token stores
-      }
-    }
-   } else {
     // lane = output feature (TMEM lane), registers = 32 consecutive tokens.  A warp-wide 2-byte
     // store covers 32 consecutive features of one token (64 contiguous bytes = 2 full sectors).
     // The two warps of a lane quarter take alternate 32-token pieces; the TMEM load of the next
@@ -459,7 +375,6 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
         if (lane == 0) mbar_arrive_relaxed(acc_empty + buf);   // no release: do not wait for the token stores
       }
     }
-   }
   } else if (warp >= kWarpGather0) {
     // ===================== gather warps =====================
     const int gt = threadIdx.x - kWarpGather0 * 32;        // 0..255
@@ -516,12 +431,12 @@ __global__ void embed_weight_prep_kernel(const float* __restrict__ w, const floa
   out[idx] = __float2bfloat16_rn(w[(size_t)d * pe::kFeat + (i * 8 + j) * 3 + c]);
 }
 
-template <typename InT, bool TOKM>
+template <typename InT>
 static int launch_embed(const CUtensorMap& tw, const EmbedParams& p, int out_dtype, int dim, cudaStream_t st) {
   void (*kern)(const CUtensorMap, const EmbedParams);
-  if (out_dtype == LAFS_F32) kern = dim == 768 ? gather_embed_kernel<InT, float, 768, TOKM> : gather_embed_kernel<InT, float, 0, TOKM>;
-  else kern = dim == 768 ? gather_embed_kernel<InT, __nv_bfloat16, 768, TOKM>
-            : dim == 384 ? gather_embed_kernel<InT, __nv_bfloat16, 384, TOKM> : gather_embed_kernel<InT, __nv_bfloat16, 0, TOKM>;
+  if (out_dtype == LAFS_F32) kern = dim == 768 ? gather_embed_kernel<InT, float, 768> : gather_embed_kernel<InT, float, 0>;
+  else kern = dim == 768 ? gather_embed_kernel<InT, __nv_bfloat16, 768>
+            : dim == 384 ? gather_embed_kernel<InT, __nv_bfloat16, 384> : gather_embed_kernel<InT, __nv_bfloat16, 0>;
   constexpr int smem = pe::Layout<InT>::kSmemBytes;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   LAFS_REQUIRE(e == cudaSuccess, LAFS_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -581,8 +496,6 @@ extern "C" int lafs_gather_embed_fwd_save(const void* imgs, int in_dtype, float 
   // pass over the weights itself is not the limiter: 52-56 us for every G); ties go to the larger
   // group.  The groups of a last, at most half-filled round are split into two half units (first /
   // second half of the weight chunks), which makes that round cost half.
-  bool tokm = true;
-  if (const char* e = getenv("LAFS_PE_TOKN")) tokm = atoi(e) == 0;
   {
     int gmax = pe::kTokRows / n < 1 ? 1 : pe::kTokRows / n;
     if (gmax > Bv) gmax = Bv;
@@ -597,10 +510,7 @@ extern "C" int lafs_gather_embed_fwd_save(const void* imgs, int in_dtype, float 
       const int rem = groups % kNumSMs;
       const bool split = groups > kNumSMs && rem > 0 && 2 * rem <= kNumSMs && (p.mchunks % 2 == 0);
       const long long half_rounds = 2LL * (groups / kNumSMs) + (rem == 0 ? 0 : (split ? 1 : 2));
-      // work of one unit: the gather grows with the faces in the group, the UMMA time with the 128-token M tiles
-      // the group occupies (token-major kernel); both in units of "one 36..196-token face"
-      const long long unit = tokm ? (long long)g * n + 128LL * ((g * n + 127) / 128) : (long long)g;
-      const long long cost = half_rounds * unit;
+      const long long cost = half_rounds * g;
       if (best_cost < 0 || cost <= best_cost) {
         best_cost = cost;
         p.gfaces = g;
@@ -614,9 +524,5 @@ extern "C" int lafs_gather_embed_fwd_save(const void* imgs, int in_dtype, float 
   else { p.in_scale = 1.f; p.in_shift = 0.f; p.pad_raw = 0.f; }
   if (const char* dbg = getenv("LAFS_PE_DEBUG")) p.debug = atoi(dbg);
   cudaStream_t st = (cudaStream_t)stream;
-  if (tokm)
-    return in_dtype == LAFS_U8 ? launch_embed<uint8_t, true>(tw, p, out_dtype, dim, st)
-                               : launch_embed<float, true>(tw, p, out_dtype, dim, st);
-  return in_dtype == LAFS_U8 ? launch_embed<uint8_t, false>(tw, p, out_dtype, dim, st)
-                             : launch_embed<float, false>(tw, p, out_dtype, dim, st);
+  return in_dtype == LAFS_U8 ? launch_embed<uint8_t>(tw, p, out_dtype, dim, st) : launch_embed<float>(tw, p, out_dtype, dim, st);
 }

@@ -213,17 +213,20 @@ def gather_embed(imgs, landmarks, weights: PatchEmbedWeights, out_dtype=torch.bf
 
 class _GatherEmbedTrainFn(torch.autograd.Function):
     """Differentiable gather -> patch_to_embedding for the finetune path (the landmark CNN and the
-    embedding are trained, ViT_face.py:706,760-761).  Forward: the fused tcgen05 kernel (no token
-    tensor in HBM).  Backward: the tokens are re-gathered, then
-        grad_weight = grad_emb^T . tokens,  grad_bias = column sums of grad_emb,
+    embedding are trained, ViT_face.py:706,760-761).  Forward: the fused tcgen05 kernel, which also keeps the
+    gathered tokens in bf16 (14 % of the output bytes; no fp32 token tensor, no re-gather).  Backward:
+        [grad_weight | grad_bias] = grad_emb^T . [tokens | 1]      (one split-K GEMM, lafs_embed_bwd_weight_perm)
         grad_tokens = grad_emb . W  ->  lafs_gather_bwd  ->  grad_landmarks (, grad_imgs)
     on the same tcgen05 GEMM the margin head's backward uses (bf16 operands, fp32 accumulation)."""
 
     @staticmethod
     def forward(ctx, imgs, theta, weight, bias):
         w = PatchEmbedWeights([(weight, bias)])
-        (emb,) = gather_embed(imgs, theta, w, out_dtype=torch.bfloat16)
+        need_w = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
+        tok = new_token_buffer(theta.shape[0] * theta.shape[1], theta.device) if need_w else None
+        (emb,) = gather_embed(imgs, theta, w, out_dtype=torch.bfloat16, save_tokens=tok)
         ctx.save_for_backward(imgs, theta, weight)
+        ctx.tok = tok
         ctx.has_bias = bias is not None
         return emb
 

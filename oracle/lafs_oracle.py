@@ -14,6 +14,8 @@ tests/golden/ that tests/golden/make_golden.py generated from the reference):
   patch_embed                            pinned   face_pre_pro/ViT_face.py:759-761
   dino_loss / dino_center_update         pinned   lafs_train.py:643-679
   ema_update                             pinned   lafs_train.py:610-613
+  clip_gradients_ / student_update_      pinned   utils.py:132-141, lafs_train.py:511-517,601-613 (torch.optim.AdamW
+                                                  is PyTorch itself; the clip is checked against utils.clip_gradients)
   cosface_logits                         pinned   face_pre_pro/ViT_face.py:49-89
   shard_bounds / label_to_shard          pinned   face_pre_pro/ViT_face.py:56 (torch.chunk)
   cross_entropy (hard labels)            pinned   train_largescale.py:604 (torch.nn.CrossEntropyLoss)
@@ -175,6 +177,38 @@ def ema_update_(teacher_params, student_params, m):
     with torch.no_grad():
         for q, k in zip(student_params, teacher_params):
             k.mul_(m).add_((1 - m) * q.detach())
+
+
+def clip_gradients_(grads, clip):
+    """utils.clip_gradients, utils.py:132-141, on a list of gradient tensors (None = no gradient): per-TENSOR
+    L2 norm, `clip_coef = clip / (norm + 1e-6)`, gradient scaled in place when clip_coef < 1.  Returns the norms."""
+    norms = []
+    for g in grads:
+        if g is not None:
+            param_norm = g.norm(2)
+            norms.append(param_norm.item())
+            clip_coef = clip / (param_norm + 1e-6)
+            if clip_coef < 1:
+                g.mul_(clip_coef)
+    return norms
+
+
+def student_update_(params, grads, teacher, optimizer, lr, weight_decay, clip, ema_m):
+    """One student update exactly as lafs_train.py:511-517,601-613 runs it: schedule values into the param groups
+    (weight decay only into group 0), utils.clip_gradients, optimizer.step() (torch.optim.AdamW built over
+    utils.get_params_groups' two groups), then the teacher EMA loop.  `optimizer` is a torch.optim.AdamW whose
+    params are `params`; grads[i] None = cancelled / absent gradient.  In place; returns the gradient norms."""
+    for i, group in enumerate(optimizer.param_groups):
+        group["lr"] = lr
+        if i == 0:
+            group["weight_decay"] = weight_decay
+    for p, g in zip(params, grads):
+        p.grad = None if g is None else g.clone()
+    norms = clip_gradients_([p.grad for p in params], clip) if clip else []
+    optimizer.step()
+    if teacher is not None:
+        ema_update_(teacher, params, ema_m)
+    return norms
 
 
 def cosine_scheduler(base_value, final_value, epochs, niter_per_ep):

@@ -163,3 +163,42 @@ def head_reference_step(device, B, C, D, iters=3, seed=7):
         if i > 0:
             ts.append(time.perf_counter() - t0)
     return float(np.median(ts)), float(loss)
+
+
+def student_update_reference_step(device, param_shapes, iters=3, seed=3):
+    """The reference's student update on `device`, eager: utils.clip_gradients (utils.py:132-141, one .item() per
+    tensor), torch.optim.AdamW over utils.get_params_groups' two groups (lafs_train.py:396-400), the teacher EMA loop
+    (lafs_train.py:610-613).  Returns seconds per step (median of `iters` after one warm-up)."""
+    ns = ref_harness.load()
+    dev = torch.device(device)
+    g = torch.Generator().manual_seed(seed)
+
+    class Holder(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.ps = nn.ParameterList([nn.Parameter((torch.randn(*s, generator=g) * 0.02).to(dev)) for s in param_shapes])
+
+    student = Holder()
+    teacher = [p.detach().clone() for p in student.ps]
+    reg = [p for p in student.ps if p.dim() > 1]
+    noreg = [p for p in student.ps if p.dim() <= 1]
+    opt = torch.optim.AdamW([{"params": reg}, {"params": noreg, "weight_decay": 0.}])
+    grads = [(torch.randn(*s, generator=g) * 0.01).to(dev) for s in param_shapes]
+    ts = []
+    for i in range(iters + 1):
+        for p, gr in zip(student.ps, grads):
+            p.grad = gr.clone()
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ns.dutils.clip_gradients(student, 3.0)
+        opt.step()
+        with torch.no_grad():
+            m = 0.996
+            for param_q, param_k in zip(student.ps, teacher):
+                param_k.data.mul_(m).add_((1 - m) * param_q.detach().data)
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+        if i > 0:
+            ts.append(time.perf_counter() - t0)
+    return float(np.median(ts))

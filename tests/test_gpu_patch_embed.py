@@ -127,25 +127,24 @@ def test_gather_embed_train_backward_vs_autograd(P, B, n, dim):
         assert cs > 0.999, (name, float(cs))
 
 
-@pytest.mark.parametrize("B,n,dim,u8", [(333, 36, 768, True), (300, 196, 768, True), (41, 196, 384, False), (7, 49, 128, True),
-                                        (149, 100, 256, False)])
-def test_token_major_kernel_equals_dims_major_kernel(P, B, n, dim, u8):
-    """The default kernel (tokens on the UMMA M side, row-per-thread epilogue) against the dims-on-lanes form
-    (LAFS_PE_TOKN=1): same operands, same products, fp32 accumulation over K = 192; two models in one launch, ragged last groups, out-of-image landmarks."""
+@pytest.mark.parametrize("B,n,u8", [(37, 36, True), (11, 196, True), (9, 196, False), (5, 49, True)])
+def test_saved_tokens_match_oracle_tokens(P, B, n, u8):
+    """gather_embed(save_tokens=): the bf16 tokens kept for the weight gradient are the oracle's tokens in the
+    kernel's K order (k = c*64 + j*8 + i  <-  feature (i*8+j)*3 + c), with the ones / zero columns untouched."""
     torch.manual_seed(B + n)
-    imgs = (torch.randint(0, 256, (B, 3, 112, 112), dtype=torch.uint8) if u8 else torch.rand(B, 3, 112, 112) * 2 - 1).cuda()
-    th = (torch.rand(B, n, 2) * 111 + torch.randn(B, n, 2) * 8).cuda()
-    la, lb = torch.nn.Linear(192, dim), torch.nn.Linear(192, dim)
-    wts = P.PatchEmbedWeights([(la.weight.detach().cuda(), la.bias.detach().cuda()),
-                               (lb.weight.detach().cuda(), lb.bias.detach().cuda())])
-    got = [t.clone() for t in P.gather_embed(imgs, th, wts)]
-    os.environ["LAFS_PE_TOKN"] = "1"
-    try:
-        ref = [t.clone() for t in P.gather_embed(imgs, th, wts)]
-        torch.cuda.synchronize()
-    finally:
-        os.environ.pop("LAFS_PE_TOKN", None)
-    for a, b in zip(got, ref):
-        # identical products and K order; allow one bf16 ulp for a different accumulation tree of the swapped roles
-        assert (a.float() - b.float()).abs().max() <= 2 ** -7 * b.float().abs().max()
-        assert (a != b).float().mean() < 1e-2
+    if u8:
+        raw = torch.randint(0, 256, (B, 3, 112, 112), dtype=torch.uint8)
+        imgs, ref_img = raw.cuda(), (raw.float() / 255 - 0.5) / 0.5
+    else:
+        ref_img = torch.rand(B, 3, 112, 112) * 2 - 1
+        imgs = ref_img.cuda()
+    th = torch.rand(B, n, 2) * 111 + torch.randn(B, n, 2) * 6
+    lin = torch.nn.Linear(192, 128)
+    wts = P.PatchEmbedWeights([(lin.weight.detach().cuda(), lin.bias.detach().cuda())])
+    buf = P.new_token_buffer(B * n, "cuda")
+    P.gather_embed(imgs, th.cuda(), wts, save_tokens=buf)
+    tok = O.extract_tokens(ref_img, th).reshape(B * n, 8, 8, 3)          # [.., i, j, c]
+    want = tok.permute(0, 3, 2, 1).reshape(B * n, 192)                     # k = c*64 + j*8 + i
+    got = buf.float().cpu()
+    assert (got[:, :192] - want).abs().max() <= 2 ** -8 * max(1.0, float(want.abs().max())) + 1e-3
+    assert bool((got[:, 192] == 1).all()) and bool((got[:, 193:] == 0).all())

@@ -173,3 +173,20 @@ def test_attention_with_mask_matches_reference(ref):
     x = torch.randn(2, n + 1, dim)
     torch.testing.assert_close(oa(x), ra(x), rtol=1e-5, atol=1e-6)     # unmasked path (SDPA) agrees too
     assert torch.isfinite(oa(x, mask=torch.zeros(2, n, dtype=torch.bool))).all()   # batched masks work here
+
+
+def test_clip_gradients_matches_reference(ref):
+    """oracle clip_gradients_ (a list of gradients) == utils.clip_gradients (a model), norms and clipped gradients."""
+    torch.manual_seed(5)
+    model = torch.nn.Sequential(torch.nn.Linear(40, 30), torch.nn.LayerNorm(30), torch.nn.Linear(30, 7))
+    for i, p in enumerate(model.parameters()):
+        p.grad = torch.randn_like(p) * (10.0 if i % 2 == 0 else 0.01)
+    list(model.parameters())[3].grad = None
+    grads = [None if p.grad is None else p.grad.clone() for p in model.parameters()]
+    norms_ref = ref.dutils.clip_gradients(model, 3.0)
+    norms = O.clip_gradients_(grads, 3.0)
+    assert norms == norms_ref
+    for p, g in zip(model.parameters(), grads):
+        assert (p.grad is None) == (g is None)
+        if g is not None:
+            assert torch.equal(p.grad, g)
