@@ -1,6 +1,7 @@
 // Error plumbing + version of liblafs_b200.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/lafs_b200.h"
 
@@ -12,6 +13,15 @@ void set_last_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LAFS_PDL");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v != 0;
 }
 
 int check_launch(const char* what) {

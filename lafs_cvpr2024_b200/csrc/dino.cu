@@ -117,6 +117,7 @@ dino_fwd_partial(const T* __restrict__ student, const T* __restrict__ teacher,
                  const float* __restrict__ center, int B, int K, float a_s, float a_t,
                  int nslices, int ngroups, float* __restrict__ part, float* __restrict__ colsum_part,
                  int b_begin, int b_count, unsigned* __restrict__ done_counter) {
+  pdl_wait();
   constexpr int VEC = VecOf<T>::VEC;
   constexpr int NC = VEC;
   constexpr int REC = rec_floats(NCROPS);
@@ -295,6 +296,7 @@ template <int NCROPS>
 __global__ void __launch_bounds__(kFinalizeWarps * 32)
 dino_rows_finalize(const float* __restrict__ part, int B, int nslices, float inv_ts,
                    float* __restrict__ row_stats, float* __restrict__ sample_loss, int b_begin, int b_count) {
+  pdl_wait();
   constexpr int REC = rec_floats(NCROPS);
   constexpr int NR = 2 + NCROPS;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -356,6 +358,7 @@ __global__ void __launch_bounds__(kDinoThreads)
 dino_tail(const float* __restrict__ sample_loss, int B, float inv_norm, float* __restrict__ loss_out,
           const float* __restrict__ colsum_part, int ngroups, int K, float* __restrict__ colsum_out,
           const float* __restrict__ center, float* __restrict__ center_out, float count, float mom, float om) {
+  pdl_wait();
   const int k = blockIdx.x * kDinoThreads + threadIdx.x;
   if (k < K) {
     float acc = 0.f;
@@ -395,12 +398,10 @@ dino_finish(const float* __restrict__ part, int B, int nslices, float inv_ts, fl
             unsigned* __restrict__ done_counter, const float* __restrict__ colsum_part, int ngroups, int K,
             float* __restrict__ colsum_out, const float* __restrict__ center, float* __restrict__ center_out,
             float count, float mom, float om) {
+  pdl_wait();
   constexpr int REC = rec_floats(NCROPS);
   constexpr int NR = 2 + NCROPS;
   extern __shared__ __align__(16) float fin_smem[];
-  // launched with programmatic stream serialisation: the CTAs are scheduled while the streaming kernel
-  // drains and block here until it has completed and its writes are visible (a no-op for a plain launch)
-  asm volatile("griddepcontrol.wait;" ::: "memory");
   if ((int)blockIdx.x >= nfin) {
     const int k = (((int)blockIdx.x - nfin) * 64 + (int)threadIdx.x) * 4;
     if (k < K) {                                        // K % 4 == 0 (checked by the host)
@@ -507,6 +508,7 @@ dino_bwd_kernel(const T* __restrict__ student, const T* __restrict__ teacher,
                 const float* __restrict__ center, const float* __restrict__ row_stats,
                 const float* __restrict__ grad_out, int B, int K, float a_s, float a_t,
                 float gcoef, T* __restrict__ grad_student, int b_begin) {
+  pdl_wait();
   constexpr int VEC = VecOf<T>::VEC;
   const int b = b_begin + blockIdx.y;
   const int col = (blockIdx.x * kDinoThreads + threadIdx.x) * VEC;
@@ -550,6 +552,7 @@ dino_bwd_kernel(const T* __restrict__ student, const T* __restrict__ teacher,
 template <typename T>
 __global__ void __launch_bounds__(kDinoThreads)
 colsum_partial_kernel(const T* __restrict__ x, int rows, int K, int ngroups, float* __restrict__ part) {
+  pdl_wait();
   constexpr int VEC = VecOf<T>::VEC;
   const int col = (blockIdx.x * kDinoThreads + threadIdx.x) * VEC;
   if (col >= K) return;
@@ -568,6 +571,7 @@ colsum_partial_kernel(const T* __restrict__ x, int rows, int K, int ngroups, flo
   for (int j = 0; j < VEC; ++j) part[(size_t)g * K + col + j] = acc[j];
 }
 __global__ void colsum_combine_kernel(const float* __restrict__ part, int ngroups, int K, float* __restrict__ out) {
+  pdl_wait();
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
   float acc = 0.f;
@@ -577,6 +581,7 @@ __global__ void colsum_combine_kernel(const float* __restrict__ part, int ngroup
 
 __global__ void center_ema_kernel(const float* __restrict__ center, const float* __restrict__ colsum,
                                   float count, float mom, float om, int K, float* __restrict__ center_out) {
+  pdl_wait();
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   // reference: center*momentum + (batch_center/n)*(1-momentum): separately rounded fp32 ops,
   // IEEE division as on the reference's CPU path
@@ -646,23 +651,9 @@ static bool launch_finish(const float* part, int B, int nslices, float inv_ts, f
   const int nfin = (B + 1) / 2;
   const int ncol = (K / 4 + 63) / 64;
   const float inv_norm = 1.f / ((float)(2 * NCROPS - 2) * (float)B);
-  // programmatic dependent launch (LAFS_DINO_PDL=0 falls back to a plain launch): removes the launch gap
-  // between the streaming kernel and this short tail
-  static int pdl = -1;
-  if (pdl < 0) { const char* e = getenv("LAFS_DINO_PDL"); pdl = (e && atoi(e) == 0) ? 0 : 1; }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(nfin + ncol);
-  cfg.blockDim = dim3(64);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
   const float count = (float)(2 * B);
-  if (cudaLaunchKernelEx(&cfg, kern, part, B, nslices, inv_ts, row_stats, sample_loss, nfin, inv_norm, loss_out, counter,
-                         colsum_part, ngroups, K, colsum_out, center, center_out, count, mom, om) != cudaSuccess) {
+  if (launch_pdl(kern, dim3(nfin + ncol), dim3(64), smem, st, part, B, nslices, inv_ts, row_stats, sample_loss, nfin, inv_norm,
+                 loss_out, counter, colsum_part, ngroups, K, colsum_out, center, center_out, count, mom, om) != cudaSuccess) {
     cudaGetLastError();
     return false;
   }
@@ -680,21 +671,21 @@ static int launch_fwd(const void* student, const void* teacher, const float* cen
   unsigned* counter = reinterpret_cast<unsigned*>(ws + p.off_counter);
   dim3 grid((p.nslices + kDinoWarps - 1) / kDinoWarps, p.ngroups);
   if (K % p.cols_per_slice == 0)
-    dino_fwd_partial<T, NCROPS, false><<<grid, kDinoThreads, 0, st>>>(
+    launch_pdl((dino_fwd_partial<T, NCROPS, false>), dim3(grid), dim3(kDinoThreads), (size_t)(0), st, 
         (const T*)student, (const T*)teacher, center, B, K, inv_ts * kLog2e, inv_tt * kLog2e,
         p.nslices, p.ngroups, part, colsum_part, 0, B, counter);
   else
-    dino_fwd_partial<T, NCROPS, true><<<grid, kDinoThreads, 0, st>>>(
+    launch_pdl((dino_fwd_partial<T, NCROPS, true>), dim3(grid), dim3(kDinoThreads), (size_t)(0), st, 
         (const T*)student, (const T*)teacher, center, B, K, inv_ts * kLog2e, inv_tt * kLog2e,
         p.nslices, p.ngroups, part, colsum_part, 0, B, counter);
   const int nparts = (int)grid.x;   // the streaming kernel leaves ONE merged record per (sample, CTA along K)
   if (launch_finish<NCROPS>(part, B, nparts, inv_ts, row_stats, sample_loss, loss_out, counter, colsum_part,
                             p.ngroups, K, colsum_out, center, center_out, mom, om, st))
     return check_launch("lafs_dino_fwd");
-  dino_rows_finalize<NCROPS><<<(B + kFinalizeWarps - 1) / kFinalizeWarps, kFinalizeWarps * 32, 0, st>>>(
+  launch_pdl((dino_rows_finalize<NCROPS>), dim3((B + kFinalizeWarps - 1) / kFinalizeWarps), dim3(kFinalizeWarps * 32), (size_t)(0), st, 
       part, B, nparts, inv_ts, row_stats, sample_loss, 0, B);
   const float inv_norm = 1.f / ((float)(2 * NCROPS - 2) * (float)B);
-  dino_tail<<<(K + kDinoThreads - 1) / kDinoThreads, kDinoThreads, 0, st>>>(
+  launch_pdl((dino_tail), dim3((K + kDinoThreads - 1) / kDinoThreads), dim3(kDinoThreads), (size_t)(0), st, 
       sample_loss, B, inv_norm, loss_out, colsum_part, p.ngroups, K, colsum_out, center, center_out,
       (float)(2 * B), mom, om);
   return check_launch("lafs_dino_fwd");
@@ -707,7 +698,7 @@ static int launch_bwd(const void* student, const void* teacher, const float* cen
   constexpr int VEC = VecOf<T>::VEC;
   dim3 grid((K / VEC + kDinoThreads - 1) / kDinoThreads, B);
   const float gcoef = inv_ts / ((float)(2 * NCROPS - 2) * (float)B);
-  dino_bwd_kernel<T, NCROPS><<<grid, kDinoThreads, 0, st>>>(
+  launch_pdl((dino_bwd_kernel<T, NCROPS>), dim3(grid), dim3(kDinoThreads), (size_t)(0), st, 
       (const T*)student, (const T*)teacher, center, row_stats, grad_out, B, K, inv_ts * kLog2e,
       inv_tt * kLog2e, gcoef, (T*)grad_student, 0);
   return check_launch("lafs_dino_bwd");
@@ -779,11 +770,11 @@ static int launch_fused(const void* student, const void* teacher, const float* c
     dim3 grid((p.nslices + kDinoWarps - 1) / kDinoWarps, p.ngroups);
     float* cpart = colsum_part + (size_t)w * p.ngroups * K;
     if (!ragged)
-      dino_fwd_partial<T, NCROPS, false><<<grid, kDinoThreads, 0, st>>>(
+      launch_pdl((dino_fwd_partial<T, NCROPS, false>), dim3(grid), dim3(kDinoThreads), (size_t)(0), st, 
           (const T*)student, (const T*)teacher, center, B, K, inv_ts * kLog2e, inv_tt * kLog2e,
           p.nslices, p.ngroups, part, cpart, b0, bc, counter);
     else
-      dino_fwd_partial<T, NCROPS, true><<<grid, kDinoThreads, 0, st>>>(
+      launch_pdl((dino_fwd_partial<T, NCROPS, true>), dim3(grid), dim3(kDinoThreads), (size_t)(0), st, 
           (const T*)student, (const T*)teacher, center, B, K, inv_ts * kLog2e, inv_tt * kLog2e,
           p.nslices, p.ngroups, part, cpart, b0, bc, counter);
     const int nparts = (int)grid.x;
@@ -791,20 +782,20 @@ static int launch_fused(const void* student, const void* teacher, const float* c
         launch_finish<NCROPS>(part, B, nparts, inv_ts, row_stats, sample_loss, loss_out, counter, colsum_part,
                               p.ngroups, K, colsum_out, center, center_out, mom, om, st)) {
       dim3 gb1((K / VEC + kDinoThreads - 1) / kDinoThreads, B);
-      dino_bwd_kernel<T, NCROPS><<<gb1, kDinoThreads, 0, st>>>(
+      launch_pdl((dino_bwd_kernel<T, NCROPS>), dim3(gb1), dim3(kDinoThreads), (size_t)(0), st, 
           (const T*)student, (const T*)teacher, center, row_stats, grad_out, B, K, inv_ts * kLog2e,
           inv_tt * kLog2e, gcoef, (T*)grad_student, 0);
       return check_launch("lafs_dino_fwd_bwd");
     }
-    dino_rows_finalize<NCROPS><<<(bc + kFinalizeWarps - 1) / kFinalizeWarps, kFinalizeWarps * 32, 0, st>>>(
+    launch_pdl((dino_rows_finalize<NCROPS>), dim3((bc + kFinalizeWarps - 1) / kFinalizeWarps), dim3(kFinalizeWarps * 32), (size_t)(0), st, 
         part, B, nparts, inv_ts, row_stats, sample_loss, b0, bc);
     dim3 gb((K / VEC + kDinoThreads - 1) / kDinoThreads, bc);
-    dino_bwd_kernel<T, NCROPS><<<gb, kDinoThreads, 0, st>>>(
+    launch_pdl((dino_bwd_kernel<T, NCROPS>), dim3(gb), dim3(kDinoThreads), (size_t)(0), st, 
         (const T*)student, (const T*)teacher, center, row_stats, grad_out, B, K, inv_ts * kLog2e,
         inv_tt * kLog2e, gcoef, (T*)grad_student, b0);
   }
   const float inv_norm = 1.f / ((float)(2 * NCROPS - 2) * (float)B);
-  dino_tail<<<(K + kDinoThreads - 1) / kDinoThreads, kDinoThreads, 0, st>>>(
+  launch_pdl((dino_tail), dim3((K + kDinoThreads - 1) / kDinoThreads), dim3(kDinoThreads), (size_t)(0), st, 
       sample_loss, B, inv_norm, loss_out, colsum_part, p.nwaves * p.ngroups, K, colsum_out, center, center_out,
       (float)(2 * B), mom, om);
   return check_launch("lafs_dino_fwd_bwd");
@@ -941,7 +932,7 @@ extern "C" int lafs_center_ema(const float* center, const float* colsum, float c
   if (int brc = lafs::bind_device_of(center)) return brc;
   using namespace lafs;
   LAFS_REQUIRE(center && colsum && center_out && K > 0, LAFS_ERR_ARG, "lafs_center_ema: bad argument");
-  center_ema_kernel<<<(K + 255) / 256, 256, 0, (cudaStream_t)stream>>>(center, colsum, count, momentum,
+  launch_pdl((center_ema_kernel), dim3((K + 255) / 256), dim3(256), (size_t)(0), (cudaStream_t)stream, center, colsum, count, momentum,
                                                                       one_minus_momentum, K, center_out);
   return check_launch("lafs_center_ema");
 }
@@ -960,9 +951,9 @@ extern "C" int lafs_colsum(const void* x, int rows, int K, int dtype, float* out
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((K / vec + kDinoThreads - 1) / kDinoThreads, ngroups);
   float* part = (float*)workspace;
-  if (dtype == LAFS_F32) colsum_partial_kernel<float><<<grid, kDinoThreads, 0, st>>>((const float*)x, rows, K, ngroups, part);
-  else if (dtype == LAFS_BF16) colsum_partial_kernel<__nv_bfloat16><<<grid, kDinoThreads, 0, st>>>((const __nv_bfloat16*)x, rows, K, ngroups, part);
-  else colsum_partial_kernel<__half><<<grid, kDinoThreads, 0, st>>>((const __half*)x, rows, K, ngroups, part);
-  colsum_combine_kernel<<<(K + 255) / 256, 256, 0, st>>>(part, ngroups, K, out);
+  if (dtype == LAFS_F32) launch_pdl((colsum_partial_kernel<float>), dim3(grid), dim3(kDinoThreads), (size_t)(0), st, (const float*)x, rows, K, ngroups, part);
+  else if (dtype == LAFS_BF16) launch_pdl((colsum_partial_kernel<__nv_bfloat16>), dim3(grid), dim3(kDinoThreads), (size_t)(0), st, (const __nv_bfloat16*)x, rows, K, ngroups, part);
+  else launch_pdl((colsum_partial_kernel<__half>), dim3(grid), dim3(kDinoThreads), (size_t)(0), st, (const __half*)x, rows, K, ngroups, part);
+  launch_pdl((colsum_combine_kernel), dim3((K + 255) / 256), dim3(256), (size_t)(0), st, part, ngroups, K, out);
   return check_launch("lafs_colsum");
 }

@@ -24,6 +24,7 @@ __device__ __forceinline__ float ema1(float k, float q, float m, float om) {
 // to co-schedule the EMA next to a kernel that leaves HBM bandwidth unused (one 256-thread CTA per SM).
 __global__ void __launch_bounds__(kEmaThreads)
 ema_multi_kernel(const EmaChunk* __restrict__ table, int nchunks, float m, float om) {
+  pdl_wait();
  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
   const EmaChunk c = table[chunk];
   const int n = (int)c.n;
@@ -76,7 +77,7 @@ extern "C" int lafs_ema_multi(const void* table, int nchunks, float m, float one
   if (nchunks == 0) return LAFS_OK;
   LAFS_REQUIRE(table != nullptr && nchunks > 0, LAFS_ERR_ARG, "lafs_ema_multi: null table or nchunks<0");
   const int grid = (max_ctas > 0 && max_ctas < nchunks) ? max_ctas : nchunks;
-  ema_multi_kernel<<<grid, kEmaThreads, 0, (cudaStream_t)stream>>>(
+  launch_pdl((ema_multi_kernel), dim3(grid), dim3(kEmaThreads), (size_t)(0), (cudaStream_t)stream, 
       reinterpret_cast<const EmaChunk*>(table), nchunks, m, one_minus_m);
   return check_launch("lafs_ema_multi");
 }

@@ -88,6 +88,7 @@ __device__ __forceinline__ void xbarrier(const uint64_t* __restrict__ peer_base,
 __global__ void __launch_bounds__(kXThreads)
 xchg_stats_kernel(const uint64_t* __restrict__ peer_base, int rank, int world, int B, XLayout l,
                   const float* __restrict__ local_stats, float* __restrict__ merged) {
+  pdl_wait();
   __shared__ unsigned s_epoch;
   char* my = reinterpret_cast<char*>(peer_base[rank]);
   unsigned* counters = reinterpret_cast<unsigned*>(my + l.off_counters);
@@ -127,6 +128,7 @@ xchg_stats_kernel(const uint64_t* __restrict__ peer_base, int rank, int world, i
 // of a thread issued before the first use (a peer load is ~2 us of latency).
 __global__ void __launch_bounds__(kXThreads)
 xchg_allreduce_kernel(const uint64_t* __restrict__ peer_base, int rank, int world, XLayout l, int n4) {
+  pdl_wait();
   __shared__ unsigned s_epoch;
   __shared__ int s_last;
   char* my = reinterpret_cast<char*>(peer_base[rank]);
@@ -224,7 +226,7 @@ extern "C" int lafs_xchg_stats(const void* peer_base, int rank, int world, int B
   if (rc) return rc;
   LAFS_REQUIRE(local_stats && merged && ((((uintptr_t)local_stats | (uintptr_t)merged) & 15u) == 0), LAFS_ERR_ARG,
                "lafs_xchg_stats: null or misaligned statistics");
-  xchg_stats_kernel<<<1, kXThreads, 0, (cudaStream_t)stream>>>((const uint64_t*)peer_base, rank, world, B,
+  launch_pdl((xchg_stats_kernel), dim3(1), dim3(kXThreads), (size_t)(0), (cudaStream_t)stream, (const uint64_t*)peer_base, rank, world, B,
                                                                xlayout(world, B, D), local_stats, merged);
   return check_launch("lafs_xchg_stats");
 }
@@ -235,7 +237,7 @@ extern "C" int lafs_xchg_allreduce(const void* peer_base, int rank, int world, i
   int rc = xchg_check(peer_base, rank, world, B, D, "lafs_xchg_allreduce");
   if (rc) return rc;
   const long long n4 = (long long)B * D / 4;
-  xchg_allreduce_kernel<<<kXReduceCtas, kXThreads, 0, (cudaStream_t)stream>>>((const uint64_t*)peer_base, rank, world,
+  launch_pdl((xchg_allreduce_kernel), dim3(kXReduceCtas), dim3(kXThreads), (size_t)(0), (cudaStream_t)stream, (const uint64_t*)peer_base, rank, world,
                                                                          xlayout(world, B, D), (int)n4);
   return check_launch("lafs_xchg_allreduce");
 }

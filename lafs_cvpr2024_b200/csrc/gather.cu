@@ -64,6 +64,7 @@ template <bool RECIP>
 __global__ void __launch_bounds__(kGatherThreads)
 gather_fwd_kernel(const float* __restrict__ imgs, const float* __restrict__ theta, float* __restrict__ out,
                   int total_patches, int C, int H, int W, int n, int r, int layout) {
+  pdl_wait();
   __shared__ float tile[kPatchesPerCta][kPatchPix * kMaxC];
   const int p_local = threadIdx.x >> 6, t = threadIdx.x & 63;
   const int i = t & 7, j = t >> 3;
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(kGatherThreads)
 gather_bwd_kernel(const float* __restrict__ imgs, const float* __restrict__ theta,
                   const float* __restrict__ gout, float* __restrict__ gimgs, float* __restrict__ gtheta,
                   int total_patches, int C, int H, int W, int n, int r, int layout) {
+  pdl_wait();
   __shared__ float red[kPatchesPerCta][2][2];
   const int p_local = threadIdx.x >> 6, t = threadIdx.x & 63;
   const int i = t & 7, j = t >> 3;
@@ -155,6 +157,7 @@ __global__ void __launch_bounds__(128)
 landmark_post_kernel(const float* __restrict__ raw, const float* __restrict__ noise,
                      const int64_t* __restrict__ extract_id, float* __restrict__ theta_out,
                      float* __restrict__ minmax_out, int B, int n, int keep, float scale) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (b >= B) return;
@@ -211,6 +214,7 @@ landmark_post_kernel(const float* __restrict__ raw, const float* __restrict__ no
 __global__ void __launch_bounds__(128)
 landmark_post_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ gtheta,
                          float* __restrict__ graw, int B, int n, float scale) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (b >= B) return;
@@ -287,9 +291,9 @@ extern "C" int lafs_gather_fwd(const float* imgs, const float* theta, float* out
   const int grid = (total + kPatchesPerCta - 1) / kPatchesPerCta;
   cudaStream_t st = (cudaStream_t)stream;
   if (coord_mode == LAFS_COORD_RECIP)
-    gather_fwd_kernel<true><<<grid, kGatherThreads, 0, st>>>(imgs, theta, out, total, C, H, W, n, r, layout);
+    launch_pdl((gather_fwd_kernel<true>), dim3(grid), dim3(kGatherThreads), (size_t)(0), st, imgs, theta, out, total, C, H, W, n, r, layout);
   else
-    gather_fwd_kernel<false><<<grid, kGatherThreads, 0, st>>>(imgs, theta, out, total, C, H, W, n, r, layout);
+    launch_pdl((gather_fwd_kernel<false>), dim3(grid), dim3(kGatherThreads), (size_t)(0), st, imgs, theta, out, total, C, H, W, n, r, layout);
   return check_launch("lafs_gather_fwd");
 }
 
@@ -308,9 +312,9 @@ extern "C" int lafs_gather_bwd(const float* imgs, const float* theta, const floa
   const int grid = (total + kPatchesPerCta - 1) / kPatchesPerCta;
   cudaStream_t st = (cudaStream_t)stream;
   if (coord_mode == LAFS_COORD_RECIP)
-    gather_bwd_kernel<true><<<grid, kGatherThreads, 0, st>>>(imgs, theta, grad_out, grad_imgs, grad_theta, total, C, H, W, n, r, layout);
+    launch_pdl((gather_bwd_kernel<true>), dim3(grid), dim3(kGatherThreads), (size_t)(0), st, imgs, theta, grad_out, grad_imgs, grad_theta, total, C, H, W, n, r, layout);
   else
-    gather_bwd_kernel<false><<<grid, kGatherThreads, 0, st>>>(imgs, theta, grad_out, grad_imgs, grad_theta, total, C, H, W, n, r, layout);
+    launch_pdl((gather_bwd_kernel<false>), dim3(grid), dim3(kGatherThreads), (size_t)(0), st, imgs, theta, grad_out, grad_imgs, grad_theta, total, C, H, W, n, r, layout);
   return check_launch("lafs_gather_bwd");
 }
 
@@ -324,7 +328,7 @@ extern "C" int lafs_landmark_post(const float* raw, const float* noise, const in
   LAFS_REQUIRE(B >= 0 && n > 0, LAFS_ERR_ARG, "lafs_landmark_post: B=%d n=%d", B, n);
   LAFS_REQUIRE(extract_id == nullptr || keep > 0, LAFS_ERR_ARG, "lafs_landmark_post: keep=%d with extract_id", keep);
   if (B == 0) return LAFS_OK;
-  landmark_post_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(raw, noise, extract_id, theta_out, minmax_out,
+  launch_pdl((landmark_post_kernel), dim3((B + 3) / 4), dim3(128), (size_t)(0), (cudaStream_t)stream, raw, noise, extract_id, theta_out, minmax_out,
                                                                      B, n, keep, scale);
   return check_launch("lafs_landmark_post");
 }
@@ -336,6 +340,6 @@ extern "C" int lafs_landmark_post_bwd(const float* raw, const float* grad_theta,
   LAFS_REQUIRE(raw && grad_theta && grad_raw, LAFS_ERR_ARG, "lafs_landmark_post_bwd: null pointer");
   LAFS_REQUIRE(B >= 0 && n > 0, LAFS_ERR_ARG, "lafs_landmark_post_bwd: B=%d n=%d", B, n);
   if (B == 0) return LAFS_OK;
-  landmark_post_bwd_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(raw, grad_theta, grad_raw, B, n, scale);
+  launch_pdl((landmark_post_bwd_kernel), dim3((B + 3) / 4), dim3(128), (size_t)(0), (cudaStream_t)stream, raw, grad_theta, grad_raw, B, n, scale);
   return check_launch("lafs_landmark_post_bwd");
 }

@@ -76,6 +76,7 @@ template <int BN, int MODE, bool PAIR>
 __global__ void __launch_bounds__(kHeadThreads, 1)
 head_gemm_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_constant__ CUtensorMap tmap_w,
                  const HeadParams p) {
+  pdl_wait();
   constexpr int kStageRows = PAIR ? BN / 2 : BN;     // W rows this CTA loads per k step
   constexpr int kStageBytes = kStageRows * 128;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -384,6 +385,7 @@ head_gemm_kernel(const __grid_constant__ CUtensorMap tmap_e, const __grid_consta
 __global__ void __launch_bounds__(256)
 head_merge_kernel(const float* __restrict__ part, int B, int nparts, long long part_stride,
                   long long row_stride, float* __restrict__ out) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (b >= B) return;
@@ -409,6 +411,7 @@ __global__ void __launch_bounds__(256)
 head_loss_kernel(const float* __restrict__ stats, const int64_t* __restrict__ label_a,
                  const int64_t* __restrict__ label_b, float lam, int B, float* __restrict__ row_lse2,
                  float* __restrict__ loss_out) {
+  pdl_wait();
   __shared__ float red[256];
   float acc = 0.f;
   for (int b = threadIdx.x; b < B; b += 256) {
@@ -434,6 +437,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 normalize_rows_kernel(const T* __restrict__ x, int R, int D, __nv_bfloat16* __restrict__ out,
                       float* __restrict__ inv_norm) {
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + warp;
   if (r >= R) return;
@@ -546,13 +550,15 @@ static int launch_head(const CUtensorMap& te, const CUtensorMap& tw, const HeadP
   cfg.blockDim = dim3(kHeadThreads);
   cfg.dynamicSmemBytes = hl.smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = PAIR ? 2 : 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see common.cuh: every kernel starts with pdl_wait()
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   e = cudaLaunchKernelEx(&cfg, kern, te, tw, p);
   LAFS_REQUIRE(e == cudaSuccess, LAFS_ERR_CUDA, "head_gemm_kernel launch: %s", cudaGetErrorString(e));
   return check_launch("head_gemm_kernel");
@@ -653,9 +659,9 @@ extern "C" int lafs_normalize_rows(const void* x, int dtype, int R, int D, void*
   if (R == 0) return LAFS_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = (R + 7) / 8;
-  if (dtype == LAFS_F32) normalize_rows_kernel<float><<<grid, 256, 0, st>>>((const float*)x, R, D, (__nv_bfloat16*)out_bf16, inv_norm);
-  else if (dtype == LAFS_BF16) normalize_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, R, D, (__nv_bfloat16*)out_bf16, inv_norm);
-  else normalize_rows_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, R, D, (__nv_bfloat16*)out_bf16, inv_norm);
+  if (dtype == LAFS_F32) launch_pdl((normalize_rows_kernel<float>), dim3(grid), dim3(256), (size_t)(0), st, (const float*)x, R, D, (__nv_bfloat16*)out_bf16, inv_norm);
+  else if (dtype == LAFS_BF16) launch_pdl((normalize_rows_kernel<__nv_bfloat16>), dim3(grid), dim3(256), (size_t)(0), st, (const __nv_bfloat16*)x, R, D, (__nv_bfloat16*)out_bf16, inv_norm);
+  else launch_pdl((normalize_rows_kernel<__half>), dim3(grid), dim3(256), (size_t)(0), st, (const __half*)x, R, D, (__nv_bfloat16*)out_bf16, inv_norm);
   return check_launch("lafs_normalize_rows");
 }
 
@@ -680,7 +686,7 @@ extern "C" int lafs_head_fwd(const void* e_hat, const void* w_hat, const int64_t
   cudaStream_t st = (cudaStream_t)stream;
   rc = launch_head_any<HEAD_STATS>(te, tw, p, hl, st);
   if (rc) return rc;
-  head_merge_kernel<<<(B + 7) / 8, 256, 0, st>>>(p.part, B, 2 * hl.nranges, 4, (long long)hl.nranges * 8, row_stats);
+  launch_pdl((head_merge_kernel), dim3((B + 7) / 8), dim3(256), (size_t)(0), st, p.part, B, 2 * hl.nranges, 4, (long long)hl.nranges * 8, row_stats);
   return check_launch("lafs_head_fwd/merge");
 }
 
@@ -700,7 +706,7 @@ extern "C" int lafs_head_logits(const void* e_hat, const void* w_hat, const int6
 extern "C" int lafs_head_merge(const float* parts, int nparts, int B, float* row_stats, lafs_stream_t stream) {
   if (int brc = lafs::bind_device_of(parts)) return brc;
   LAFS_REQUIRE(parts && row_stats && nparts > 0 && B > 0, LAFS_ERR_ARG, "lafs_head_merge: bad argument");
-  head_merge_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(parts, B, nparts, (long long)B * 4, 4, row_stats);
+  launch_pdl((head_merge_kernel), dim3((B + 7) / 8), dim3(256), (size_t)(0), (cudaStream_t)stream, parts, B, nparts, (long long)B * 4, 4, row_stats);
   return check_launch("lafs_head_merge");
 }
 
@@ -708,7 +714,7 @@ extern "C" int lafs_head_loss(const float* row_stats, const int64_t* label_a, co
                               float* row_lse2, float* loss_out, lafs_stream_t stream) {
   if (int brc = lafs::bind_device_of(row_stats)) return brc;
   LAFS_REQUIRE(row_stats && label_a && row_lse2 && loss_out && B > 0, LAFS_ERR_ARG, "lafs_head_loss: bad argument");
-  head_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(row_stats, label_a, label_b, lam, B, row_lse2, loss_out);
+  launch_pdl((head_loss_kernel), dim3(1), dim3(256), (size_t)(0), (cudaStream_t)stream, row_stats, label_a, label_b, lam, B, row_lse2, loss_out);
   return check_launch("lafs_head_loss");
 }
 

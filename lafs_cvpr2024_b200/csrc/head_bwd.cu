@@ -57,6 +57,7 @@ template <bool A_MN, int CL>
 __global__ void __launch_bounds__(gb::kThreads, 1)
 gemm_bwd_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const GemmParams p) {
+  pdl_wait();
   using namespace gb;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -251,6 +252,7 @@ struct DiagParams {
 
 // t[c] = sum_q tpart[q][c], in place into row 0 (a thread owns a column: no hazard)
 __global__ void t_reduce_kernel(float* __restrict__ tpart, int tparts, long long ldt, int C) {
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float acc = 0.f;
@@ -261,6 +263,7 @@ __global__ void t_reduce_kernel(float* __restrict__ tpart, int tparts, long long
 __global__ void __launch_bounds__(gb::kThreads, 1)
 dw_diag_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_w, const GemmParams p, const DiagParams dp) {
+  pdl_wait();
   using namespace gb;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -436,6 +439,7 @@ dw_diag_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 __global__ void __launch_bounds__(256)
 normalize_bwd_kernel(const float* __restrict__ g, const __nv_bfloat16* __restrict__ x_hat,
                      const float* __restrict__ inv_norm, int R, int D, float* __restrict__ out, int reverse) {
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int r = blockIdx.x * 8 + warp;
   if (r >= R) return;
@@ -490,6 +494,7 @@ normalize_bwd_kernel(const float* __restrict__ g, const __nv_bfloat16* __restric
 
 __global__ void split_reduce_kernel(const float* __restrict__ part, int splits, long long stride, long long n,
                                     float* __restrict__ out) {
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float acc = 0.f;
@@ -557,10 +562,12 @@ static int launch_gemm_cl(const CUtensorMap& ta, const CUtensorMap& tb, const Ge
   cfg.blockDim = dim3(gb::kThreads);
   cfg.dynamicSmemBytes = gb::kSmem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see common.cuh: every kernel starts with pdl_wait()
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
   const int total = ((p.m_tiles + CL - 1) / CL) * p.n_tiles * p.splits;
   cfg.gridDim = dim3((total < nclusters ? total : nclusters) * CL);
   e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
@@ -637,7 +644,7 @@ extern "C" int lafs_head_bwd_embed(const void* grad_bf16, long long ldg, const v
   else rc = launch_gemm_cl<false, 1>(ta, tb, p, kNumSMs, st);
   if (rc) return rc;
   const long long n = (long long)B * D;
-  split_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const float*)workspace, p.splits, n, n, grad_e_hat);
+  launch_pdl((split_reduce_kernel), dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)(0), st, (const float*)workspace, p.splits, n, n, grad_e_hat);
   return check_launch("lafs_head_bwd_embed");
 }
 
@@ -663,7 +670,7 @@ extern "C" int lafs_head_bwd_weight(const void* grad_bf16, long long ldg, const 
   p.out = grad_w; p.ldo = D; p.split_stride = 0;
   rc = launch_gemm<true>(ta, tb, p, st);
   if (rc) return rc;
-  normalize_bwd_kernel<<<(C_local + 7) / 8, 256, 0, st>>>(grad_w, (const __nv_bfloat16*)w_hat, inv_norm_w, C_local, D, grad_w, 1);
+  launch_pdl((normalize_bwd_kernel), dim3((C_local + 7) / 8), dim3(256), (size_t)(0), st, grad_w, (const __nv_bfloat16*)w_hat, inv_norm_w, C_local, D, grad_w, 1);
   return check_launch("lafs_head_bwd_weight");
 }
 
@@ -674,7 +681,7 @@ extern "C" int lafs_normalize_bwd(const float* g, const void* x_hat_bf16, const 
   LAFS_REQUIRE(g && x_hat_bf16 && inv_norm && out && R >= 0 && D > 0 && D <= 768, LAFS_ERR_ARG, "lafs_normalize_bwd: bad argument");
   if (R == 0) return LAFS_OK;
   LAFS_REQUIRE(D % 8 == 0, LAFS_ERR_ARG, "lafs_normalize_bwd: D=%d must be a multiple of 8", D);
-  normalize_bwd_kernel<<<(R + 7) / 8, 256, 0, (cudaStream_t)stream>>>(g, (const __nv_bfloat16*)x_hat_bf16, inv_norm, R, D, out, 0);
+  launch_pdl((normalize_bwd_kernel), dim3((R + 7) / 8), dim3(256), (size_t)(0), (cudaStream_t)stream, g, (const __nv_bfloat16*)x_hat_bf16, inv_norm, R, D, out, 0);
   return check_launch("lafs_normalize_bwd");
 }
 
@@ -704,6 +711,7 @@ extern "C" size_t lafs_embed_bwd_workspace_bytes(int M, int dim) {
 // ((i*8+j)*3 + c  <-  kernel order c*64 + j*8 + i) and grad_b [dim] (the ones column, k = 192)
 __global__ void embed_dw_unpermute_kernel(const float* __restrict__ part, int splits, int dim, float* __restrict__ grad_w,
                                           float* __restrict__ grad_b, int accumulate) {
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= dim * 193) return;
   const int d = idx / 193, k = idx - d * 193;
@@ -745,7 +753,7 @@ extern "C" int lafs_embed_bwd_weight_perm(const void* grad_emb_bf16, const void*
   rc = launch_gemm<true>(ta, tb, p, st);
   if (rc) return rc;
   const int total = dim * 193;
-  embed_dw_unpermute_kernel<<<(total + 255) / 256, 256, 0, st>>>((const float*)workspace, p.splits, dim, grad_w, grad_b,
+  launch_pdl((embed_dw_unpermute_kernel), dim3((total + 255) / 256), dim3(256), (size_t)(0), st, (const float*)workspace, p.splits, dim, grad_w, grad_b,
                                                                   accumulate ? 1 : 0);
   return check_launch("lafs_embed_bwd_weight_perm");
 }
@@ -776,7 +784,7 @@ extern "C" int lafs_embed_bwd_weight(const void* grad_emb_bf16, const void* toke
   rc = launch_gemm<true>(ta, tb, p, st);
   if (rc) return rc;
   const long long n = (long long)dim * 192;
-  split_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const float*)workspace, p.splits, n, n, grad_w);
+  launch_pdl((split_reduce_kernel), dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)(0), st, (const float*)workspace, p.splits, n, n, grad_w);
   return check_launch("lafs_embed_bwd_weight");
 }
 
@@ -824,11 +832,11 @@ extern "C" int lafs_head_bwd_weight_t(const void* grad_bf16, long long ldg, cons
   p.kblocks_total = (B + 63) / 64; p.kblocks_per_split = p.kblocks_total;
   p.out = grad_w; p.ldo = D; p.split_stride = 0;
   cudaStream_t st = (cudaStream_t)stream;
-  t_reduce_kernel<<<(C_local + 255) / 256, 256, 0, st>>>(tpart, tparts, ldt, C_local);   // row 0 <- sum of the rows
+  launch_pdl((t_reduce_kernel), dim3((C_local + 255) / 256), dim3(256), (size_t)(0), st, tpart, tparts, ldt, C_local);   // row 0 <- sum of the rows
   DiagParams dp{tpart, inv_norm_w};
   cudaError_t e = cudaFuncSetAttribute(dw_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gb::kSmem);
   LAFS_REQUIRE(e == cudaSuccess, LAFS_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   const int total = p.m_tiles * p.n_tiles;
-  dw_diag_kernel<<<total < kNumSMs ? total : kNumSMs, gb::kThreads, gb::kSmem, st>>>(ta, tb, tw, p, dp);
+  launch_pdl((dw_diag_kernel), dim3(total < kNumSMs ? total : kNumSMs), dim3(gb::kThreads), (size_t)(gb::kSmem), st, ta, tb, tw, p, dp);
   return check_launch("lafs_head_bwd_weight_t");
 }

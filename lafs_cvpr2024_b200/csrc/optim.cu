@@ -40,6 +40,7 @@ constexpr int kOptThreads = 256;
 // ---- pass 1: sum of squares per chunk (fixed summation order: deterministic) ---------------------------------
 __global__ void __launch_bounds__(kOptThreads)
 grad_sumsq_kernel(const OptChunk* __restrict__ table, int nchunks, float* __restrict__ chunk_sumsq) {
+  pdl_wait();
   __shared__ float red[kOptThreads / 32];
   const int chunk = blockIdx.x;
   const OptChunk c = table[chunk];
@@ -73,6 +74,7 @@ grad_sumsq_kernel(const OptChunk* __restrict__ table, int nchunks, float* __rest
 // per tensor: norm = sqrt(sum of its chunks), coef = clip/(norm + 1e-6) if that is < 1, else 1 (utils.py:137-140)
 __global__ void clip_coef_kernel(const float* __restrict__ chunk_sumsq, const int* __restrict__ first_chunk, int ntensors,
                                  const float* __restrict__ hyper, float* __restrict__ norms, float* __restrict__ coef) {
+  pdl_wait();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ntensors) return;
   float s = 0.f;
@@ -108,6 +110,7 @@ __device__ __forceinline__ float ema_of(float k, float q, const OptScalars& s) {
 __global__ void __launch_bounds__(kOptThreads)
 adamw_ema_kernel(const OptChunk* __restrict__ table, int nchunks, const float* __restrict__ hyper,
                  const float* __restrict__ coef, const uint8_t* __restrict__ regularized) {
+  pdl_wait();
   OptScalars s;
   s.omb1 = hyper[H_OMB1]; s.b2 = hyper[H_B2]; s.omb2 = hyper[H_OMB2];
   s.step_size = hyper[H_STEP_SIZE]; s.bc2_sqrt = hyper[H_BC2_SQRT]; s.eps = hyper[H_EPS];
@@ -202,8 +205,8 @@ extern "C" int lafs_adamw_ema_multi(const void* table, int nchunks, const int* f
                "lafs_adamw_ema_multi: workspace %zu too small", workspace_bytes);
   cudaStream_t st = (cudaStream_t)stream;
   float* chunk_sumsq = (float*)workspace;
-  grad_sumsq_kernel<<<nchunks, kOptThreads, 0, st>>>(reinterpret_cast<const OptChunk*>(table), nchunks, chunk_sumsq);
-  clip_coef_kernel<<<(ntensors + 127) / 128, 128, 0, st>>>(chunk_sumsq, first_chunk, ntensors, hyper, grad_norms, clip_coef);
-  adamw_ema_kernel<<<nchunks, kOptThreads, 0, st>>>(reinterpret_cast<const OptChunk*>(table), nchunks, hyper, clip_coef, regularized);
+  launch_pdl((grad_sumsq_kernel), dim3(nchunks), dim3(kOptThreads), (size_t)(0), st, reinterpret_cast<const OptChunk*>(table), nchunks, chunk_sumsq);
+  launch_pdl((clip_coef_kernel), dim3((ntensors + 127) / 128), dim3(128), (size_t)(0), st, chunk_sumsq, first_chunk, ntensors, hyper, grad_norms, clip_coef);
+  launch_pdl((adamw_ema_kernel), dim3(nchunks), dim3(kOptThreads), (size_t)(0), st, reinterpret_cast<const OptChunk*>(table), nchunks, hyper, clip_coef, regularized);
   return check_launch("lafs_adamw_ema_multi");
 }

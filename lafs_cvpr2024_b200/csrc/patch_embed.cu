@@ -188,6 +188,7 @@ __device__ __forceinline__ void gather_plane(const InT* __restrict__ plane, uint
 template <typename InT, typename OutT, int DIM>
 __global__ void __launch_bounds__(pe::kThreads, 1)
 gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParams p) {
+  pdl_wait();
   using namespace pe;
   using L = Layout<InT>;
   constexpr int NTB = L::kTokBufs;
@@ -423,6 +424,7 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
 // W fp32 [dim, 192] (feature f = (i*8+j)*3 + c) -> bf16 [dim, 192] with K order c*64 + j*8 + i
 __global__ void embed_weight_prep_kernel(const float* __restrict__ w, const float* __restrict__ bias, int dim,
                                         __nv_bfloat16* __restrict__ out, float* __restrict__ bias_out) {
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < dim && bias_out != nullptr) bias_out[idx] = bias != nullptr ? bias[idx] : 0.f;
   if (idx >= dim * pe::kFeat) return;
@@ -441,7 +443,7 @@ static int launch_embed(const CUtensorMap& tw, const EmbedParams& p, int out_dty
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   LAFS_REQUIRE(e == cudaSuccess, LAFS_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   const int grid = p.nunits < kNumSMs ? p.nunits : kNumSMs;
-  kern<<<grid, pe::kThreads, smem, st>>>(tw, p);
+  launch_pdl((kern), dim3(grid), dim3(pe::kThreads), (size_t)(smem), st, tw, p);
   return check_launch("lafs_gather_embed_fwd");
 }
 
@@ -454,7 +456,7 @@ extern "C" int lafs_embed_weight_prep(const float* weight, const float* bias, in
   if (int brc = lafs::bind_device_of(weight)) return brc;
   LAFS_REQUIRE(weight && out_bf16 && dim > 0, LAFS_ERR_ARG, "lafs_embed_weight_prep: bad argument");
   const int total = dim * pe::kFeat;
-  embed_weight_prep_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(weight, bias, dim, (__nv_bfloat16*)out_bf16, bias_out);
+  launch_pdl((embed_weight_prep_kernel), dim3((total + 255) / 256), dim3(256), (size_t)(0), (cudaStream_t)stream, weight, bias, dim, (__nv_bfloat16*)out_bf16, bias_out);
   return check_launch("lafs_embed_weight_prep");
 }
 

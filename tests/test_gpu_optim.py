@@ -1,7 +1,9 @@
 """GPU parity: the fused student update (per-tensor clip + AdamW + teacher EMA, csrc/optim.cu) against the oracle
 (utils.clip_gradients restated + torch.optim.AdamW + the EMA loop, on the host in fp32).  Tolerance 1e-5 relative
-(two fp32 evaluations of the same formulas: summation order of the norms, FMA contraction on the host); the north
-star's bound for updated / EMA'd weights is 1e-3."""
+on the parameters (two fp32 evaluations of the same formulas; FMA contraction on the host).  The per-tensor norms
+are compared at 5e-5: torch's fp32 CPU reduction is itself 2.1e-5 off the float64 value on a 2112x768 tensor (the
+kernel's fixed-order chunked sum is the closer one), and that relative error carries into the clip coefficient and
+the moments of clipped tensors.  The north star's bound for updated / EMA'd weights is 1e-3."""
 import numpy as np
 import pytest
 import torch
@@ -39,14 +41,14 @@ def _case(shapes, reg, steps, clip, seed=0, cancel=None, teacher=True):
         if clip:
             have = [i for i, x in enumerate(grads) if x is not None]
             got = norms.cpu()[have]
-            np.testing.assert_allclose(got.numpy(), np.array(norms_ref, dtype=np.float32), rtol=3e-6)
+            np.testing.assert_allclose(got.numpy(), np.array(norms_ref, dtype=np.float32), rtol=5e-5)
     for i, (a, b) in enumerate(zip(p_ref, p_gpu)):
         torch.testing.assert_close(b.cpu(), a.detach(), rtol=1e-5, atol=1e-8, msg=lambda m, i=i: f"param {i}: {m}")
     for i, p in enumerate(p_ref):
         st = opt.state.get(p, None)
         if st:
-            torch.testing.assert_close(upd.exp_avg[i].cpu(), st["exp_avg"], rtol=1e-5, atol=1e-10)
-            torch.testing.assert_close(upd.exp_avg_sq[i].cpu(), st["exp_avg_sq"], rtol=1e-5, atol=1e-14)
+            torch.testing.assert_close(upd.exp_avg[i].cpu(), st["exp_avg"], rtol=5e-5, atol=1e-10)
+            torch.testing.assert_close(upd.exp_avg_sq[i].cpu(), st["exp_avg_sq"], rtol=1e-4, atol=1e-14)
     if teacher:
         for a, b in zip(k_ref, k_gpu):
             torch.testing.assert_close(b.cpu(), a, rtol=1e-5, atol=1e-8)
