@@ -232,6 +232,18 @@ LAFS_API int lafs_gather_embed_fwd_save(const void* imgs, int in_dtype, float in
                                         int Bv, int H, int W, int n, int dim, int n_models, void* tokens_perm_out,
                                         lafs_stream_t stream);
 
+/* Sequence form: the kernel's epilogue also does what ViT_face.py:762-768 does after
+ * patch_to_embedding -- `torch.cat((cls_tokens, x), 1); x += pos_embedding[:, :n+1]; x = dropout(x)` -- so out_m is
+ * the transformer input [Bv, n+1, dim]: row 0 = cls_m + pos_m[0], row 1+t = embedding[t] + pos_m[1+t].  pos_m points at
+ * pos_embedding's rows ([>= n+1, dim] fp32), cls_m at cls_token ([dim] fp32); pos0 == NULL selects the plain form.
+ * drop_p in [0,1): inverted dropout with a counter-based mask (a function of drop_seed, model and output element;
+ * torch's Philox stream is not reproduced -- the reference is stochastic here).  tokens_perm_out as above. */
+LAFS_API int lafs_gather_embed_seq_fwd(const void* imgs, int in_dtype, float in_scale, float in_shift, const float* theta,
+                                       const void* w_perm_bf16, const float* bias, void* out0, void* out1, int out_dtype,
+                                       int Bv, int H, int W, int n, int dim, int n_models, void* tokens_perm_out,
+                                       const float* pos0, const float* cls0, const float* pos1, const float* cls1,
+                                       float drop_p, unsigned int drop_seed, lafs_stream_t stream);
+
 /* Backward of patch_to_embedding (the training path of the fused kernel; the reference gets it from
  * autograd through nn.Linear, ViT_face.py:760-761 / lafs_train.py:544): two tcgen05 GEMMs over the
  * M = faces*landmarks token rows.  grad_emb [M,dim], tokens [M,192] ('(p1 p2 c)' order), weight

@@ -40,6 +40,8 @@ SIGNATURES = {
     "lafs_embed_weight_prep": (_i, [_p, _p, _i, _p, _p, _p]),
     "lafs_gather_embed_fwd": (_i, [_p, _i, _f, _f, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "lafs_gather_embed_fwd_save": (_i, [_p, _i, _f, _f, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "lafs_gather_embed_seq_fwd": (_i, [_p, _i, _f, _f, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _f,
+                                       C.c_uint, _p]),
     "lafs_embed_bwd_weight_perm": (_i, [_p, _p, _i, _i, _p, _p, _i, _p, _z, _p]),
     "lafs_normalize_rows": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "lafs_head_workspace_bytes": (_z, [_i, _i, _i]),

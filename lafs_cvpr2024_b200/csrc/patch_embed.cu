@@ -88,7 +88,23 @@ struct EmbedParams {
   float in_scale, in_shift; // normalised pixel = in_scale * raw + in_shift   (1, 0 for fp32 input)
   float pad_raw;            // raw value of a zero-padded (out-of-image) pixel = -in_shift / in_scale
   int debug;                // development ablations (env LAFS_PE_DEBUG): 1 = no stores, 2 = no gather math, 4 = no UMMA
+  // sequence epilogue (ViT_face.py:762-768): out_m is [Bv, n+1, dim]; row 0 = cls_token + pos[0],
+  // row 1+t = embedding[t] + pos[1+t], then dropout(p) -- the torch.cat / += / dropout passes never run
+  int seq;                  // 0: plain [Bv, n, dim] embeddings
+  const float* pos[2];      // per model: pos_embedding rows [>= n+1, dim] fp32
+  const float* cls[2];      // per model: cls_token [dim] fp32
+  float drop_p, drop_scale; // dropout probability and 1/(1-p)  (p = 0: off)
+  uint32_t drop_seed;
 };
+
+// counter-based uniform in [0,1) for the fused dropout: a 32-bit mix of (seed, element index).  The mask is a
+// function of (seed, model, output element) only, so it is reproducible and independent of the launch geometry;
+// it cannot (and need not) reproduce torch's Philox stream -- the reference is itself stochastic here.
+__device__ __forceinline__ float hash_uniform(uint32_t seed, uint32_t idx) {
+  uint32_t x = idx * 0x9E3779B1u + seed;
+  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+  return (float)(x >> 8) * (1.0f / 16777216.0f);
+}
 
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -363,13 +379,42 @@ gather_embed_kernel(const __grid_constant__ CUtensorMap tmap_w, const EmbedParam
               if (t0 + j < ntok) store_out(q + (size_t)j * dim, __uint_as_float(v[j]) + bias);
           }
         };
+        // sequence form: token tt of the group = (face f + tt / n, landmark t = tt % n) -> output row
+        // (f + tt/n)*(n+1) + 1 + t, plus pos_embedding[1 + t] and dropout; the thread that owns landmark 0 of a
+        // face also writes that face's cls row
+        auto emit_seq = [&](int t0, const uint32_t (&v)[32]) {
+          if (p.debug & 1) return;
+          const float* pos = model == 0 ? p.pos[0] : p.pos[1];
+          OutT* base = reinterpret_cast<OutT*>(model == 0 ? p.out[0] : p.out[1]);
+          const uint32_t mseed = p.drop_seed + (uint32_t)model * 0x85EBCA6Bu;
+          int ff = t0 / p.n, t = t0 - ff * p.n;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (t0 + j < ntok) {
+              const size_t row = (size_t)(f + ff) * (p.n + 1) + 1 + t;
+              float val = __uint_as_float(v[j]) + bias + __ldg(pos + (size_t)(1 + t) * dim + dd);
+              if (p.drop_p > 0.f)
+                val = hash_uniform(mseed, (uint32_t)(row * dim + dd)) < p.drop_p ? 0.f : val * p.drop_scale;
+              store_out(base + row * dim + dd, val);
+              if (t == 0) {
+                const float* cls = model == 0 ? p.cls[0] : p.cls[1];
+                float cv = __ldg(cls + dd) + __ldg(pos + dd);
+                if (p.drop_p > 0.f)
+                  cv = hash_uniform(mseed, (uint32_t)((row - 1) * dim + dd)) < p.drop_p ? 0.f : cv * p.drop_scale;
+                store_out(base + (row - 1) * dim + dd, cv);
+              }
+            }
+            if (++t == p.n) { t = 0; ++ff; }
+          }
+        };
         // (software-pipelining the TMEM loads over two register sets bought nothing and cost 24
         //  registers per thread, which matter for co-residency with the EMA kernel)
         for (int t0 = half * 32; t0 < ntok; t0 += 64) {
           uint32_t v[32];
           issue_ld(t0, v);
           tmem_ld_wait();
-          emit(t0, v);
+          if (p.seq) emit_seq(t0, v);
+          else emit(t0, v);
         }
         tc_fence_before();
         __syncwarp();
@@ -471,6 +516,15 @@ extern "C" int lafs_gather_embed_fwd_save(const void* imgs, int in_dtype, float 
                                           const void* w_perm_bf16, const float* bias, void* out0, void* out1, int out_dtype,
                                           int Bv, int H, int W, int n, int dim, int n_models, void* tokens_perm_out,
                                           lafs_stream_t stream) {
+  return lafs_gather_embed_seq_fwd(imgs, in_dtype, in_scale, in_shift, theta, w_perm_bf16, bias, out0, out1, out_dtype, Bv, H, W, n,
+                                   dim, n_models, tokens_perm_out, nullptr, nullptr, nullptr, nullptr, 0.f, 0u, stream);
+}
+
+extern "C" int lafs_gather_embed_seq_fwd(const void* imgs, int in_dtype, float in_scale, float in_shift, const float* theta,
+                                         const void* w_perm_bf16, const float* bias, void* out0, void* out1, int out_dtype,
+                                         int Bv, int H, int W, int n, int dim, int n_models, void* tokens_perm_out,
+                                         const float* pos0, const float* cls0, const float* pos1, const float* cls1,
+                                         float drop_p, unsigned int drop_seed, lafs_stream_t stream) {
   if (int brc = lafs::bind_device_of(imgs)) return brc;
   if (Bv == 0) return LAFS_OK;
   LAFS_REQUIRE(imgs && theta && w_perm_bf16 && bias && out0, LAFS_ERR_ARG, "lafs_gather_embed_fwd: null pointer");
@@ -491,6 +545,15 @@ extern "C" int lafs_gather_embed_fwd_save(const void* imgs, int in_dtype, float 
   p.out[0] = out0; p.out[1] = out1;
   LAFS_REQUIRE(((uintptr_t)tokens_perm_out & 15u) == 0, LAFS_ERR_ARG, "lafs_gather_embed_fwd_save: tokens_perm_out misaligned");
   p.tok_out = (__nv_bfloat16*)tokens_perm_out;
+  if (pos0 != nullptr) {
+    LAFS_REQUIRE(cls0 != nullptr && (n_models == 1 || (pos1 != nullptr && cls1 != nullptr)), LAFS_ERR_ARG,
+                 "lafs_gather_embed_seq_fwd: pos / cls of every model are required");
+    LAFS_REQUIRE(drop_p >= 0.f && drop_p < 1.f, LAFS_ERR_ARG, "lafs_gather_embed_seq_fwd: drop_p=%f outside [0,1)", drop_p);
+    LAFS_REQUIRE((long long)Bv * (n + 1) * dim < (1LL << 32), LAFS_ERR_ARG, "lafs_gather_embed_seq_fwd: output too large for the dropout counter");
+    p.seq = 1;
+    p.pos[0] = pos0; p.cls[0] = cls0; p.pos[1] = pos1; p.cls[1] = cls1;
+    p.drop_p = drop_p; p.drop_scale = 1.f / (1.f - drop_p); p.drop_seed = drop_seed;
+  }
   p.Bv = Bv; p.n = n; p.n_pad = (n + 15) & ~15; p.dim = dim; p.n_models = n_models;
   p.mchunks = n_models * dim / 128;
   // faces per group: as many as fit the tile, traded against load balance over the 148 CTAs.

@@ -178,7 +178,8 @@ def embed_backward_weight(grad_emb, tokens_perm, grad_w=None, grad_b=None, accum
 
 
 @torch.no_grad()
-def gather_embed(imgs, landmarks, weights: PatchEmbedWeights, out_dtype=torch.bfloat16, mean=0.5, std=0.5, save_tokens=None):
+def gather_embed(imgs, landmarks, weights: PatchEmbedWeights, out_dtype=torch.bfloat16, mean=0.5, std=0.5, save_tokens=None,
+                 seq=None, drop_p=0.0, seed=0):
     """tokens(imgs, landmarks) @ W^T + b for every model in `weights`, without materialising the
     patches: list of [B, n, dim] tensors.  Forward only (the SSL landmark CNN is frozen and
     the teacher has no gradient).
@@ -186,7 +187,10 @@ def gather_embed(imgs, landmarks, weights: PatchEmbedWeights, out_dtype=torch.bf
     imgs: fp32 [B,3,112,112] already normalised (the reference's tensors), or uint8 decoded pixels;
     for uint8 the reference's ToTensor + Normalize(mean, std) (lafs_train.py:800-803) runs inside
     the kernel, which quarters the image bytes moved over PCIe / read from HBM.
-    save_tokens: a new_token_buffer(B*n) the kernel also fills with the gathered bf16 tokens (training path)."""
+    save_tokens: a new_token_buffer(B*n) the kernel also fills with the gathered bf16 tokens (training path).
+    seq: one (pos_embedding, cls_token) pair per model -> the kernel's epilogue also does ViT_face.py:762-768
+    (`cat(cls, x)`, `+= pos_embedding[:, :n+1]`, dropout(drop_p)) and the outputs are the transformer inputs
+    [B, n+1, dim]; `seed` selects the dropout mask (counter-based, not torch's stream)."""
     _lib.require_cuda(imgs, landmarks)
     if imgs.dtype == torch.uint8:
         x = imgs.detach().contiguous()
@@ -200,14 +204,27 @@ def gather_embed(imgs, landmarks, weights: PatchEmbedWeights, out_dtype=torch.bf
         raise ValueError("the fused path expects 3-channel images")
     n = th.shape[1]
     m = len(weights.linears)
-    outs = [torch.empty(Bv, n, weights.dim, dtype=out_dtype, device=x.device) for _ in range(m)]
+    pc = [None, None, None, None]
+    if seq is not None:
+        if len(seq) != m:
+            raise ValueError("seq needs one (pos_embedding, cls_token) pair per model")
+        for i, (pos, cls) in enumerate(seq):
+            _lib.require_cuda(pos, cls)
+            pos2 = pos.detach().float().reshape(-1, weights.dim).contiguous()
+            cls1 = cls.detach().float().reshape(-1).contiguous()
+            if pos2.shape[0] < n + 1 or cls1.numel() != weights.dim:
+                raise ValueError(f"pos_embedding needs >= {n + 1} rows of {weights.dim}, cls_token {weights.dim} values")
+            pc[2 * i], pc[2 * i + 1] = pos2, cls1
+    rows = n + 1 if seq is not None else n
+    outs = [torch.empty(Bv, rows, weights.dim, dtype=out_dtype, device=x.device) for _ in range(m)]
     if save_tokens is not None and (save_tokens.shape != (Bv * n, _lib.TOK_LD) or save_tokens.dtype != torch.bfloat16
                                     or not save_tokens.is_contiguous()):
         raise ValueError(f"save_tokens must be a contiguous bf16 [{Bv * n}, {_lib.TOK_LD}] buffer (new_token_buffer)")
-    _lib.call("lafs_gather_embed_fwd_save", x.data_ptr(), in_dtype, scale, shift, th.data_ptr(),
+    _lib.call("lafs_gather_embed_seq_fwd", x.data_ptr(), in_dtype, scale, shift, th.data_ptr(),
               weights.w_perm.data_ptr(), weights.bias.data_ptr(), outs[0].data_ptr(),
               outs[1].data_ptr() if m > 1 else None, _lib.dtype_code(outs[0]), Bv, H, W, n, weights.dim, m,
-              _lib.ptr(save_tokens), _lib.stream())
+              _lib.ptr(save_tokens), _lib.ptr(pc[0]), _lib.ptr(pc[1]), _lib.ptr(pc[2]), _lib.ptr(pc[3]),
+              float(drop_p), int(seed) & 0xFFFFFFFF, _lib.stream())
     return outs
 
 

@@ -259,6 +259,16 @@ class ViT_face_landmark_patch8(nn.Module):
             num_land = self._num_land(x)
             need_grad = torch.is_grad_enabled() and (theta.requires_grad or x.requires_grad
                                                      or self.patch_to_embedding.weight.requires_grad)
+            lin = self.patch_to_embedding
+            if (not need_grad and lin.weight.shape[0] % 128 == 0 and num_land <= 208 and x.shape[1] == 3
+                    and tuple(x.shape[-2:]) == (112, 112) and self.pos_embedding.shape[1] >= num_land + 1):
+                # inference / frozen path: cls row, pos_embedding and dropout are part of the fused kernel's epilogue
+                # (SURVEY 8f row 2): the transformer input leaves ONE kernel
+                p_drop = self.dropout.p if self.training else 0.0
+                seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if p_drop > 0 else 0
+                (x,) = gather_embed(x.float(), theta[:, :num_land], PatchEmbedWeights([(lin.weight, lin.bias)]),
+                                    seq=[(self.pos_embedding, self.cls_token)], drop_p=p_drop, seed=seed)
+                return self._after_embedding(x.to(lin.weight.dtype), label, mask, visualize, save_token, opt, theta)
             x = _tokens_and_embedding(x.float(), theta[:, :num_land], self.patch_to_embedding, need_grad)
         else:
             x = self.patch_to_embedding(x)                       # SSL path: tokens prepared by the landmark CNN
@@ -266,6 +276,9 @@ class ViT_face_landmark_patch8(nn.Module):
         x = torch.cat((self.cls_token.expand(b, -1, -1).to(x.dtype), x), dim=1)
         x = x + self.pos_embedding[:, :(n + 1)].to(x.dtype)
         x = self.dropout(x)
+        return self._after_embedding(x, label, mask, visualize, save_token, opt, theta)
+
+    def _after_embedding(self, x, label, mask, visualize, save_token, opt, theta):
         x = self.transformer(x, mask)
         tokens = x[:, 1:] if save_token else None
         x = x.mean(dim=1) if self.pool == 'mean' else x[:, 0]

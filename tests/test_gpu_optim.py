@@ -47,8 +47,11 @@ def _case(shapes, reg, steps, clip, seed=0, cancel=None, teacher=True):
     for i, p in enumerate(p_ref):
         st = opt.state.get(p, None)
         if st:
-            torch.testing.assert_close(upd.exp_avg[i].cpu(), st["exp_avg"], rtol=5e-5, atol=1e-10)
-            torch.testing.assert_close(upd.exp_avg_sq[i].cpu(), st["exp_avg_sq"], rtol=1e-4, atol=1e-14)
+            # exp_avg is a signed running mean: an element that cancels to ~0 carries the absolute rounding error of
+            # its terms, so the absolute tolerance scales with the tensor (2e-6 of its largest entry)
+            torch.testing.assert_close(upd.exp_avg[i].cpu(), st["exp_avg"], rtol=5e-5, atol=2e-6 * float(st["exp_avg"].abs().max()))
+            torch.testing.assert_close(upd.exp_avg_sq[i].cpu(), st["exp_avg_sq"], rtol=1e-4,
+                                       atol=1e-7 * float(st["exp_avg_sq"].abs().max()))
     if teacher:
         for a, b in zip(k_ref, k_gpu):
             torch.testing.assert_close(b.cpu(), a, rtol=1e-5, atol=1e-8)

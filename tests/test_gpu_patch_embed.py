@@ -148,3 +148,51 @@ def test_saved_tokens_match_oracle_tokens(P, B, n, u8):
     got = buf.float().cpu()
     assert (got[:, :192] - want).abs().max() <= 2 ** -8 * max(1.0, float(want.abs().max())) + 1e-3
     assert bool((got[:, 192] == 1).all()) and bool((got[:, 193:] == 0).all())
+
+
+@pytest.mark.parametrize("B,n,dim,u8", [(9, 196, 768, True), (23, 36, 256, True), (5, 196, 128, False), (160, 36, 384, True)])
+def test_sequence_epilogue_cls_pos_matches_reference_ops(P, B, n, dim, u8):
+    """the fused kernel's sequence epilogue against the reference's op sequence after
+    patch_to_embedding (ViT_face.py:762-768: cat(cls, x); x += pos_embedding[:, :n+1]; dropout off), two models
+    (student / teacher parameters) from one gather.  Same bf16 rounding as the plain form: the sum is formed in fp32
+    and rounded once."""
+    torch.manual_seed(B + n + dim)
+    imgs = torch.randint(0, 256, (B, 3, 112, 112), dtype=torch.uint8) if u8 else torch.rand(B, 3, 112, 112) * 2 - 1
+    ref_img = (imgs.float() / 255 - 0.5) / 0.5 if u8 else imgs
+    th = torch.rand(B, n, 2) * 111 + torch.randn(B, n, 2) * 5
+    lins = [torch.nn.Linear(192, dim), torch.nn.Linear(192, dim)]
+    pos = [torch.randn(1, 197, dim), torch.randn(1, 197, dim)]
+    cls = [torch.randn(1, 1, dim), torch.randn(1, 1, dim)]
+    wts = P.PatchEmbedWeights([(l.weight.detach().cuda(), l.bias.detach().cuda()) for l in lins])
+    outs = P.gather_embed(imgs.cuda(), th.cuda(), wts, out_dtype=torch.float32,
+                          seq=[(pos[0].cuda(), cls[0].cuda()), (pos[1].cuda(), cls[1].cuda())])
+    for m in range(2):
+        x = O.gather_embed(ref_img, th, lins[m].weight.detach(), lins[m].bias.detach(), round_bf16=True)
+        x = torch.cat((cls[m].expand(B, -1, -1), x), dim=1)
+        x = x + pos[m][:, :(n + 1)]
+        assert outs[m].shape == (B, n + 1, dim)
+        assert (outs[m].cpu() - x).abs().max() <= 1e-3 * x.abs().max()
+        assert torch.equal(outs[m][:, 0].cpu(), (cls[m] + pos[m][:, :1]).expand(B, 1, dim)[:, 0])     # cls row: exact
+
+
+def test_sequence_epilogue_dropout_is_inverted_dropout(P):
+    """dropout(p) in the epilogue: every element is either 0 or the p = 0 value times 1/(1-p); the kept fraction is
+    1-p; the mask depends on the seed only (reproducible), and differs between seeds."""
+    torch.manual_seed(0)
+    B, n, dim, p = 64, 36, 256, 0.1
+    imgs = torch.randint(0, 256, (B, 3, 112, 112), dtype=torch.uint8).cuda()
+    th = (torch.rand(B, n, 2) * 111).cuda()
+    lin = torch.nn.Linear(192, dim)
+    wts = P.PatchEmbedWeights([(lin.weight.detach().cuda(), lin.bias.detach().cuda())])
+    seq = [(torch.randn(1, 197, dim).cuda(), torch.randn(1, 1, dim).cuda())]
+    (base,) = P.gather_embed(imgs, th, wts, out_dtype=torch.float32, seq=seq)
+    (a,) = P.gather_embed(imgs, th, wts, out_dtype=torch.float32, seq=seq, drop_p=p, seed=7)
+    (a2,) = P.gather_embed(imgs, th, wts, out_dtype=torch.float32, seq=seq, drop_p=p, seed=7)
+    (b,) = P.gather_embed(imgs, th, wts, out_dtype=torch.float32, seq=seq, drop_p=p, seed=8)
+    assert torch.equal(a, a2) and not torch.equal(a, b)
+    kept = a != 0
+    torch.testing.assert_close(a[kept], (base * (1 / (1 - p)))[kept], rtol=1e-6, atol=1e-6)
+    frac = float(kept.float().mean())
+    assert abs(frac - (1 - p)) < 5e-3, frac
+    assert abs(float((a != 0).float()[:, 0].mean()) - (1 - p)) < 2e-2                  # the cls rows are dropped too
+    assert abs(float(((a != 0) & (b != 0)).float().mean()) - (1 - p) ** 2) < 5e-3       # independent masks
