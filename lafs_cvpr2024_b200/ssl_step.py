@@ -151,26 +151,12 @@ class GraphedSSLStep:
         if with_bwd:                         # student patch_to_embedding backward (lafs_train.py:600 / ViT_face.py:761)
             gw, gb = p.student_embed_backward(i["grad_s_g"], i["grad_s_l"])
         loss, grad = p.loss_and_grad(i["student_out"], i["teacher_out"], epoch, fused=self.fused_loss)
-        cside = getattr(p.loss, "_side", None) if getattr(p.loss, "_center_event", None) is not None else None
-        if cside is not None:
-            # several ranks: the centre exchange is running on the loss's side stream.  The static centre buffer
-            # is refreshed there too, but only after the gradient pass (which still reads the OLD centre from it)
-            # has finished on the main stream; the teacher EMA overlaps both.
-            after_bwd = torch.cuda.Event()
-            after_bwd.record(main)
-            with torch.cuda.stream(cside):
-                cside.wait_event(after_bwd)
-                self.center.copy_(p.loss.center)
-            p.loss._center_event = None
-        else:
-            self.center.copy_(p.loss.center)          # static centre buffer <- re-bound new centre
+        self.center.copy_(p.loss.center)              # static centre buffer <- re-bound new centre
         p.loss.center = self.center
         if self.overlap_ema:
             main.wait_stream(self.side)
         else:
             p.ema_step(momentum)
-        if cside is not None:
-            main.wait_stream(cside)
         self.out = {"loss": loss.detach(), "grad_student": grad, "s_g": s_g, "t_g": t_g, "s_l": s_l,
                     "grad_embed_w": gw, "grad_embed_b": gb}
 

@@ -1,7 +1,10 @@
 #!/bin/bash
-# gpurun with retry while the pod answers "busy" (exit code 3: nothing charged).  usage: gpurun_retry.sh <timeout> '<command>'
+# gpurun with retry while the pod answers "busy" (exit code 3: nothing charged).
+# usage: gpurun_retry.sh <timeout> '<command>' [gpus]
+G=""
+if [ -n "$3" ]; then G="--gpus $3"; fi
 for i in $(seq 1 40); do
-  /usr/local/graft/bin/gpurun --timeout "$1" -- "$2"
+  /usr/local/graft/bin/gpurun $G --timeout "$1" -- "$2"
   rc=$?
   if [ $rc -ne 3 ]; then exit $rc; fi
   sleep 90
