@@ -75,8 +75,10 @@ def _dw_diag_enabled(D):
     return os.environ.get("LAFS_DW_DIAG", "1") not in ("", "0") and D % 64 == 0
 
 
-def _head_backward(G, ldg, e_hat, w_hat, inv_e, inv_w, B, C, D, sharded, xchg=None, tpart=None):
-    """dE [B,D], dW [C,D] (fp32) from the bf16 logit gradient G [B, ldg] via two tcgen05 GEMMs."""
+def _head_backward(G, ldg, e_hat, w_hat, inv_e, inv_w, B, C, D, sharded, xchg=None, tpart=None, rows=None):
+    """dE [B,D], dW [C,D] (fp32) from the bf16 logit gradient G [B, ldg] via two tcgen05 GEMMs.
+    rows=(lo, n): batch-sharded caller -- only rows [lo, lo+n) of dE are wanted on this rank: the partial dE_hat of
+    the class shards is reduce-scattered (NCCL) instead of all-reduced, and the Jacobian runs on those rows only."""
     dev = e_hat.device
     nbytes = _lib.lib().lafs_head_bwd_workspace_bytes(B, C, D)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
@@ -85,10 +87,20 @@ def _head_backward(G, ldg, e_hat, w_hat, inv_e, inv_w, B, C, D, sharded, xchg=No
               ws.data_ptr(), nbytes, _lib.stream())
     if sharded and xchg is not None:
         de_hat = xchg.allreduce_de()                 # sum over the class shards through peer memory
+        if rows is not None:
+            de_hat = de_hat[rows[0]:rows[0] + rows[1]]
+    elif sharded and rows is not None:
+        mine = torch.empty(rows[1], D, dtype=torch.float32, device=dev)
+        dist.reduce_scatter_tensor(mine, de_hat)     # sum over the class shards, each rank keeps its batch slice
+        de_hat = mine
     elif sharded:
         dist.all_reduce(de_hat)                      # sum over the class shards
+    if rows is not None:
+        e_hat, inv_e, nb = e_hat[rows[0]:rows[0] + rows[1]], inv_e[rows[0]:rows[0] + rows[1]], rows[1]
+    else:
+        nb = B
     de = torch.empty_like(de_hat)
-    _lib.call("lafs_normalize_bwd", de_hat.data_ptr(), e_hat.data_ptr(), inv_e.data_ptr(), B, D, de.data_ptr(),
+    _lib.call("lafs_normalize_bwd", de_hat.data_ptr(), e_hat.data_ptr(), inv_e.data_ptr(), nb, D, de.data_ptr(),
               _lib.stream())
     dw = torch.empty(C, D, dtype=torch.float32, device=dev)
     if tpart is not None:
@@ -106,6 +118,22 @@ class _HeadLossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, input, weight, head, la, lb, lam):
+        ctx.rows = None
+        if getattr(head, "batch_sharded", False) and head.shard is not None and head.shard[1] > 1:
+            # every rank holds B/R samples; the class shards need all of them -> all_gather of the
+            # embeddings and labels (the reference's only precedent is the replicated batch, ViT_face.py:55-64)
+            world, rank = head.shard[1], head.shard[0]
+            b_loc = input.shape[0]
+            full = torch.empty(world * b_loc, input.shape[1], dtype=input.dtype, device=input.device)
+            dist.all_gather_into_tensor(full, input.detach().contiguous())
+            la_f = torch.empty(world * b_loc, dtype=la.dtype, device=la.device)
+            dist.all_gather_into_tensor(la_f, la)
+            if lb is not None:
+                lb_f = torch.empty(world * b_loc, dtype=lb.dtype, device=lb.device)
+                dist.all_gather_into_tensor(lb_f, lb)
+                lb = lb_f
+            input, la = full, la_f
+            ctx.rows = (rank * b_loc, b_loc)
         B, D = input.shape
         C = weight.shape[0]
         e_hat, inv_e = _prep(input, want_inv=True)
@@ -158,7 +186,7 @@ class _HeadLossFn(torch.autograd.Function):
             _lib.call("lafs_head_grad_logits", e_hat.data_ptr(), w_hat.data_ptr(), la.data_ptr(),
                       lb.data_ptr() if has_b else None, lam, B, C, D, class_lo, s, m, kind, lse2.data_ptr(),
                       g.data_ptr(), s / B, G.data_ptr(), ldg, _lib.stream())
-        de, dw = _head_backward(G, ldg, e_hat, w_hat, inv_e, inv_w, B, C, D, sharded, ctx.xchg, tpart)
+        de, dw = _head_backward(G, ldg, e_hat, w_hat, inv_e, inv_w, B, C, D, sharded, ctx.xchg, tpart, rows=ctx.rows)
         return de.to(in_dtype), dw, None, None, None, None
 
 
@@ -206,8 +234,13 @@ class _HeadLogitsFn(torch.autograd.Function):
 class _MarginHead(nn.Module):
     kind = KIND_COSFACE
 
-    def __init__(self, in_features, out_features, device_id, s=64.0, m=0.4, shard=None):
+    def __init__(self, in_features, out_features, device_id, s=64.0, m=0.4, shard=None, batch_sharded=False):
+        """shard=(rank, world): keep the torch.chunk class slice of this rank (ViT_face.py:56).
+        batch_sharded (with shard): forward_loss takes this rank's B/world samples, all-gathers embeddings and
+        labels, and its backward reduce-scatters dE back to the owners; otherwise every rank is handed
+        the global batch and dE is all-reduced.  The loss is the mean over the GLOBAL batch in both forms."""
         super().__init__()
+        self.batch_sharded = bool(batch_sharded)
         self.in_features = in_features
         self.out_features = out_features
         self.device_id = device_id
@@ -345,12 +378,12 @@ class _MarginHead(nn.Module):
 class CosFace(_MarginHead):
     kind = KIND_COSFACE
 
-    def __init__(self, in_features, out_features, device_id, s=64.0, m=0.4, shard=None):
-        super().__init__(in_features, out_features, device_id, s, m, shard)
+    def __init__(self, in_features, out_features, device_id, s=64.0, m=0.4, shard=None, batch_sharded=False):
+        super().__init__(in_features, out_features, device_id, s, m, shard, batch_sharded)
 
 
 class ArcFace(_MarginHead):
     kind = KIND_ARCFACE
 
-    def __init__(self, in_features, out_features, device_id, s=64.0, m=0.5, shard=None):
-        super().__init__(in_features, out_features, device_id, s, m, shard)
+    def __init__(self, in_features, out_features, device_id, s=64.0, m=0.5, shard=None, batch_sharded=False):
+        super().__init__(in_features, out_features, device_id, s, m, shard, batch_sharded)

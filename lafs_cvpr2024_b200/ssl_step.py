@@ -102,10 +102,11 @@ class GraphedSSLStep:
 
     def __init__(self, path: SSLHotPath, static_inputs: dict, epoch: int, momentum: float, overlap_ema=False, ema_ctas=444,
                  fused_loss=True, center=None):
-        """overlap_ema: put the teacher EMA (as `ema_ctas` persistent CTAs) on a second captured stream
-        so that it runs concurrently with the gather->embed / DINO kernels.  Measured on B200: between
-        -3 % and +17 % step time depending on the box (the persistent CTAs halve the occupancy of the
-        DINO forward kernel), so it is off by default."""
+        """overlap_ema: put the teacher EMA (as `ema_ctas` persistent CTAs; 0 = one CTA per chunk) on a second
+        captured stream.  True / "early": forked before the gather->embed kernels (measured on B200 in round 1:
+        between -3 % and +17 % step time; the gather CTA fills an SM's registers, so the EMA cannot co-reside with it).
+        "late": forked AFTER the gather->embed kernels, next to the patch-embed backward GEMMs and the DINO kernels,
+        which leave 45-55 % of the HBM bandwidth idle -- the EMA (HBM-bound at 0.95) fills it."""
         self.path, self.inp = path, static_inputs
         self.overlap_ema = overlap_ema
         self.fused_loss = fused_loss
@@ -136,7 +137,9 @@ class GraphedSSLStep:
         p, i = self.path, self.inp
         p.loss.center = self.center
         main = torch.cuda.current_stream()
-        if self.overlap_ema:
+        early = self.overlap_ema in (True, "early")
+        late = self.overlap_ema == "late"
+        if early:
             # the EMA reads the teacher's patch_to_embedding weights that the weight-prep kernels
             # also read, and writes them: run the prep first, then fork
             p.embed_global.refresh()
@@ -146,7 +149,11 @@ class GraphedSSLStep:
                 p.ema_step(momentum, max_ctas=self.ema_ctas)
         with_bwd = "grad_s_g" in i          # synthetic gradients of the student's embedded tokens (static inputs)
         s_g, t_g, s_l = p.landmarks_and_embeddings(i["raw_g"], i["noise_g"], i["img_g"], i["raw_l"], i["noise_l"],
-                                                   i["idx_l"], i["img_l"], refresh=not self.overlap_ema, keep_tokens=with_bwd)
+                                                   i["idx_l"], i["img_l"], refresh=not early, keep_tokens=with_bwd)
+        if late:      # the teacher's embedding weights have been read by the kernels above: the EMA may now move them
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side):
+                p.ema_step(momentum, max_ctas=self.ema_ctas)
         gw = gb = None
         if with_bwd:                         # student patch_to_embedding backward (lafs_train.py:600 / ViT_face.py:761)
             gw, gb = p.student_embed_backward(i["grad_s_g"], i["grad_s_l"])

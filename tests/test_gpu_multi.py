@@ -55,6 +55,20 @@ def _worker(rank, world, port, ret):
         dist.all_gather(gx_all, x2.grad.contiguous())
         assert all(torch.equal(gx_all[0], g) for g in gx_all)
         h2._xchg[(B, D)].check()
+        # batch-sharded form: each rank feeds B/world samples; all_gather(E, labels) in, reduce_scatter(dE) out
+        bl = B // world
+        for peer in (False, True):
+            h3 = P.CosFace(D, C, None, shard=(rank, world), batch_sharded=True).cuda()
+            if peer:
+                h3.enable_peer_exchange()
+            with torch.no_grad():
+                h3.weight.copy_(w[lo:hi])
+            x3 = x[rank * bl:(rank + 1) * bl].cuda().requires_grad_(True)
+            l3 = h3.forward_loss(x3, lab[rank * bl:(rank + 1) * bl].cuda())
+            l3.backward()
+            assert abs(float(l3) - float(lf)) <= 1e-5 * abs(float(lf)), (peer, float(l3), float(lf))
+            assert (x3.grad - xf.grad[rank * bl:(rank + 1) * bl]).abs().max() <= 2e-3 * xf.grad.abs().max()
+            assert (h3.weight.grad - full.weight.grad[lo:hi]).abs().max() <= 2e-3 * full.weight.grad.abs().max()
         # DINO centre: every rank ends with the same centre = EMA of the global teacher mean
         K = 4096
         g = torch.Generator().manual_seed(10 + rank)

@@ -10,13 +10,15 @@ B, L = bench.B_PER_GPU, bench.N_LOCAL
 host = bench.make_host_inputs(B, 1, uint8=True)
 st = bench.make_device_state(B, 2, dev)
 inp = {k: v.to(dev) for k, v in host.items()}
-inp.update(raw_g=st["raw_g"], raw_l=st["raw_l"], student_out=st["student_out"], teacher_out=st["teacher_out"])
+inp.update(raw_g=st["raw_g"], raw_l=st["raw_l"], student_out=st["student_out"], teacher_out=st["teacher_out"],
+           grad_s_g=st["grad_s_g"], grad_s_l=st["grad_s_l"])
 path = SSLHotPath(bench.OUT_DIM, L, st["teacher_params"], st["student_params"],
                   student_embed=(st["student_params"][1], st["student_params"][2]),
                   teacher_embed=(st["teacher_params"][1], st["teacher_params"][2]))
 path.loss.center = torch.randn(1, bench.OUT_DIM, device=dev) * 0.1
 import sys as _s
-g = GraphedSSLStep(path, inp, epoch=3, momentum=0.996, overlap_ema=("--overlap" in _s.argv),
+mode = os.environ.get("EMA_OVERLAP", "")          # "", "early", "late"
+g = GraphedSSLStep(path, inp, epoch=3, momentum=0.996, overlap_ema=(mode or False),
                    ema_ctas=int(os.environ.get("EMA_CTAS", "148")))
 def t(fn, n=50):
     for _ in range(5): fn()
@@ -30,4 +32,4 @@ c0 = g.center.clone()
 l1 = float(g.replay()); c1 = g.center.clone()
 l2 = float(g.replay()); c2 = g.center.clone()
 print("loss", l1, l2, "centre moved:", float((c1 - c0).abs().max()), float((c2 - c1).abs().max()))
-print("graph replay ms/step: %.4f" % t(g.replay))
+print("EMA_OVERLAP=%r EMA_CTAS=%s graph replay ms/step: %.4f" % (mode, os.environ.get("EMA_CTAS", "148"), t(g.replay)))
