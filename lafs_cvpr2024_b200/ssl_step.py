@@ -138,7 +138,8 @@ class GraphedSSLStep:
         p.loss.center = self.center
         main = torch.cuda.current_stream()
         early = self.overlap_ema in (True, "early")
-        late = self.overlap_ema == "late"
+        late = self.overlap_ema in ("late", "late2")
+        side2 = self.overlap_ema == "late2"      # "late2": the patch-embed backward GEMMs get their own stream as well
         if early:
             # the EMA reads the teacher's patch_to_embedding weights that the weight-prep kernels
             # also read, and writes them: run the prep first, then fork
@@ -155,13 +156,21 @@ class GraphedSSLStep:
             with torch.cuda.stream(self.side):
                 p.ema_step(momentum, max_ctas=self.ema_ctas)
         gw = gb = None
-        if with_bwd:                         # student patch_to_embedding backward (lafs_train.py:600 / ViT_face.py:761)
+        if with_bwd and side2:
+            if getattr(self, "side_b", None) is None:
+                self.side_b = torch.cuda.Stream()
+            self.side_b.wait_stream(main)
+            with torch.cuda.stream(self.side_b):
+                gw, gb = p.student_embed_backward(i["grad_s_g"], i["grad_s_l"])
+        elif with_bwd:                       # student patch_to_embedding backward (lafs_train.py:600 / ViT_face.py:761)
             gw, gb = p.student_embed_backward(i["grad_s_g"], i["grad_s_l"])
         loss, grad = p.loss_and_grad(i["student_out"], i["teacher_out"], epoch, fused=self.fused_loss)
         self.center.copy_(p.loss.center)              # static centre buffer <- re-bound new centre
         p.loss.center = self.center
         if self.overlap_ema:
             main.wait_stream(self.side)
+            if side2 and with_bwd:
+                main.wait_stream(self.side_b)
         else:
             p.ema_step(momentum)
         self.out = {"loss": loss.detach(), "grad_student": grad, "s_g": s_g, "t_g": t_g, "s_l": s_l,
