@@ -10,6 +10,61 @@ import torch.multiprocessing as mp
 pytestmark = pytest.mark.gpu
 
 
+def _guarded(rank, world, port, ret, body):
+    """Run a worker body; on any failure record the traceback and leave at once (a rank that raised must not sit in
+    destroy_process_group while its peer waits in a collective: that turns an assertion into a hang)."""
+    import datetime
+    import traceback
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank),
+                            timeout=datetime.timedelta(seconds=60))
+    try:
+        globals()[body](rank, world, ret)
+        torch.cuda.synchronize()
+        ret[rank] = "ok"
+    except BaseException:
+        traceback.print_exc()
+        ret[rank] = "FAILED: " + traceback.format_exc()[-1500:]
+        os._exit(1)
+    dist.destroy_process_group()
+
+
+def _body_batch_sharded(rank, world, ret):
+    """SURVEY 8e batch contract: each rank feeds B/world samples; all_gather(E, labels) in, reduce_scatter(dE) out."""
+    import sys
+    import lafs_cvpr2024_b200 as P
+    torch.manual_seed(0)
+    B, C, D = 192, 10007, 512
+    x, w = torch.randn(B, D), torch.randn(C, D) * 0.05
+    lab = torch.randint(0, C, (B,))
+    lo, hi = P.shard_bounds(C, world)[rank]
+    full = P.CosFace(D, C, None).cuda()
+    with torch.no_grad():
+        full.weight.copy_(w)
+    xf = x.cuda().requires_grad_(True)
+    lf = full.forward_loss(xf, lab.cuda())
+    lf.backward()
+    bl = B // world
+    for peer in (False, True):
+        print(f"[rank {rank}] batch-sharded head, peer={peer}", file=sys.stderr, flush=True)
+        h3 = P.CosFace(D, C, None, shard=(rank, world), batch_sharded=True).cuda()
+        if peer:
+            h3.enable_peer_exchange()
+        with torch.no_grad():
+            h3.weight.copy_(w[lo:hi])
+        x3 = x[rank * bl:(rank + 1) * bl].cuda().requires_grad_(True)
+        l3 = h3.forward_loss(x3, lab[rank * bl:(rank + 1) * bl].cuda())
+        print(f"[rank {rank}] forward done", file=sys.stderr, flush=True)
+        l3.backward()
+        torch.cuda.synchronize()
+        print(f"[rank {rank}] backward done", file=sys.stderr, flush=True)
+        assert abs(float(l3) - float(lf)) <= 1e-5 * abs(float(lf)), (peer, float(l3), float(lf))
+        assert (x3.grad - xf.grad[rank * bl:(rank + 1) * bl]).abs().max() <= 2e-3 * xf.grad.abs().max()
+        assert (h3.weight.grad - full.weight.grad[lo:hi]).abs().max() <= 2e-3 * full.weight.grad.abs().max()
+
+
 def _worker(rank, world, port, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -55,20 +110,6 @@ def _worker(rank, world, port, ret):
         dist.all_gather(gx_all, x2.grad.contiguous())
         assert all(torch.equal(gx_all[0], g) for g in gx_all)
         h2._xchg[(B, D)].check()
-        # batch-sharded form: each rank feeds B/world samples; all_gather(E, labels) in, reduce_scatter(dE) out
-        bl = B // world
-        for peer in (False, True):
-            h3 = P.CosFace(D, C, None, shard=(rank, world), batch_sharded=True).cuda()
-            if peer:
-                h3.enable_peer_exchange()
-            with torch.no_grad():
-                h3.weight.copy_(w[lo:hi])
-            x3 = x[rank * bl:(rank + 1) * bl].cuda().requires_grad_(True)
-            l3 = h3.forward_loss(x3, lab[rank * bl:(rank + 1) * bl].cuda())
-            l3.backward()
-            assert abs(float(l3) - float(lf)) <= 1e-5 * abs(float(lf)), (peer, float(l3), float(lf))
-            assert (x3.grad - xf.grad[rank * bl:(rank + 1) * bl]).abs().max() <= 2e-3 * xf.grad.abs().max()
-            assert (h3.weight.grad - full.weight.grad[lo:hi]).abs().max() <= 2e-3 * full.weight.grad.abs().max()
         # DINO centre: every rank ends with the same centre = EMA of the global teacher mean
         K = 4096
         g = torch.Generator().manual_seed(10 + rank)
@@ -107,3 +148,20 @@ def test_sharded_head_and_center_two_gpus():
         ret = mgr.dict()
         mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
         assert dict(ret) == {0: "ok", 1: "ok"}
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_batch_sharded_head_two_gpus():
+    world = 2
+    port = 29900 + (os.getpid() % 100)
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        ctx = mp.spawn(_guarded, args=(world, port, ret, "_body_batch_sharded"), nprocs=world, join=False)
+        import time
+        t0 = time.time()
+        while time.time() - t0 < 150 and any(p.is_alive() for p in ctx.processes):
+            time.sleep(0.5)
+        for p in ctx.processes:
+            if p.is_alive():
+                p.kill()
+        assert dict(ret) == {0: "ok", 1: "ok"}, dict(ret)
