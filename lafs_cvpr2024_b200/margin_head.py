@@ -95,12 +95,11 @@ def _head_backward(G, ldg, e_hat, w_hat, inv_e, inv_w, B, C, D, sharded, xchg=No
         de_hat = mine
     elif sharded:
         dist.all_reduce(de_hat)                      # sum over the class shards
+    e_rows, inv_rows, nb = e_hat, inv_e, B          # the rows whose dE this rank returns (dW below needs ALL rows of e_hat)
     if rows is not None:
-        e_hat, inv_e, nb = e_hat[rows[0]:rows[0] + rows[1]], inv_e[rows[0]:rows[0] + rows[1]], rows[1]
-    else:
-        nb = B
+        e_rows, inv_rows, nb = e_hat[rows[0]:rows[0] + rows[1]], inv_e[rows[0]:rows[0] + rows[1]], rows[1]
     de = torch.empty_like(de_hat)
-    _lib.call("lafs_normalize_bwd", de_hat.data_ptr(), e_hat.data_ptr(), inv_e.data_ptr(), nb, D, de.data_ptr(),
+    _lib.call("lafs_normalize_bwd", de_hat.data_ptr(), e_rows.data_ptr(), inv_rows.data_ptr(), nb, D, de.data_ptr(),
               _lib.stream())
     dw = torch.empty(C, D, dtype=torch.float32, device=dev)
     if tpart is not None:
