@@ -31,6 +31,17 @@ def _guarded(rank, world, port, ret, body):
     dist.destroy_process_group()
 
 
+def _spawn_and_wait(body, world, port, ret, limit=200):
+    import time
+    ctx = mp.spawn(_guarded, args=(world, port, ret, body), nprocs=world, join=False)
+    t0 = time.time()
+    while time.time() - t0 < limit and any(p.is_alive() for p in ctx.processes):
+        time.sleep(0.5)
+    for p in ctx.processes:
+        if p.is_alive():
+            p.kill()
+
+
 def _body_batch_sharded(rank, world, ret):
     """SURVEY 8e batch contract: each rank feeds B/world samples; all_gather(E, labels) in, reduce_scatter(dE) out."""
     import sys
@@ -65,12 +76,8 @@ def _body_batch_sharded(rank, world, ret):
         assert (h3.weight.grad - full.weight.grad[lo:hi]).abs().max() <= 2e-3 * full.weight.grad.abs().max()
 
 
-def _worker(rank, world, port, ret):
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-    try:
+def _body_main(rank, world, ret):
+    if True:
         import lafs_cvpr2024_b200 as P
         torch.manual_seed(0)
         B, C, D = 192, 10007, 512
@@ -135,9 +142,6 @@ def _worker(rank, world, port, ret):
         cs = [torch.empty_like(crit3.center) for _ in range(world)]
         dist.all_gather(cs, crit3.center.contiguous())
         assert all(torch.equal(cs[0], c) for c in cs)      # identical bits on every rank
-        ret[rank] = "ok"
-    finally:
-        dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
@@ -146,8 +150,8 @@ def test_sharded_head_and_center_two_gpus():
     port = 29800 + (os.getpid() % 100)
     with mp.Manager() as mgr:
         ret = mgr.dict()
-        mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
-        assert dict(ret) == {0: "ok", 1: "ok"}
+        _spawn_and_wait("_body_main", world, port, ret)
+        assert dict(ret) == {0: "ok", 1: "ok"}, dict(ret)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
@@ -156,12 +160,5 @@ def test_batch_sharded_head_two_gpus():
     port = 29900 + (os.getpid() % 100)
     with mp.Manager() as mgr:
         ret = mgr.dict()
-        ctx = mp.spawn(_guarded, args=(world, port, ret, "_body_batch_sharded"), nprocs=world, join=False)
-        import time
-        t0 = time.time()
-        while time.time() - t0 < 150 and any(p.is_alive() for p in ctx.processes):
-            time.sleep(0.5)
-        for p in ctx.processes:
-            if p.is_alive():
-                p.kill()
+        _spawn_and_wait("_body_batch_sharded", world, port, ret)
         assert dict(ret) == {0: "ok", 1: "ok"}, dict(ret)
