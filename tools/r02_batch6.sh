@@ -10,7 +10,8 @@ for mode in "" late late2 early; do for ctas in 0 148 296; do
 done; done | tee gpurun_out/ema_overlap_sweep.txt
 echo "=== other SSL configs"
 for c in cfg1_L8 cfg4 cfg0; do
-  $T 600 python bench.py --config $c --steps 100 --warmup 5 > gpurun_out/bench_$c.json 2> gpurun_out/bench_$c.err
+  EXTRA="--no-cpu --no-ref-gpu"; if [ $c == cfg0 ]; then EXTRA=""; fi
+  $T 600 python bench.py --config $c --steps 100 --warmup 5 $EXTRA > gpurun_out/bench_$c.json 2> gpurun_out/bench_$c.err
   python - <<PY
 import json
 try:
