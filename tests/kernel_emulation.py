@@ -98,12 +98,33 @@ def xchg_allreduce(parts):
     return out.reshape(np.asarray(parts[0]).shape)
 
 
-def dino_sliced_loss(student, teacher, center, ncrops, inv_ts, inv_tt, slice_cols=256):
+def _merge_records(rec_t, rec_s, group):
+    """merge_cta_records (csrc/dino.cu): the records of `group` adjacent slices -> one record of the same format
+    (teacher: max, Z, A rescaled to the group max; student: max, sum)."""
+    B, nsl = rec_t.shape[:2]
+    ng = -(-nsl // group)
+    out_t = np.zeros((B, ng) + rec_t.shape[2:])
+    out_s = np.zeros((B, ng) + rec_s.shape[2:])
+    for g in range(ng):
+        rt, rs = rec_t[:, g * group:(g + 1) * group], rec_s[:, g * group:(g + 1) * group]
+        m = rt[..., 0].max(1)
+        f = np.exp2(rt[..., 0] - m[:, None])
+        out_t[:, g, :, 0] = m
+        out_t[:, g, :, 1] = (rt[..., 1] * f).sum(1)
+        out_t[:, g, :, 2] = (rt[..., 2] * f).sum(1)
+        m = rs[..., 0].max(1)
+        out_s[:, g, :, 0] = m
+        out_s[:, g, :, 1] = (rs[..., 1] * np.exp2(rs[..., 0] - m[:, None])).sum(1)
+    return out_t, out_s
+
+
+def dino_sliced_loss(student, teacher, center, ncrops, inv_ts, inv_tt, slice_cols=256, cta_slices=1):
     """The DINO forward as the kernels decompose it (csrc/dino.cu), in float64: per (sample, column slice)
     partial records in the log2 domain -- teacher view iq: (max, Z, A) with A = sum_k e_iq,k * (S_k - s_iq,k),
     S = sum of the student rows; student crop v: (max, sum) -- then dino_finish's two-pass merge over the
     slices, the per-sample loss  sum_v n_v*lse(s_v/ts) - (1/ts) * sum_iq A_iq/Z_iq  and the mean over
-    samples / (2*ncrops - 2).  Returns (loss, per-row log2-domain lse [ncrops+2, B], column sums [K])."""
+    samples / (2*ncrops - 2).  cta_slices = 8 adds the per-CTA pre-merge of 8 adjacent slice records in between
+    (merge_cta_records).  Returns (loss, per-row log2-domain lse [ncrops+2, B], column sums [K])."""
     s = np.asarray(student, dtype=np.float64)
     t = np.asarray(teacher, dtype=np.float64)
     c = np.asarray(center, dtype=np.float64).reshape(-1)
@@ -128,6 +149,8 @@ def dino_sliced_loss(student, teacher, center, ncrops, inv_ts, inv_tt, slice_col
             for v in range(ncrops):
                 mx = srows[v].max() * a_s
                 rec_s[b, sl, v] = (mx, np.exp2(srows[v] * a_s - mx).sum())
+    if cta_slices > 1:      # the streaming kernel merges the records of a CTA's adjacent slices before they leave
+        rec_t, rec_s = _merge_records(rec_t, rec_s, cta_slices)
     stats = np.zeros((ncrops + 2, B))
     total = 0.0
     for b in range(B):

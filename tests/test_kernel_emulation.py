@@ -58,6 +58,10 @@ def test_dino_slice_records_and_merge_equal_the_reference_loss():
         ref = O.dino_loss(s.float(), t.float(), c.float(), nc, tt)
         loss, stats, colsum = dino_sliced_loss(s.float().numpy(), t.float().numpy(), c.float().numpy(), nc, 10.0, 1.0 / tt)
         assert abs(loss - float(ref)) <= 2e-6 * abs(float(ref)), (loss, float(ref))
+        # two-level form of round 2: 8 adjacent slice records merged per CTA, then over the CTAs -- same numbers
+        loss2, stats2, _ = dino_sliced_loss(s.float().numpy(), t.float().numpy(), c.float().numpy(), nc, 10.0, 1.0 / tt,
+                                            slice_cols=64, cta_slices=8)
+        assert abs(loss2 - loss) <= 1e-12 * abs(loss) and np.allclose(stats2, stats, rtol=1e-12, atol=1e-12)
         lse = torch.logsumexp(s.float().double() * 10.0, dim=1).view(nc, B).numpy()
         assert np.allclose(stats[:nc] * np.log(2.0), lse, rtol=1e-10, atol=1e-9)
         assert np.allclose(colsum, t.float().double().sum(0).numpy())
