@@ -307,7 +307,10 @@ def run_ours(args):
     # this is the device-resident headline `value`; the eager run above gives the per-kernel split
     ginp = dict(dev_in, raw_g=st["raw_g"], raw_l=st["raw_l"], student_out=st["student_out"], teacher_out=st["teacher_out"],
                 grad_s_g=st["grad_s_g"], grad_s_l=st["grad_s_l"])
-    graphed = GraphedSSLStep(path, ginp, epoch=3, momentum=float(sched[1000]))
+    # teacher EMA and the patch-embed backward GEMMs on two captured side streams next to the DINO kernels (measured
+    # on B200, tools/graph_probe.py: 0.6084 -> 0.5863 ms; the kernels on the main stream leave ~half of the HBM
+    # bandwidth idle, the EMA fills it)
+    graphed = GraphedSSLStep(path, ginp, epoch=3, momentum=float(sched[1000]), overlap_ema="late2", ema_ctas=0)
     for _ in range(3):
         graphed.replay()
     ms_graph, _ = timed(lambda i, ev: graphed.replay(), args.steps)
@@ -333,7 +336,8 @@ def run_ours(args):
                       grad_s_g=st["grad_s_g"], grad_s_l=st["grad_s_l"])
         bufs = [dict({k: v.to(dev) for k, v in hbuf.items()}, **shared) for _ in range(2)]
         center = path.loss.center.detach().clone().contiguous()
-        graphs = [GraphedSSLStep(path, bufs[b], epoch=3, momentum=float(sched[1000]), center=center) for b in range(2)]
+        graphs = [GraphedSSLStep(path, bufs[b], epoch=3, momentum=float(sched[1000]), center=center, overlap_ema="late2",
+                                 ema_ctas=0) for b in range(2)]
         copy_stream = torch.cuda.Stream(device=dev)
         ready = [torch.cuda.Event() for _ in range(2)]
         free = [torch.cuda.Event() for _ in range(2)]
@@ -480,7 +484,7 @@ def run_ours(args):
                             "transport": "the reference's fp32 normalised image tensors (PCIe-bound)"},
         "value_fp32_images": round(faces / (ms_total_f32 / args.steps / 1e3), 1),
         "value_eager_launches": round(faces / (ms_step_eager / 1e3), 1),
-        "launch": "value: the step's 15 kernels replayed as one CUDA graph (lafs_cvpr2024_b200.ssl_step.GraphedSSLStep); "
+        "launch": "value: the step's 15 kernels replayed as one CUDA graph with three captured streams (DINO kernels | teacher EMA | patch-embed backward) (lafs_cvpr2024_b200.ssl_step.GraphedSSLStep); "
                   "value_eager_launches / kernels / e2e: the same kernels launched one by one from Python",
         # 2 landmark, 3 weight prep, 2 gather-embed, 2 x (dW GEMM + reduce/un-permute), 2 dino fwd (+centre), 1 dino bwd, 1 ema
         "gpu_launches": 15,

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Profiling pass for a round (run under gpurun, ONE GPU).  Writes everything to gpurun_out/.
 #   1. launch list of the bench command (per-launch device time, cold-cache & serialised)
-#   2. one `--set full` capture of each hot kernel
+#   2. one `--set full` capture of each hot kernel (no source import: gpurun_out/ must stay under 64 MiB)
 set -u
 mkdir -p gpurun_out
 rm -f gpurun_out/*.ncu-rep
@@ -9,11 +9,11 @@ T="timeout -s KILL"
 $T 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_bench.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu --no-ref-gpu > gpurun_out/launches_bench.log 2>&1
 cap() {  # name regex driver-mode skip
-  $T 300 ncu --set full --clock-control none --import-source on -k regex:$2 -s $4 -c 1 -o gpurun_out/$1 \
+  $T 300 ncu --set full --clock-control none -k regex:$2 -s $4 -c 1 -o gpurun_out/$1 \
       python tools/prof_driver.py $3 3 > gpurun_out/$1.log 2>&1
 }
 # the dominant kernel of the bench step, captured from the bench command itself (full 147-tensor list)
-$T 600 ncu --set full --clock-control none --import-source on -k regex:ema_multi_kernel -s 4 -c 1 -o gpurun_out/ema_bench \
+$T 600 ncu --set full --clock-control none -k regex:ema_multi_kernel -s 4 -c 1 -o gpurun_out/ema_bench \
     python bench.py --steps 2 --warmup 3 --no-cpu --no-ref-gpu > gpurun_out/ema_bench.log 2>&1
 cap dino_fwd dino_fwd_partial dino 1
 cap dino_finish dino_finish dino 1

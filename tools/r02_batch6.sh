@@ -3,15 +3,10 @@
 mkdir -p gpurun_out
 T="timeout -s KILL"
 export PYTHONUNBUFFERED=1
-echo "=== graphed step: EMA overlap sweep"
-for mode in "" late late2 early; do for ctas in 0 148 296; do
-  if [ -z "$mode" ] && [ $ctas != 0 ]; then continue; fi
-  EMA_OVERLAP=$mode EMA_CTAS=$ctas $T 200 python tools/graph_probe.py 2>&1 | tail -1
-done; done | tee gpurun_out/ema_overlap_sweep.txt
 echo "=== other SSL configs"
 for c in cfg1_L8 cfg4 cfg0; do
   EXTRA="--no-cpu --no-ref-gpu"; if [ $c == cfg0 ]; then EXTRA=""; fi
-  $T 600 python bench.py --config $c --steps 100 --warmup 5 $EXTRA > gpurun_out/bench_$c.json 2> gpurun_out/bench_$c.err
+  $T 600 python bench.py --config $c --steps 50 --warmup 5 $EXTRA > gpurun_out/bench_$c.json 2> gpurun_out/bench_$c.err
   python - <<PY
 import json
 try:
