@@ -26,4 +26,10 @@ cap head_fwd head_gemm_kernel head_bwd 2     # launches per repetition: forward 
 cap head_grad head_gemm_kernel head_bwd 3
 cap head_de gemm_bwd_kernel head_bwd 1
 cap head_dw dw_diag_kernel head_bwd 1
-ls -la gpurun_out/*.ncu-rep
+# gpurun brings back at most 64 MiB: keep the raw metric pages as CSV and drop the reports (the DINO ones are 15 MB each)
+mkdir -p gpurun_out/ncu_raw
+for r in gpurun_out/*.ncu-rep; do
+  ncu -i $r --page raw --csv > gpurun_out/ncu_raw/$(basename $r .ncu-rep).csv 2>/dev/null
+  rm -f $r
+done
+ls -la gpurun_out/ncu_raw; du -sh gpurun_out

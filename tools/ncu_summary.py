@@ -17,16 +17,20 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 def main(tag):
     out_rows = []
-    for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "*.ncu-rep"))):
-        r = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True)
-        rows = list(csv.reader(r.stdout.splitlines()))
+    reps = sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "*.ncu-rep")) + glob.glob(os.path.join(ROOT, "gpurun_out", "ncu_raw", "*.csv")))
+    for rep in reps:
+        if rep.endswith(".csv"):          # raw page exported on the GPU box (tools/ncu_round.sh)
+            text = open(rep).read()
+        else:
+            text = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(text.splitlines()))
         if len(rows) < 3:
             continue
         hdr, units = rows[0], rows[1]
         for vals in rows[2:]:
             d = dict(zip(hdr, vals))
             u = dict(zip(hdr, units))
-            rec = {"report": os.path.basename(rep), "kernel": d.get("Kernel Name", "")[:80]}
+            rec = {"report": os.path.basename(rep).replace(".csv", ".ncu-rep"), "kernel": d.get("Kernel Name", "")[:80]}
             for w in WANT:
                 if w in d:
                     rec[w + (" [" + u[w] + "]" if u.get(w) else "")] = d[w]
