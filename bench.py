@@ -418,6 +418,14 @@ def run_ours(args):
     del st, path, dev_in
     torch.cuda.empty_cache()
     head = bench_head(P, world, rank, dev, dist, args)
+    # ---- secondary: DINOHead.last_layer fused with the DINO loss (per-GPU work, no collective
+    # beyond the centre all-reduce already measured above: reported at N = 1) -------------------------------------
+    if world == 1:
+        try:
+            extras["dino_head_fused(last_layer+loss)"] = bench_dino_head(dev, iters=max(5, min(args.steps, 20)))
+        except Exception as e:
+            extras["dino_head_fused_error"] = str(e).splitlines()[0][:160]
+            torch.cuda.synchronize()
 
     if rank != 0:
         if world > 1:
@@ -639,6 +647,112 @@ def bench_head(P, world, rank, dev, dist, args):
             if out[name]["parity_max_rel"] > HEAD_PARITY_TOL:
                 raise SystemExit(f"bench.py: sharded head {name} deviates from the unsharded head by "
                                  f"{out[name]['parity_max_rel']} (> {HEAD_PARITY_TOL}) at world={world}")
+    return out
+
+
+def bench_dino_head(dev, iters=20, B=None, ncrops=None, K=None, D=256):
+    """DINOHead.last_layer (weight-normed 256 -> 65536) fused with the DINO loss
+    (lafs_cvpr2024_b200/dino_head.py) against the unfused form of the same work on the same GPU: cuBLAS bf16
+    last-layer GEMMs that write the [(ncrops+2)B, K] logits + this repo's DINO loss kernels on those logits + autograd
+    (cuBLAS dX / dW, weight-norm and normalize backward).  Both from the bottleneck features to
+    (loss, d features, d weight_v, new centre); CUDA-graph replays, device events."""
+    import lafs_cvpr2024_b200 as P
+    B = B or B_PER_GPU
+    ncrops = ncrops or (N_LOCAL + 2)
+    K = K or OUT_DIM
+    torch.manual_seed(11)
+    xs = torch.randn(ncrops * B, D, device=dev)
+    xt = torch.randn(2 * B, D, device=dev)
+    vs = torch.randn(K, D, device=dev) * 0.02
+    vt = vs + torch.randn(K, D, device=dev) * 0.002
+    one = torch.ones(K, device=dev)
+    center = torch.randn(K, device=dev) * 0.05
+    gout = torch.ones((), device=dev)
+    inv_ts, inv_tt = 10.0, 25.0
+
+    def fused_fwd():
+        return P.dino_head_forward(xs, xt, vs, one, vt, one, center, ncrops, inv_ts, inv_tt, keep_for_backward=False)[0]
+
+    def fused_step():
+        loss, colsum, saved = P.dino_head_forward(xs, xt, vs, one, vt, one, center, ncrops, inv_ts, inv_tt)
+        dx, dv, _ = P.dino_head_backward(saved, gout)
+        return loss, dx, dv
+
+    dl = P.DINOLoss(K, ncrops, 0.04, 0.04, 0, 1).to(dev)
+    c0 = center.view(1, -1).clone()
+    xs_u = xs.clone().requires_grad_(True)
+    vs_u = vs.clone().requires_grad_(True)
+
+    def unfused_step():
+        xs_u.grad = None
+        vs_u.grad = None
+        dl.center = c0
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            ws = vs_u * (one / vs_u.norm(dim=1)).unsqueeze(1)            # torch._weight_norm
+            s_out = torch.nn.functional.linear(torch.nn.functional.normalize(xs_u, dim=-1, p=2), ws)
+            with torch.no_grad():
+                wt = vt * (one / vt.norm(dim=1)).unsqueeze(1)
+                t_out = torch.nn.functional.linear(torch.nn.functional.normalize(xt, dim=-1, p=2), wt)
+        loss = dl(s_out, t_out, 0)
+        loss.backward()
+        return loss
+
+    def graph_time(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        mode = "cuda_graph"
+        run = None
+        try:
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                fn()
+            run = gr.replay
+            for _ in range(3):
+                run()
+        except Exception as e:
+            mode = "eager (graph capture failed: %s)" % str(e).splitlines()[0][:80]
+            torch.cuda.synchronize()
+            run = fn
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters, mode
+
+    out = {"B": B, "ncrops": ncrops, "out_dim": K, "bottleneck": D}
+    ms_f, mode_f = graph_time(fused_fwd)
+    ms_fb, mode_fb = graph_time(fused_step)
+    loss_f = float(fused_step()[0])
+    rows_s, rows_t, Dt = ncrops * B, 2 * B, D + 64
+    issued = 2.0 * K * (2 * rows_t * Dt + rows_t * D + rows_s * D) + 2.0 * K * D * (2 * rows_s + rows_s + rows_t)
+    useful = 2.0 * K * D * (rows_s + rows_t) + 4.0 * K * D * rows_s
+    # HBM traffic of the composition: fp32 prototypes in (2), bf16 operand copies out and back (3 + 2 GEMM passes each),
+    # probabilities (bf16) written once and read twice, dW out and its weight-norm pass; the logits themselves: none
+    probs = (rows_s + rows_t) * K * 2
+    out["fused"] = {"ms_fwd": round(ms_f, 4), "ms_fwd_bwd": round(ms_fb, 4), "launch": mode_fb, "loss": loss_f,
+                    "TFLOPs_issued": round(issued / ms_fb / 1e9, 1), "TFLOPs_6RKD": round(useful / ms_fb / 1e9, 1),
+                    "logit_bytes_in_hbm": 0, "probability_bytes_written": probs,
+                    "note": "no [rows, K] logits or fp32 gradient in HBM; bf16 probabilities written once by the "
+                            "recomputing GEMM (teacher rows in the forward, student rows in the backward)"}
+    try:
+        ms_u, mode_u = graph_time(unfused_step)
+        loss_u = float(unfused_step())
+        out["unfused_same_gpu"] = {"ms_fwd_bwd": round(ms_u, 4), "launch": mode_u, "loss": loss_u,
+                                   "logit_bytes_in_hbm": (rows_s + rows_t) * K * 2 + rows_s * K * 2,
+                                   "note": "cuBLAS bf16 last-layer GEMMs (logits written, bf16) + this repo's DINO loss kernels "
+                                           "(logits read twice, bf16 gradient written) + autograd dX / dW GEMMs and "
+                                           "weight-norm / normalize backward in eager PyTorch"}
+        out["loss_rel_diff_fused_vs_unfused"] = float("%.3g" % (abs(loss_f - loss_u) / abs(loss_u)))
+        out["speedup_fused_over_unfused"] = round(ms_u / ms_fb, 3)
+    except Exception as e:
+        out["unfused_error"] = str(e).splitlines()[0][:160]
+        torch.cuda.synchronize()
+    del dl
+    torch.cuda.empty_cache()
     return out
 
 

@@ -262,8 +262,8 @@ LAFS_API int lafs_embed_bwd_weight_perm(const void* grad_emb_bf16, const void* t
 LAFS_API int lafs_embed_bwd_tokens(const void* grad_emb_bf16, const void* weight_bf16, int M, int dim,
                                    float* grad_tokens, lafs_stream_t stream);
 
-/* EXPERIMENTAL (written after the round's GPU budget was spent; compiled, not yet run on hardware; the Python
- * wrappers use them only with LAFS_DW_DIAG=1): the F.normalize Jacobian of dW on the tensor core.
+/* The F.normalize Jacobian of dW on the tensor core (the default dW path of the Python wrappers; verified on B200
+ * in round 2, tests/test_gpu_head.py::test_dw_jacobian_on_tensor_core_variant and the bench-shape tests).
  * lafs_head_grad_logits_t = lafs_head_grad_logits + per-class partial dots tpart[(mtile*4+quarter)*ldt + c]
  * (sum over a 32-row group of G[b,c]*cos[b,c]; 4*ceil(B/128) rows, ldt a multiple of 32 >= C_local rounded up
  * to 32, 128-byte aligned).  lafs_head_bwd_weight_t sums the rows (in place, row 0) to t[c] = <w_hat_c, dW_hat_c>
@@ -275,6 +275,54 @@ LAFS_API int lafs_head_grad_logits_t(const void* e_hat, const void* w_hat, const
 LAFS_API int lafs_head_bwd_weight_t(const void* grad_bf16, long long ldg, const void* e_hat, const void* w_hat,
                                     const float* inv_norm_w, float* tpart, int tparts, long long ldt, int B,
                                     int C_local, int D, float* grad_w, lafs_stream_t stream);
+
+/* out [M, N] fp32 = A^T . B, A [Kr rows, M cols], B [Kr rows, N cols] bf16 row-major (leading dimensions in
+ * elements, multiples of 8): the dW GEMM without a Jacobian pass.  Used by the fused DINO head below. */
+LAFS_API int lafs_gemm_tn(const void* a_bf16, long long lda, const void* b_bf16, long long ldb, int Kr, int M, int N,
+                          float* out, long long ldo, lafs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (f1) DINOHead.last_layer fused with DINOLoss  --  the [(ncrops+2)B, K] logits never exist in HBM.
+ *      replaces  x = nn.functional.normalize(x, dim=-1, p=2); x = self.last_layer(x)
+ *      (vision_transformer.py:284,296-300; last_layer = weight_norm(Linear(bottleneck, K, bias=False))) followed by
+ *      DINOLoss.forward / update_center (lafs_train.py:643-679).
+ * The contractions are the margin head's tcgen05 GEMMs (lafs_head_fwd = per-row online-softmax statistics,
+ * lafs_head_grad_logits with labels -1 = bf16 softmax probabilities, lafs_head_bwd_embed = P . W, lafs_gemm_tn);
+ * the entry points below are the streaming passes around them (csrc/dino_head.cu explains the algebra; the Python
+ * side is lafs_cvpr2024_b200/dino_head.py).
+ *   lafs_dh_extra_cols   K columns appended to the TEACHER operands (64): features [x_hat | 1 1 1 | 0..], prototypes
+ *                        [w | -c_hi -c_mid -c_lo | 0..] (three-term bf16 split of the fp32 centre), so that the
+ *                        accumulator holds <x_hat, w_k> - center[k].
+ *   lafs_dh_prep_rows    x [R, D] (any dtype code) -> F.normalize rows, bf16 [R, ld], ld = D or D + extra;
+ *                        inv_norm [R] = 1/max(||x||, 1e-12) (may be NULL).
+ *   lafs_dh_xsum         xsum [D] = sum over the R rows of x_hat (fp32, fixed order).
+ *   lafs_dh_prep_weight  weight_norm rows w_k = v_k * (g_k/||v_k||) (weight_g NULL: g = 1) -> bf16 [K, ld];
+ *                        inv_norm [K] = 1/||v_k||; with xsum: colsum [K] = <w_k, xsum> = the column sums of the
+ *                        teacher logits (torch.sum(teacher_output, dim=0), lafs_train.py:674) for lafs_center_ema.
+ *   lafs_dh_lse2         merged row statistics [R, 4] of lafs_head_fwd -> log2-domain lse [R].
+ *   lafs_dh_loss         loss = 1/((2 ncrops-2) B) sum_{iq<2, v != iq, i} [ lse(s_v,i/ts) - <U_iq,i, x_hat_v,i>/ts ],
+ *                        U [2B, D] = Q . W_s (fp32), x_hat_s bf16 [ncrops B, D].
+ *   lafs_dh_bwd_rows     student rows: dx = F.normalize backward of coef (cnt_v O - sum_{iq != v} U_iq), O = P_s . W_s;
+ *                        all rows: y [(ncrops+2) B, D] bf16 = the B operand of the dW GEMM (cnt_v x_hat_s | -X~).
+ *                        coef = inv_student_temp / ((2 ncrops-2) B) * grad_out[0].
+ *   lafs_dh_wn_bwd       weight_norm backward from the raw dW [K, D]: grad_v = coef*grad_out[0] * g/||v|| (dW - v_hat
+ *                        <v_hat, dW>), grad_g [K] = coef*grad_out[0] * <v_hat, dW> (may be NULL).  grad_v may alias dw_raw. */
+LAFS_API int lafs_dh_extra_cols(void);
+LAFS_API int lafs_dh_prep_rows(const void* x, int dtype, int R, int D, int ld, void* out_bf16, float* inv_norm,
+                               lafs_stream_t stream);
+LAFS_API int lafs_dh_xsum(const void* x_hat_bf16, int R, int D, int ld, float* xsum, lafs_stream_t stream);
+LAFS_API int lafs_dh_prep_weight(const float* weight_v, const float* weight_g, const float* center, const float* xsum,
+                                 int K, int D, int ld, void* out_bf16, float* inv_norm, float* colsum,
+                                 lafs_stream_t stream);
+LAFS_API int lafs_dh_lse2(const float* row_stats, int R, float* lse2, lafs_stream_t stream);
+LAFS_API int lafs_dh_loss(const float* lse2_s, const float* U, const void* x_hat_s_bf16, int B, int ncrops, int D,
+                          float inv_student_temp, float* loss_out, lafs_stream_t stream);
+LAFS_API int lafs_dh_bwd_rows(const float* O, const float* U, const void* x_hat_s_bf16, const float* inv_norm_s,
+                              const float* grad_out, int B, int ncrops, int D, float inv_student_temp, float* dx,
+                              void* y_bf16, lafs_stream_t stream);
+LAFS_API int lafs_dh_wn_bwd(const float* dw_raw, const float* weight_v, const float* weight_g, const float* inv_norm,
+                            const float* grad_out, int K, int D, float coef, float* grad_v, float* grad_g,
+                            lafs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * (4e) Exchange steps of the class-sharded head over NVLink peer memory (one kernel each, instead of

@@ -60,6 +60,15 @@ SIGNATURES = {
     "lafs_head_grad_logits_t": (_i, [_p, _p, _p, _p, _f, _i, _i, _i, _i, _f, _f, _i, _p, _p, _f, _p, C.c_longlong, _p,
                                      C.c_longlong, _p]),
     "lafs_head_bwd_weight_t": (_i, [_p, C.c_longlong, _p, _p, _p, _p, _i, C.c_longlong, _i, _i, _i, _p, _p]),
+    "lafs_gemm_tn": (_i, [_p, C.c_longlong, _p, C.c_longlong, _i, _i, _i, _p, C.c_longlong, _p]),
+    "lafs_dh_extra_cols": (_i, []),
+    "lafs_dh_prep_rows": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
+    "lafs_dh_xsum": (_i, [_p, _i, _i, _i, _p, _p]),
+    "lafs_dh_prep_weight": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p]),
+    "lafs_dh_lse2": (_i, [_p, _i, _p, _p]),
+    "lafs_dh_loss": (_i, [_p, _p, _p, _i, _i, _i, _f, _p, _p]),
+    "lafs_dh_bwd_rows": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _f, _p, _p, _p]),
+    "lafs_dh_wn_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _f, _p, _p, _p]),
     "lafs_optim_workspace_bytes": (_z, [_i, _i]),
     "lafs_adamw_ema_multi": (_i, [_p, _i, _p, _p, _i, _p, _p, _p, _p, _z, _p]),
     "lafs_xchg_bytes": (_z, [_i, _i, _i, _p]),

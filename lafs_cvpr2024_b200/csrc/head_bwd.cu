@@ -840,3 +840,28 @@ extern "C" int lafs_head_bwd_weight_t(const void* grad_bf16, long long ldg, cons
   launch_pdl((dw_diag_kernel), dim3(total < kNumSMs ? total : kNumSMs), dim3(gb::kThreads), (size_t)(gb::kSmem), st, ta, tb, tw, p, dp);
   return check_launch("lafs_head_bwd_weight_t");
 }
+
+/* out [M, N] fp32 = A^T . B  with A [Kr rows, M cols] and B [Kr rows, N cols] bf16 row-major (both operands MN-major;
+ * the contraction runs over the rows): the dW GEMM above without a Jacobian pass.  Used by the fused DINO head
+ * (dino_head.cu): dW_raw [K, D] = (P_s ; Q)^T . (cnt X_hat_s ; -X~). */
+extern "C" int lafs_gemm_tn(const void* a_bf16, long long lda, const void* b_bf16, long long ldb, int Kr, int M, int N,
+                            float* out, long long ldo, lafs_stream_t stream) {
+  if (int brc = lafs::bind_device_of(a_bf16)) return brc;
+  LAFS_REQUIRE(a_bf16 && b_bf16 && out, LAFS_ERR_ARG, "lafs_gemm_tn: null pointer");
+  LAFS_REQUIRE(Kr > 0 && M > 0 && N > 0, LAFS_ERR_ARG, "lafs_gemm_tn: Kr=%d M=%d N=%d", Kr, M, N);
+  LAFS_REQUIRE(lda % 8 == 0 && lda >= M && ldb % 8 == 0 && ldb >= N && ldo % 4 == 0 && ldo >= N, LAFS_ERR_ARG,
+               "lafs_gemm_tn: lda=%lld ldb=%lld (multiples of 8, >= M / N), ldo=%lld (multiple of 4, >= N)", lda, ldb, ldo);
+  LAFS_REQUIRE((((uintptr_t)a_bf16 | (uintptr_t)b_bf16 | (uintptr_t)out) & 15u) == 0, LAFS_ERR_ARG,
+               "lafs_gemm_tn: pointers must be 16-byte aligned");
+  CUtensorMap ta, tb;
+  int rc = encode_bf16_2d(&ta, a_bf16, (uint64_t)Kr, (uint64_t)M, (uint64_t)lda * 2, 64, 64);   // MN-major A: [K=Kr, M]
+  if (rc) return rc;
+  rc = encode_bf16_2d(&tb, b_bf16, (uint64_t)Kr, (uint64_t)N, (uint64_t)ldb * 2, 64, 64);       // MN-major B: [K=Kr, N]
+  if (rc) return rc;
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = Kr;
+  p.m_tiles = (M + 127) / 128; p.n_tiles = (N + 255) / 256; p.splits = 1;
+  p.kblocks_total = (Kr + 63) / 64; p.kblocks_per_split = p.kblocks_total;
+  p.out = out; p.ldo = ldo; p.split_stride = 0;
+  return launch_gemm<true>(ta, tb, p, (cudaStream_t)stream);
+}

@@ -121,6 +121,13 @@ class DINOLoss(nn.Module):
         return xchg.allreduce_de().view(-1)
 
     def forward(self, student_output, teacher_output, epoch):
+        from .dino_head import DeferredLogits, fused_dino_loss
+        if isinstance(student_output, DeferredLogits) or isinstance(teacher_output, DeferredLogits):
+            # heads built with fused_loss=True hand over bottleneck features: last_layer GEMM + loss in one path
+            if not (isinstance(student_output, DeferredLogits) and isinstance(teacher_output, DeferredLogits)):
+                raise TypeError("student_output and teacher_output must both be DeferredLogits (fused_loss=True on "
+                                "both heads) or both be logit tensors")
+            return fused_dino_loss(self, student_output, teacher_output, epoch)
         temp = self.teacher_temp_schedule[epoch]
         single = not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
         loss, _ = _DinoLossFn.apply(student_output, teacher_output, self.center, self.ncrops,

@@ -13,6 +13,8 @@ tests/golden/ that tests/golden/make_golden.py generated from the reference):
   landmark_post                          pinned   face_pre_pro/ViT_face.py:1347-1378
   patch_embed                            pinned   face_pre_pro/ViT_face.py:759-761
   dino_loss / dino_center_update         pinned   lafs_train.py:643-679
+  dino_head_logits / dino_head_loss      pinned   vision_transformer.py:296-300 (F.normalize + weight-normed last_layer)
+                                                  feeding lafs_train.py:643-679 (golden dino_head.npz + live test)
   ema_update                             pinned   lafs_train.py:610-613
   clip_gradients_ / student_update_      pinned   utils.py:132-141, lafs_train.py:511-517,601-613 (torch.optim.AdamW
                                                   is PyTorch itself; the clip is checked against utils.clip_gradients)
@@ -167,6 +169,45 @@ def dino_center_update(center, teacher_output, momentum=0.9, world_size=1, allre
         batch_center = allreduced_sum
     batch_center = batch_center / (len(teacher_output) * world_size)
     return center * momentum + batch_center * (1 - momentum)
+
+
+# --------------------------------------------------------------------------------------
+# (f1) DINOHead tail (F.normalize + weight-normed last_layer) feeding the DINO loss
+# --------------------------------------------------------------------------------------
+def _bf16_st(t):
+    """round to bf16 with a straight-through gradient (the operand rounding of the tensor-core path)."""
+    return t + (t.detach().bfloat16().float() - t.detach())
+
+
+def dino_head_logits(x, weight_v, weight_g, round_bf16=False):
+    """DINOHead.forward after the mlp, vision_transformer.py:298-300:
+    x = F.normalize(x, dim=-1, p=2); x = last_layer(x) with last_layer = weight_norm(Linear(D, K, bias=False)),
+    i.e. weight = v * (g / ||v||_row) (torch._weight_norm, dim=0).  weight_g [K,1] or [K]."""
+    xh = F.normalize(x.float(), dim=-1, p=2)
+    w = weight_v.float() * (weight_g.float().reshape(-1, 1) / weight_v.float().norm(dim=1, keepdim=True))
+    if round_bf16:
+        xh, w = _bf16_st(xh), _bf16_st(w)
+    return xh @ w.t()
+
+
+def dino_head_loss(xs, xt, vs, gs, vt, gt, center, ncrops, teacher_temp, student_temp=0.1, round_bf16=False):
+    """loss of lafs_train.py:581-583 from the bottleneck features: student / teacher logits through their own
+    last layers, then DINOLoss.forward.  Returns (loss, teacher_logits)."""
+    s = dino_head_logits(xs, vs, gs, round_bf16)
+    with torch.no_grad():
+        t = dino_head_logits(xt, vt, gt, round_bf16)
+    return dino_loss(s, t, center, ncrops, teacher_temp, student_temp), t
+
+
+def dino_head_loss_and_grads(xs, xt, vs, gs, vt, gt, center, ncrops, teacher_temp, student_temp=0.1,
+                             round_bf16=False, grad_out=1.0):
+    """(loss, d/d xs, d/d weight_v, d/d weight_g, new centre) by autograd through the restatement."""
+    xs_ = xs.detach().float().clone().requires_grad_(True)
+    vs_ = vs.detach().float().clone().requires_grad_(True)
+    gs_ = gs.detach().float().clone().requires_grad_(True)
+    loss, t = dino_head_loss(xs_, xt, vs_, gs_, vt, gt, center, ncrops, teacher_temp, student_temp, round_bf16)
+    dx, dv, dg = torch.autograd.grad(loss, (xs_, vs_, gs_), torch.tensor(grad_out, dtype=loss.dtype, device=loss.device))
+    return loss.detach(), dx, dv, dg, dino_center_update(center.reshape(1, -1), t)
 
 
 # --------------------------------------------------------------------------------------

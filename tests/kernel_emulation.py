@@ -205,3 +205,72 @@ def head_sharded_loss(cos, label, s, m, world, chunk=256):
         T += tg
     lse = (M + np.log2(L)) * 0.6931471805599453
     return float((lse - T).mean())
+
+
+# ---- (f1) fused DINO head: the decomposition of csrc/dino_head.cu + dino_head.py, step by step ----------------
+def _bf16(t):
+    return t.bfloat16().float()
+
+
+def dino_head_fused(xs, xt, vs, gs, vt, gt, center, ncrops, inv_ts, inv_tt, grad_out=1.0):
+    """torch-CPU emulation of dino_head_forward / dino_head_backward: same operands (bf16 where the kernels round),
+    same algebra (centre as three bf16 K columns, U = Q.W_s, dX from O and U, dW from (P_s;Q)^T(cnt x_hat; -X~),
+    weight-norm Jacobian), fp32 accumulation.  Returns (loss, colsum, dx, dv, dg)."""
+    import torch
+    xs, xt, vs, vt = xs.float(), xt.float(), vs.float(), vt.float()
+    gs, gt, c = gs.float().reshape(-1), gt.float().reshape(-1), center.float().reshape(-1)
+    B = xt.shape[0] // 2
+    K, D = vs.shape
+    rs = ncrops * B
+    # dh_prep_rows
+    inv_xs = 1.0 / xs.norm(dim=1).clamp_min(1e-12)
+    xs_hat = _bf16(xs * inv_xs[:, None])
+    xt_hat = _bf16(xt / xt.norm(dim=1, keepdim=True).clamp_min(1e-12))
+    ones3 = torch.ones(2 * B, 3)
+    xt_aug = torch.cat([xt_hat, ones3], 1)
+    xsum = xt_hat.sum(0)
+    # dh_prep_weight
+    inv_w = 1.0 / vs.norm(dim=1)
+    ws = _bf16(vs * (gs * inv_w)[:, None])
+    wt = _bf16(vt * (gt / vt.norm(dim=1))[:, None])
+    hi = _bf16(c); mid = _bf16(c - hi); lo = _bf16((c - hi) - mid)
+    wt_aug = torch.cat([wt, -hi[:, None], -mid[:, None], -lo[:, None]], 1)
+    colsum = wt @ xsum
+    # teacher statistics + Q (bf16) + U
+    zt = (xt_aug @ wt_aug.t()) * inv_tt
+    lse_t = torch.logsumexp(zt, 1, keepdim=True)
+    Q = _bf16(torch.exp(zt - lse_t))
+    U = Q @ ws
+    # student statistics + loss
+    zs = (xs_hat @ ws.t()) * inv_ts
+    lse_s = torch.logsumexp(zs, 1)
+    n_terms = 2 * ncrops - 2
+    total = 0.0
+    for v in range(ncrops):
+        cnt = 1.0 if v < 2 else 2.0
+        rows = slice(v * B, (v + 1) * B)
+        u = sum(U[iq * B:(iq + 1) * B] for iq in range(2) if iq != v)
+        total = total + (cnt * lse_s[rows]).sum() - inv_ts * (u * xs_hat[rows]).sum()
+    loss = total / (n_terms * B)
+    # backward
+    coef = inv_ts / (n_terms * B) * grad_out
+    P = _bf16(torch.exp(zs - lse_s[:, None]))
+    O = P @ ws
+    dx = torch.empty(rs, D)
+    y = torch.empty(rs + 2 * B, D)
+    for v in range(ncrops):
+        cnt = 1.0 if v < 2 else 2.0
+        rows = slice(v * B, (v + 1) * B)
+        u = sum(U[iq * B:(iq + 1) * B] for iq in range(2) if iq != v)
+        d = coef * (cnt * O[rows] - u)
+        dot = (d * xs_hat[rows]).sum(1, keepdim=True)
+        dx[rows] = (d - xs_hat[rows] * dot) * inv_xs[rows, None]
+        y[rows] = cnt * xs_hat[rows]
+    for iq in range(2):
+        y[rs + iq * B: rs + (iq + 1) * B] = _bf16(-sum(xs_hat[v * B:(v + 1) * B] for v in range(ncrops) if v != iq))
+    dw_raw = torch.cat([P, Q], 0).t() @ y
+    v_hat = vs * inv_w[:, None]
+    dot = (dw_raw * v_hat).sum(1)
+    dv = (coef * gs * inv_w)[:, None] * (dw_raw - v_hat * dot[:, None])
+    dg = coef * dot
+    return loss, colsum, dx, dv, dg

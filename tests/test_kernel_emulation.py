@@ -84,3 +84,33 @@ def test_head_chunk_and_rank_merge_equal_cross_entropy():
     for world in (1, 2, 4, 8):
         got = head_sharded_loss(cos.numpy(), lab.numpy(), 64.0, 0.4, world, chunk=100)
         assert abs(got - ref) <= 1e-5 * abs(ref), (world, got, ref)
+
+
+def test_fused_dino_head_decomposition_equals_the_oracle():
+    """(f1) the algebra of csrc/dino_head.cu (centre folded into three bf16 K columns, U = Q.W_s cross terms,
+    dX from O and U, dW from one TN GEMM, weight-norm Jacobian) against autograd through the oracle on the same
+    bf16-rounded operands -- checked on CPU before any GPU time is spent."""
+    import torch
+    from oracle import lafs_oracle as O
+    from tests import kernel_emulation as KE
+    g = torch.Generator().manual_seed(5)
+    for (B, K, D, ncrops, gscale) in ((3, 777, 64, 6, 1.0), (5, 1500, 128, 4, 8.0), (2, 300, 64, 2, 1.0)):
+        xs = torch.randn(ncrops * B, D, generator=g) * 2
+        xt = torch.randn(2 * B, D, generator=g) * 2
+        vs = torch.randn(K, D, generator=g) * 0.3
+        vt = vs + torch.randn(K, D, generator=g) * 0.05
+        gs = 0.5 + torch.rand(K, generator=g)
+        gt = 0.5 + torch.rand(K, generator=g)
+        center = torch.randn(K, generator=g) * 0.1
+        tt, ts = 0.05, 0.1
+        loss, colsum, dx, dv, dg = KE.dino_head_fused(xs, xt, vs, gs, vt, gt, center, ncrops, 1 / ts, 1 / tt, gscale)
+        rl, rdx, rdv, rdg, rc1 = O.dino_head_loss_and_grads(xs, xt, vs, gs, vt, gt, center, ncrops, tt, ts,
+                                                            round_bf16=True, grad_out=gscale)
+        assert abs(float(loss) - float(rl)) <= 2e-4 * abs(float(rl)), (B, K, float(loss), float(rl))
+        for a, b, name in ((dx, rdx, "dx"), (dv, rdv, "dv"), (dg, rdg, "dg")):
+            err = float((a - b).abs().max() / b.abs().max())
+            assert err < 5e-3, (name, B, K, err)
+        # centre: colsum is the column sum of the teacher logits the GEMM sees
+        t = O.dino_head_logits(xt, vt, gt, round_bf16=True)
+        torch.testing.assert_close(colsum, t.sum(0), rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(O.dino_center_update(center.reshape(1, -1), t), rc1)

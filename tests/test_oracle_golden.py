@@ -131,3 +131,18 @@ def test_arcface_unpinned_sanity():
     assert torch.allclose(z[off], 64 * cos[off])
     th = torch.acos(cos[~off].clamp(-1, 1))
     assert torch.allclose(z[~off], 64 * torch.cos(th + 0.5), atol=1e-4)
+
+
+def test_dino_head_tail_and_loss_golden(golden):
+    """(f1) F.normalize + weight-normed last_layer (vision_transformer.py:296-300) feeding DINOLoss: the oracle
+    against the reference's own student/teacher DINOHead + DINOLoss run (tests/golden/make_golden_dino_head.py)."""
+    g = golden("dino_head")
+    xs, xt, vs, gs, vt, gt = (T(g[k]) for k in ("xs", "xt", "vs", "gs", "vt", "gt"))
+    close(O.dino_head_logits(xs, vs, gs)[0], T(g["student_logits_row0"]), rtol=1e-5, atol=1e-6)
+    close(O.dino_head_logits(xt, vt, gt)[0], T(g["teacher_logits_row0"]), rtol=1e-5, atol=1e-6)
+    loss, dx, dv, dg, c1 = O.dino_head_loss_and_grads(xs, xt, vs, gs, vt, gt, T(g["center0"]), int(g["ncrops"]),
+                                                      float(g["temp"]))
+    close(loss, T(g["loss"]), rtol=1e-6, atol=0)
+    for a, b in ((dx, T(g["grad_xs"])), (dv, T(g["grad_vs"])), (dg.reshape(-1, 1), T(g["grad_gs"]))):
+        close(a, b, rtol=1e-4, atol=1e-5 * float(b.abs().max()))      # fp32 summation order of autograd
+    close(c1, T(g["center1"]), rtol=1e-6, atol=1e-7)

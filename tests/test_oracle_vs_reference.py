@@ -190,3 +190,49 @@ def test_clip_gradients_matches_reference(ref):
         assert (p.grad is None) == (g is None)
         if g is not None:
             assert torch.equal(p.grad, g)
+
+
+def test_dino_head_tail_matches_reference(ref):
+    """(f1) the live reference DINOHead (vision_transformer.py:265-301) + DINOLoss against the oracle restatement,
+    and our DINOHead module: same state-dict keys, same init statistics, reference checkpoints load strict."""
+    import warnings
+    torch.manual_seed(11)
+    in_dim, K, B, nc = 40, 900, 3, 5
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        hs = ref.vt.DINOHead(in_dim, K, nlayers=2, hidden_dim=64, bottleneck_dim=64, norm_last_layer=False)
+        ht = ref.vt.DINOHead(in_dim, K, nlayers=2, hidden_dim=64, bottleneck_dim=64)
+    with torch.no_grad():
+        hs.last_layer.weight_g.uniform_(0.5, 1.5)
+    fs, ft = torch.randn(nc * B, in_dim), torch.randn(2 * B, in_dim)
+    dl = ref.L.DINOLoss(K, nc, 0.04, 0.07, 30, 41)
+    dl.center = torch.randn(1, K) * 0.1
+    c0 = dl.center.clone()
+    xs = hs.mlp(fs).detach().requires_grad_(True)
+    s_out = hs.last_layer(torch.nn.functional.normalize(xs, dim=-1, p=2))
+    assert torch.equal(s_out, hs(fs))
+    with torch.no_grad():
+        xt = ht.mlp(ft)
+        t_out = ht(ft)
+    loss = dl(s_out, t_out, 2)
+    loss.backward()
+    temp = float(O.teacher_temp_schedule(0.04, 0.07, 30, 41)[2])
+    ol, odx, odv, odg, oc1 = O.dino_head_loss_and_grads(xs, xt, hs.last_layer.weight_v, hs.last_layer.weight_g,
+                                                        ht.last_layer.weight_v, ht.last_layer.weight_g, c0, nc, temp)
+    torch.testing.assert_close(ol, loss.detach(), rtol=1e-6, atol=0)
+    for a, b in ((odx, xs.grad), (odv, hs.last_layer.weight_v.grad), (odg.reshape(-1, 1), hs.last_layer.weight_g.grad)):
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5 * float(b.abs().max()))
+    torch.testing.assert_close(oc1, dl.center, rtol=1e-6, atol=1e-7)
+    # module surface
+    import lafs_cvpr2024_b200 as P
+    mine = P.DINOHead(in_dim, K, nlayers=2, hidden_dim=64, bottleneck_dim=64, norm_last_layer=False)
+    assert list(mine.state_dict().keys()) == list(hs.state_dict().keys())
+    mine.load_state_dict(hs.state_dict(), strict=True)
+    assert torch.equal(mine(fs), hs(fs))                       # default mode = the reference's forward
+    assert mine.last_layer.weight_g.requires_grad and not P.DINOHead(8, 16).last_layer.weight_g.requires_grad
+    mine.fused_loss = True
+    d = mine(fs)
+    assert isinstance(d, P.DeferredLogits) and torch.equal(d.features, hs.mlp(fs)) and torch.equal(d.logits(), hs(fs))
+    big = P.DINOHead(64, 32, nlayers=3, hidden_dim=512, bottleneck_dim=256)
+    assert abs(float(big.mlp[0].weight.std()) - 0.02) < 0.002 and float(big.mlp[0].bias.abs().max()) == 0.0
+    assert float(big.last_layer.weight_g.min()) == 1.0 == float(big.last_layer.weight_g.max())
