@@ -301,7 +301,8 @@ LAFS_API int lafs_gemm_tn(const void* a_bf16, long long lda, const void* b_bf16,
  *                        teacher logits (torch.sum(teacher_output, dim=0), lafs_train.py:674) for lafs_center_ema.
  *   lafs_dh_lse2         merged row statistics [R, 4] of lafs_head_fwd -> log2-domain lse [R].
  *   lafs_dh_loss         loss = 1/((2 ncrops-2) B) sum_{iq<2, v != iq, i} [ lse(s_v,i/ts) - <U_iq,i, x_hat_v,i>/ts ],
- *                        U [2B, D] = Q . W_s (fp32), x_hat_s bf16 [ncrops B, D].
+ *                        U [2B, D] = Q . W_s (fp32), x_hat_s bf16 [ncrops B, D]; sample_loss [B] = per-sample sums
+ *                        (scratch / diagnostic), added in a fixed order.
  *   lafs_dh_bwd_rows     student rows: dx = F.normalize backward of coef (cnt_v O - sum_{iq != v} U_iq), O = P_s . W_s;
  *                        all rows: y [(ncrops+2) B, D] bf16 = the B operand of the dW GEMM (cnt_v x_hat_s | -X~).
  *                        coef = inv_student_temp / ((2 ncrops-2) B) * grad_out[0].
@@ -316,7 +317,7 @@ LAFS_API int lafs_dh_prep_weight(const float* weight_v, const float* weight_g, c
                                  lafs_stream_t stream);
 LAFS_API int lafs_dh_lse2(const float* row_stats, int R, float* lse2, lafs_stream_t stream);
 LAFS_API int lafs_dh_loss(const float* lse2_s, const float* U, const void* x_hat_s_bf16, int B, int ncrops, int D,
-                          float inv_student_temp, float* loss_out, lafs_stream_t stream);
+                          float inv_student_temp, float* sample_loss, float* loss_out, lafs_stream_t stream);
 LAFS_API int lafs_dh_bwd_rows(const float* O, const float* U, const void* x_hat_s_bf16, const float* inv_norm_s,
                               const float* grad_out, int B, int ncrops, int D, float inv_student_temp, float* dx,
                               void* y_bf16, lafs_stream_t stream);

@@ -66,7 +66,7 @@ SIGNATURES = {
     "lafs_dh_xsum": (_i, [_p, _i, _i, _i, _p, _p]),
     "lafs_dh_prep_weight": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p]),
     "lafs_dh_lse2": (_i, [_p, _i, _p, _p]),
-    "lafs_dh_loss": (_i, [_p, _p, _p, _i, _i, _i, _f, _p, _p]),
+    "lafs_dh_loss": (_i, [_p, _p, _p, _i, _i, _i, _f, _p, _p, _p]),
     "lafs_dh_bwd_rows": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _f, _p, _p, _p]),
     "lafs_dh_wn_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _f, _p, _p, _p]),
     "lafs_optim_workspace_bytes": (_z, [_i, _i]),

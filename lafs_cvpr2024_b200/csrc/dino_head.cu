@@ -49,84 +49,116 @@ dh_prep_rows_kernel(const T* __restrict__ x, int R, int D, int ld, __nv_bfloat16
   for (int i = D + lane; i < ld; i += 32) dst[i] = __float2bfloat16_rn(i < D + 3 ? 1.f : 0.f);
 }
 
-// xsum[d] = sum_r x_hat[r, d]  (fp32, fixed order: bit-reproducible); one CTA, D <= 1024
+// xsum[d] = sum_r x_hat[r, d]  (fp32, fixed order: bit-reproducible).  One CTA; warp = row group (rows w, w+32, ...),
+// lane = 8 consecutive columns (one 16-byte load per row) of the current 256-column chunk.  D % 8 == 0.
 __global__ void __launch_bounds__(1024)
 dh_xsum_kernel(const __nv_bfloat16* __restrict__ x_hat, int R, int D, int ld, float* __restrict__ xsum) {
   pdl_wait();
-  __shared__ float part[8][1024];
-  const int c = threadIdx.x & 127, rg = threadIdx.x >> 7;     // 8 row groups x 128 column lanes
-  for (int d = c; d < D; d += 128) {
-    float acc = 0.f;
-    for (int r = rg; r < R; r += 8) acc += __bfloat162float(x_hat[(size_t)r * ld + d]);
-    part[rg][d] = acc;
-  }
-  __syncthreads();
-  for (int d = threadIdx.x; d < D; d += 1024) {
-    float acc = 0.f;
+  __shared__ float part[32][257];
+  const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  for (int c0 = 0; c0 < D; c0 += 256) {
+    const int d = c0 + lane * 8;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (d < D) {
+#pragma unroll 4
+      for (int r = rg; r < R; r += 32) {
+        const uint4 q = *reinterpret_cast<const uint4*>(x_hat + (size_t)r * ld + d);
+        acc[0] += Half2Ops<__nv_bfloat16>::lo(q.x); acc[1] += Half2Ops<__nv_bfloat16>::hi(q.x);
+        acc[2] += Half2Ops<__nv_bfloat16>::lo(q.y); acc[3] += Half2Ops<__nv_bfloat16>::hi(q.y);
+        acc[4] += Half2Ops<__nv_bfloat16>::lo(q.z); acc[5] += Half2Ops<__nv_bfloat16>::hi(q.z);
+        acc[6] += Half2Ops<__nv_bfloat16>::lo(q.w); acc[7] += Half2Ops<__nv_bfloat16>::hi(q.w);
+      }
+    }
 #pragma unroll
-    for (int g = 0; g < 8; ++g) acc += part[g][d];
-    xsum[d] = acc;
+    for (int j = 0; j < 8; ++j) part[rg][lane * 8 + j] = acc[j];
+    __syncthreads();
+    if (threadIdx.x < 256 && c0 + threadIdx.x < D) {
+      float t = 0.f;
+#pragma unroll
+      for (int g = 0; g < 32; ++g) t += part[g][threadIdx.x];
+      xsum[c0 + threadIdx.x] = t;
+    }
+    __syncthreads();
   }
 }
 
 // prototypes: weight_norm rows  w_k = v_k * (g_k / ||v_k||)  (torch._weight_norm, dim 0) -> bf16 [K, ld];
 // ld > D: columns D..D+2 = -(three-term bf16 split of center[k]), zeros after.  inv_norm[k] = 1/||v_k||.
 // colsum[k] = <bf16(w_k), xsum>: the column sum of the teacher logits the tensor cores will see.
+template <int NJ>
 __global__ void __launch_bounds__(256)
 dh_prep_weight_kernel(const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ center,
                       const float* __restrict__ xsum, int K, int D, int ld, __nv_bfloat16* __restrict__ out,
                       float* __restrict__ inv_norm, float* __restrict__ colsum) {
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int k = blockIdx.x * 8 + warp;
+  const int nwarps = gridDim.x * 8;
+  int k = blockIdx.x * 8 + warp;
   if (k >= K) return;
-  const float* src = v + (size_t)k * D;
-  // the row is read once: a lane keeps its <= 8 float4 (D <= 1024, D % 4 == 0) in registers
-  float4 a[8];
-  float ss = 0.f;
+  // a lane owns NJ float4 of a row (D <= 128 NJ, D % 8 == 0); the row is read once, and the next row of this warp is
+  // in flight while the current one is reduced, converted and stored
+  float4 cur[NJ], nxt[NJ];
+  float4 xs[NJ];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < NJ; ++j) {
     const int d = j * 128 + lane * 4;
-    if (d < D) {
-      a[j] = ld_stream_f4(src + d);
-      ss = fmaf(a[j].x, a[j].x, ss); ss = fmaf(a[j].y, a[j].y, ss);
-      ss = fmaf(a[j].z, a[j].z, ss); ss = fmaf(a[j].w, a[j].w, ss);
-    }
+    xs[j] = (xsum != nullptr && d < D) ? *reinterpret_cast<const float4*>(xsum + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (d < D) cur[j] = ld_stream_f4(v + (size_t)k * D + d);
   }
-  ss = warp_sum(ss);
-  const float nrm = sqrtf(ss);
-  const float scale = (g != nullptr ? g[k] : 1.f) / nrm;     // torch: v * (g / norm(v)); a zero row gives inf/nan there too
-  if (lane == 0 && inv_norm != nullptr) inv_norm[k] = 1.f / nrm;
-  __nv_bfloat16* dst = out + (size_t)k * ld;
-  float dot = 0.f;
+  for (; k < K; k += nwarps) {
+    const int kn = k + nwarps;
+    if (kn < K) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int d = j * 128 + lane * 4;
-    if (d < D) {
-      uint2 o;
-      o.x = Half2Ops<__nv_bfloat16>::pack(a[j].x * scale, a[j].y * scale);
-      o.y = Half2Ops<__nv_bfloat16>::pack(a[j].z * scale, a[j].w * scale);
-      *reinterpret_cast<uint2*>(dst + d) = o;
-      if (xsum != nullptr) {
-        const float4 xs = *reinterpret_cast<const float4*>(xsum + d);
-        dot = fmaf(Half2Ops<__nv_bfloat16>::lo(o.x), xs.x, dot); dot = fmaf(Half2Ops<__nv_bfloat16>::hi(o.x), xs.y, dot);
-        dot = fmaf(Half2Ops<__nv_bfloat16>::lo(o.y), xs.z, dot); dot = fmaf(Half2Ops<__nv_bfloat16>::hi(o.y), xs.w, dot);
+      for (int j = 0; j < NJ; ++j) {
+        const int d = j * 128 + lane * 4;
+        if (d < D) nxt[j] = ld_stream_f4(v + (size_t)kn * D + d);
       }
     }
-  }
-  if (colsum != nullptr) {
-    dot = warp_sum(dot);
-    if (lane == 0) colsum[k] = dot;
-  }
-  if (ld > D) {
-    const float c = center != nullptr ? center[k] : 0.f;
-    const float hi = bf16_round(c);
-    const float mid = bf16_round(c - hi);
-    const float lo = bf16_round((c - hi) - mid);
-    for (int i = D + lane; i < ld; i += 32) {
-      const int e = i - D;
-      dst[i] = __float2bfloat16_rn(e == 0 ? -hi : e == 1 ? -mid : e == 2 ? -lo : 0.f);
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      if (j * 128 + lane * 4 < D) {
+        ss = fmaf(cur[j].x, cur[j].x, ss); ss = fmaf(cur[j].y, cur[j].y, ss);
+        ss = fmaf(cur[j].z, cur[j].z, ss); ss = fmaf(cur[j].w, cur[j].w, ss);
+      }
     }
+    ss = warp_sum(ss);
+    const float nrm = sqrtf(ss);
+    const float scale = (g != nullptr ? g[k] : 1.f) / nrm;   // torch: v * (g / norm(v)); a zero row gives inf/nan there too
+    if (lane == 0 && inv_norm != nullptr) inv_norm[k] = 1.f / nrm;
+    __nv_bfloat16* dst = out + (size_t)k * ld;
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int d = j * 128 + lane * 4;
+      if (d < D) {
+        uint2 o;
+        o.x = Half2Ops<__nv_bfloat16>::pack(cur[j].x * scale, cur[j].y * scale);
+        o.y = Half2Ops<__nv_bfloat16>::pack(cur[j].z * scale, cur[j].w * scale);
+        *reinterpret_cast<uint2*>(dst + d) = o;
+        dot = fmaf(Half2Ops<__nv_bfloat16>::lo(o.x), xs[j].x, dot); dot = fmaf(Half2Ops<__nv_bfloat16>::hi(o.x), xs[j].y, dot);
+        dot = fmaf(Half2Ops<__nv_bfloat16>::lo(o.y), xs[j].z, dot); dot = fmaf(Half2Ops<__nv_bfloat16>::hi(o.y), xs[j].w, dot);
+      }
+    }
+    if (colsum != nullptr) {
+      dot = warp_sum(dot);
+      if (lane == 0) colsum[k] = dot;
+    }
+    if (ld > D) {
+      // 64 extra columns = 128 bytes: lane L writes columns D+2L, D+2L+1 as one 32-bit store
+      float e0 = 0.f, e1 = 0.f;
+      if (lane < 2) {
+        const float c = center != nullptr ? center[k] : 0.f;
+        const float hi = bf16_round(c);
+        const float mid = bf16_round(c - hi);
+        const float lo = bf16_round((c - hi) - mid);
+        e0 = lane == 0 ? -hi : -lo;
+        e1 = lane == 0 ? -mid : 0.f;
+      }
+      *reinterpret_cast<uint32_t*>(dst + D + 2 * lane) = Half2Ops<__nv_bfloat16>::pack(e0, e1);
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) cur[j] = nxt[j];
   }
 }
 
@@ -140,38 +172,66 @@ __global__ void dh_lse2_kernel(const float* __restrict__ stats, int R, float* __
 }
 
 // loss = 1/((2 ncrops - 2) B) sum_{iq<2} sum_{v != iq} sum_i [ lse(s_v,i / ts) - <U_iq,i , x_hat_v,i> / ts ]
-// (SURVEY 8a single-pass identity).  One CTA; warp w owns samples w, w+32, ...; fixed summation order.
-__global__ void __launch_bounds__(1024)
-dh_loss_kernel(const float* __restrict__ lse2_s, const float* __restrict__ U, const __nv_bfloat16* __restrict__ x_hat_s,
-               int B, int ncrops, int D, float inv_ts, float* __restrict__ loss_out) {
+// (SURVEY 8a single-pass identity).  One warp per sample i writes the sample's sum; dh_sum_kernel adds the B sums in
+// a fixed order.  A lane owns 8 consecutive columns of every 256-column chunk (D % 8 == 0).
+__device__ __forceinline__ void bf16x8_to_float(const uint4 q, float (&f)[8]) {
+  f[0] = Half2Ops<__nv_bfloat16>::lo(q.x); f[1] = Half2Ops<__nv_bfloat16>::hi(q.x);
+  f[2] = Half2Ops<__nv_bfloat16>::lo(q.y); f[3] = Half2Ops<__nv_bfloat16>::hi(q.y);
+  f[4] = Half2Ops<__nv_bfloat16>::lo(q.z); f[5] = Half2Ops<__nv_bfloat16>::hi(q.z);
+  f[6] = Half2Ops<__nv_bfloat16>::lo(q.w); f[7] = Half2Ops<__nv_bfloat16>::hi(q.w);
+}
+
+__global__ void __launch_bounds__(256)
+dh_loss_rows_kernel(const float* __restrict__ lse2_s, const float* __restrict__ U, const __nv_bfloat16* __restrict__ x_hat_s,
+                    int B, int ncrops, int D, float inv_ts, float* __restrict__ sample_loss) {
   pdl_wait();
-  __shared__ float red[32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float acc = 0.f;      // per-lane partial of this warp's samples
-  for (int i = warp; i < B; i += 32) {
+  const int i = blockIdx.x * 8 + warp;
+  if (i >= B) return;
+  float acc = 0.f;
+  for (int d = lane * 8; d < D; d += 256) {
+    float u0[8], u1[8];
+    {
+      const float4 a = *reinterpret_cast<const float4*>(U + (size_t)i * D + d);
+      const float4 b = *reinterpret_cast<const float4*>(U + (size_t)i * D + d + 4);
+      const float4 c = *reinterpret_cast<const float4*>(U + ((size_t)B + i) * D + d);
+      const float4 e = *reinterpret_cast<const float4*>(U + ((size_t)B + i) * D + d + 4);
+      u0[0] = a.x; u0[1] = a.y; u0[2] = a.z; u0[3] = a.w; u0[4] = b.x; u0[5] = b.y; u0[6] = b.z; u0[7] = b.w;
+      u1[0] = c.x; u1[1] = c.y; u1[2] = c.z; u1[3] = c.w; u1[4] = e.x; u1[5] = e.y; u1[6] = e.z; u1[7] = e.w;
+    }
     for (int v = 0; v < ncrops; ++v) {
-      const size_t row = (size_t)v * B + i;
-      const __nv_bfloat16* xr = x_hat_s + row * D;
-      const float cnt = v < 2 ? 1.f : 2.f;
-      if (lane == 0) acc = fmaf(cnt * kLn2D, lse2_s[row], acc);
+      float xf[8];
+      bf16x8_to_float(*reinterpret_cast<const uint4*>(x_hat_s + ((size_t)v * B + i) * D + d), xf);
       float dot = 0.f;
-      for (int d = lane; d < D; d += 32) {
-        float u = 0.f;
-        if (v != 0) u += U[(size_t)i * D + d];
-        if (v != 1) u += U[((size_t)B + i) * D + d];
-        dot = fmaf(u, __bfloat162float(xr[d]), dot);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float u = (v != 0 ? u0[j] : 0.f) + (v != 1 ? u1[j] : 0.f);
+        dot = fmaf(u, xf[j], dot);
       }
       acc = fmaf(-inv_ts, dot, acc);
     }
   }
   acc = warp_sum(acc);
-  if (lane == 0) red[warp] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int w = 0; w < 32; ++w) t += red[w];
-    *loss_out = t / ((float)(2 * ncrops - 2) * (float)B);
+  if (lane == 0) {
+    for (int v = 0; v < ncrops; ++v) acc = fmaf((v < 2 ? 1.f : 2.f) * kLn2D, lse2_s[(size_t)v * B + i], acc);
+    sample_loss[i] = acc;
   }
+}
+
+// out = scale * sum_i x[i]  (one CTA, fixed order)
+__global__ void __launch_bounds__(256)
+dh_sum_kernel(const float* __restrict__ x, int n, float scale, float* __restrict__ out) {
+  pdl_wait();
+  __shared__ float red[256];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) acc += x[i];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = red[0] * scale;
 }
 
 // backward, per row of the [(ncrops+2) B] row space (student rows first, teacher rows after):
@@ -190,36 +250,69 @@ dh_bwd_rows_kernel(const float* __restrict__ O, const float* __restrict__ U, con
   if (row >= ns + 2 * B) return;
   if (row >= ns) {
     const int iq = (row - ns) / B, i = (row - ns) - iq * B;
-    for (int d = lane; d < D; d += 32) {
-      float acc = 0.f;
-      for (int v = 0; v < ncrops; ++v)
-        if (v != iq) acc += __bfloat162float(x_hat_s[((size_t)v * B + i) * D + d]);
-      y[(size_t)row * D + d] = __float2bfloat16_rn(-acc);
+    for (int d = lane * 8; d < D; d += 256) {
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int v = 0; v < ncrops; ++v) {
+        if (v == iq) continue;
+        float xf[8];
+        bf16x8_to_float(*reinterpret_cast<const uint4*>(x_hat_s + ((size_t)v * B + i) * D + d), xf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += xf[j];
+      }
+      uint4 o;
+      o.x = Half2Ops<__nv_bfloat16>::pack(-acc[0], -acc[1]); o.y = Half2Ops<__nv_bfloat16>::pack(-acc[2], -acc[3]);
+      o.z = Half2Ops<__nv_bfloat16>::pack(-acc[4], -acc[5]); o.w = Half2Ops<__nv_bfloat16>::pack(-acc[6], -acc[7]);
+      *reinterpret_cast<uint4*>(y + (size_t)row * D + d) = o;
     }
     return;
   }
   const int v = row / B, i = row - v * B;
   const float cnt = v < 2 ? 1.f : 2.f;
   const float cf = coef * __ldg(grad_out);
-  const __nv_bfloat16* xr = x_hat_s + (size_t)row * D;
+  // D <= 768: a lane holds its <= 3 groups of 8 columns of d and x_hat in registers between the two passes
+  float dd[3][8], xf[3][8];
   float dot = 0.f;
-  for (int d = lane; d < D; d += 32) {
-    float u = 0.f;
-    if (v != 0) u += U[(size_t)i * D + d];
-    if (v != 1) u += U[((size_t)B + i) * D + d];
-    const float dd = cf * (cnt * O[(size_t)row * D + d] - u);
-    dot = fmaf(dd, __bfloat162float(xr[d]), dot);
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const int d = q * 256 + lane * 8;
+    if (d < D) {
+      bf16x8_to_float(*reinterpret_cast<const uint4*>(x_hat_s + (size_t)row * D + d), xf[q]);
+      float o[8], u[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      {
+        const float4 a = *reinterpret_cast<const float4*>(O + (size_t)row * D + d);
+        const float4 b = *reinterpret_cast<const float4*>(O + (size_t)row * D + d + 4);
+        o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+      }
+#pragma unroll
+      for (int iq = 0; iq < 2; ++iq) {
+        if (iq == v) continue;
+        const float4 a = *reinterpret_cast<const float4*>(U + ((size_t)iq * B + i) * D + d);
+        const float4 b = *reinterpret_cast<const float4*>(U + ((size_t)iq * B + i) * D + d + 4);
+        u[0] += a.x; u[1] += a.y; u[2] += a.z; u[3] += a.w; u[4] += b.x; u[5] += b.y; u[6] += b.z; u[7] += b.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        dd[q][j] = cf * (cnt * o[j] - u[j]);
+        dot = fmaf(dd[q][j], xf[q][j], dot);
+      }
+    }
   }
   dot = warp_sum(dot);
   const float inv = inv_norm_s[row];
-  for (int d = lane; d < D; d += 32) {
-    float u = 0.f;
-    if (v != 0) u += U[(size_t)i * D + d];
-    if (v != 1) u += U[((size_t)B + i) * D + d];
-    const float xh = __bfloat162float(xr[d]);
-    const float dd = cf * (cnt * O[(size_t)row * D + d] - u);
-    dx[(size_t)row * D + d] = (dd - xh * dot) * inv;
-    y[(size_t)row * D + d] = __float2bfloat16_rn(cnt * xh);
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const int d = q * 256 + lane * 8;
+    if (d < D) {
+      float r[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = (dd[q][j] - xf[q][j] * dot) * inv;
+      *reinterpret_cast<float4*>(dx + (size_t)row * D + d) = make_float4(r[0], r[1], r[2], r[3]);
+      *reinterpret_cast<float4*>(dx + (size_t)row * D + d + 4) = make_float4(r[4], r[5], r[6], r[7]);
+      uint4 o;
+      o.x = Half2Ops<__nv_bfloat16>::pack(cnt * xf[q][0], cnt * xf[q][1]); o.y = Half2Ops<__nv_bfloat16>::pack(cnt * xf[q][2], cnt * xf[q][3]);
+      o.z = Half2Ops<__nv_bfloat16>::pack(cnt * xf[q][4], cnt * xf[q][5]); o.w = Half2Ops<__nv_bfloat16>::pack(cnt * xf[q][6], cnt * xf[q][7]);
+      *reinterpret_cast<uint4*>(y + (size_t)row * D + d) = o;
+    }
   }
 }
 
@@ -281,7 +374,9 @@ extern "C" int lafs_dh_prep_rows(const void* x, int dtype, int R, int D, int ld,
 
 extern "C" int lafs_dh_xsum(const void* x_hat_bf16, int R, int D, int ld, float* xsum, lafs_stream_t stream) {
   if (int brc = lafs::bind_device_of(x_hat_bf16)) return brc;
-  LAFS_REQUIRE(x_hat_bf16 && xsum && R > 0 && D > 0 && D <= 1024 && ld >= D, LAFS_ERR_ARG, "lafs_dh_xsum: bad argument (D <= 1024)");
+  LAFS_REQUIRE(x_hat_bf16 && xsum && R > 0 && D > 0 && D % 8 == 0 && ld >= D && ld % 8 == 0, LAFS_ERR_ARG,
+               "lafs_dh_xsum: bad argument (D and ld multiples of 8)");
+  LAFS_REQUIRE(((uintptr_t)x_hat_bf16 & 15u) == 0, LAFS_ERR_ARG, "lafs_dh_xsum: x_hat must be 16-byte aligned");
   launch_pdl((dh_xsum_kernel), dim3(1), dim3(1024), (size_t)0, (cudaStream_t)stream, (const __nv_bfloat16*)x_hat_bf16, R, D, ld, xsum);
   return check_launch("lafs_dh_xsum");
 }
@@ -297,8 +392,16 @@ extern "C" int lafs_dh_prep_weight(const float* weight_v, const float* weight_g,
   LAFS_REQUIRE(ld == D || ld == D + kDhExtra, LAFS_ERR_ARG, "lafs_dh_prep_weight: ld=%d must be D or D+%d", ld, kDhExtra);
   LAFS_REQUIRE(!(center != nullptr && ld == D), LAFS_ERR_ARG, "lafs_dh_prep_weight: a centre needs ld = D+%d", kDhExtra);
   LAFS_REQUIRE((colsum == nullptr) == (xsum == nullptr), LAFS_ERR_ARG, "lafs_dh_prep_weight: colsum and xsum go together");
-  launch_pdl((dh_prep_weight_kernel), dim3((K + 7) / 8), dim3(256), (size_t)0, (cudaStream_t)stream, weight_v, weight_g, center, xsum,
-             K, D, ld, (__nv_bfloat16*)out_bf16, inv_norm, colsum);
+  // persistent warps: up to 8 CTAs of 8 warps per SM, every warp walks rows with the grid stride
+  int grid = (K + 7) / 8;
+  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* o = (__nv_bfloat16*)out_bf16;
+  const int nj = (D + 127) / 128;
+  if (nj <= 1) launch_pdl((dh_prep_weight_kernel<1>), dim3(grid), dim3(256), (size_t)0, st, weight_v, weight_g, center, xsum, K, D, ld, o, inv_norm, colsum);
+  else if (nj == 2) launch_pdl((dh_prep_weight_kernel<2>), dim3(grid), dim3(256), (size_t)0, st, weight_v, weight_g, center, xsum, K, D, ld, o, inv_norm, colsum);
+  else if (nj <= 4) launch_pdl((dh_prep_weight_kernel<4>), dim3(grid), dim3(256), (size_t)0, st, weight_v, weight_g, center, xsum, K, D, ld, o, inv_norm, colsum);
+  else launch_pdl((dh_prep_weight_kernel<8>), dim3(grid), dim3(256), (size_t)0, st, weight_v, weight_g, center, xsum, K, D, ld, o, inv_norm, colsum);
   return check_launch("lafs_dh_prep_weight");
 }
 
@@ -310,12 +413,15 @@ extern "C" int lafs_dh_lse2(const float* row_stats, int R, float* lse2, lafs_str
 }
 
 extern "C" int lafs_dh_loss(const float* lse2_s, const float* U, const void* x_hat_s_bf16, int B, int ncrops, int D,
-                            float inv_student_temp, float* loss_out, lafs_stream_t stream) {
+                            float inv_student_temp, float* sample_loss, float* loss_out, lafs_stream_t stream) {
   if (int brc = lafs::bind_device_of(lse2_s)) return brc;
-  LAFS_REQUIRE(lse2_s && U && x_hat_s_bf16 && loss_out, LAFS_ERR_ARG, "lafs_dh_loss: null pointer");
-  LAFS_REQUIRE(B > 0 && ncrops >= 2 && D > 0, LAFS_ERR_ARG, "lafs_dh_loss: B=%d ncrops=%d D=%d", B, ncrops, D);
-  launch_pdl((dh_loss_kernel), dim3(1), dim3(1024), (size_t)0, (cudaStream_t)stream, lse2_s, U, (const __nv_bfloat16*)x_hat_s_bf16,
-             B, ncrops, D, inv_student_temp, loss_out);
+  LAFS_REQUIRE(lse2_s && U && x_hat_s_bf16 && sample_loss && loss_out, LAFS_ERR_ARG, "lafs_dh_loss: null pointer");
+  LAFS_REQUIRE(B > 0 && ncrops >= 2 && D > 0 && D % 8 == 0, LAFS_ERR_ARG, "lafs_dh_loss: B=%d ncrops=%d D=%d (D %% 8 == 0)", B, ncrops, D);
+  LAFS_REQUIRE((((uintptr_t)U | (uintptr_t)x_hat_s_bf16) & 15u) == 0, LAFS_ERR_ARG, "lafs_dh_loss: U / x_hat_s must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  launch_pdl((dh_loss_rows_kernel), dim3((B + 7) / 8), dim3(256), (size_t)0, st, lse2_s, U, (const __nv_bfloat16*)x_hat_s_bf16,
+             B, ncrops, D, inv_student_temp, sample_loss);
+  launch_pdl((dh_sum_kernel), dim3(1), dim3(256), (size_t)0, st, (const float*)sample_loss, B, 1.f / ((float)(2 * ncrops - 2) * (float)B), loss_out);
   return check_launch("lafs_dh_loss");
 }
 
@@ -324,7 +430,9 @@ extern "C" int lafs_dh_bwd_rows(const float* O, const float* U, const void* x_ha
                                 void* y_bf16, lafs_stream_t stream) {
   if (int brc = lafs::bind_device_of(O)) return brc;
   LAFS_REQUIRE(O && U && x_hat_s_bf16 && inv_norm_s && grad_out && dx && y_bf16, LAFS_ERR_ARG, "lafs_dh_bwd_rows: null pointer");
-  LAFS_REQUIRE(B > 0 && ncrops >= 2 && D > 0, LAFS_ERR_ARG, "lafs_dh_bwd_rows: B=%d ncrops=%d D=%d", B, ncrops, D);
+  LAFS_REQUIRE(B > 0 && ncrops >= 2 && D > 0 && D % 8 == 0 && D <= 768, LAFS_ERR_ARG, "lafs_dh_bwd_rows: B=%d ncrops=%d D=%d (D %% 8 == 0, <= 768)", B, ncrops, D);
+  LAFS_REQUIRE((((uintptr_t)O | (uintptr_t)U | (uintptr_t)x_hat_s_bf16 | (uintptr_t)dx | (uintptr_t)y_bf16) & 15u) == 0, LAFS_ERR_ARG,
+               "lafs_dh_bwd_rows: pointers must be 16-byte aligned");
   const float coef = inv_student_temp / ((float)(2 * ncrops - 2) * (float)B);
   const int rows = (ncrops + 2) * B;
   launch_pdl((dh_bwd_rows_kernel), dim3((rows + 7) / 8), dim3(256), (size_t)0, (cudaStream_t)stream, O, U,

@@ -144,8 +144,9 @@ def dino_head_forward(xs, xt, vs, gs, vt, gt, center, ncrops, inv_ts, inv_tt, ke
     # student: row lse of s/ts; loss
     lse2_s = _row_lse2(xs_hat, ws, rs, K, D, inv_ts)
     loss = torch.empty((), dtype=torch.float32, device=dev)
+    sample_loss = torch.empty(B, dtype=torch.float32, device=dev)
     _lib.call("lafs_dh_loss", lse2_s.data_ptr(), U.data_ptr(), xs_hat.data_ptr(), B, ncrops, D, float(inv_ts),
-              loss.data_ptr(), st)
+              sample_loss.data_ptr(), loss.data_ptr(), st)
     saved = dict(B=B, K=K, D=D, ncrops=ncrops, inv_ts=float(inv_ts), ldp=ldp, xs_hat=xs_hat, inv_xs=inv_xs, ws=ws,
                  inv_w=inv_w, vs=vs_c, gs=gs_c, lse2_s=lse2_s, U=U, P=P if keep_for_backward else None)
     return loss, colsum, saved
