@@ -95,11 +95,29 @@ class Attention(nn.Module):
         self.to_out = nn.Sequential(nn.Linear(inner, dim), nn.Dropout(dropout))
         self.attention_score = 0
 
+    # The reference stores softmax(q k^T * scale) of EVERY forward in `attention_score` (ViT_face.py:178); its only
+    # reader is the evaluation-time attention-map plot (util/utils.py:662).  The flash path never forms that
+    # [b, h, n, n] tensor, so the last forward's q and k are kept (two views of the qkv projection, no copy) and
+    # the scores are computed when somebody reads the attribute.
+    @property
+    def attention_score(self):
+        qk = self.__dict__.get("_qk")
+        if qk is not None:
+            q, k = qk
+            return (torch.einsum('bhid,bhjd->bhij', q, k) * self.scale).softmax(dim=-1)
+        return self.__dict__.get("_attention_score", 0)
+
+    @attention_score.setter
+    def attention_score(self, value):
+        self.__dict__["_qk"] = None
+        self.__dict__["_attention_score"] = value
+
     def forward(self, x, mask=None):
         b, n, _ = x.shape
         q, k, v = (t.view(b, n, self.heads, -1).transpose(1, 2) for t in self.to_qkv(x).chunk(3, dim=-1))
         if mask is None:
             out = F.scaled_dot_product_attention(q, k, v, scale=self.scale)
+            self.__dict__["_qk"] = (q.detach(), k.detach())
         else:
             # the reference's masked form, op for op (ViT_face.py:164-176): masked logits are REPLACED by
             # -finfo.max, so a fully masked query row attends uniformly and stays finite (a boolean SDPA mask

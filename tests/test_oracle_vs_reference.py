@@ -172,6 +172,10 @@ def test_attention_with_mask_matches_reference(ref):
         torch.testing.assert_close(oa.attention_score, ra.attention_score, rtol=1e-5, atol=1e-7)
     x = torch.randn(2, n + 1, dim)
     torch.testing.assert_close(oa(x), ra(x), rtol=1e-5, atol=1e-6)     # unmasked path (SDPA) agrees too
+    # ... and `attention_score` of the unmasked forward (read by util/utils.py:662) is what the reference stashed
+    assert oa.attention_score.shape == (2, heads, n + 1, n + 1) and not oa.attention_score.requires_grad
+    torch.testing.assert_close(oa.attention_score, ra.attention_score, rtol=1e-5, atol=1e-7)
+    assert V.Attention(dim, heads=heads, dim_head=16).attention_score == 0          # before any forward (ViT_face.py:159)
     assert torch.isfinite(oa(x, mask=torch.zeros(2, n, dtype=torch.bool))).all()   # batched masks work here
 
 
