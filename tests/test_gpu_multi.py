@@ -144,6 +144,61 @@ def _body_main(rank, world, ret):
         assert all(torch.equal(cs[0], c) for c in cs)      # identical bits on every rank
 
 
+def _body_fused_dino_head(rank, world, ret):
+    """(f1) fused last_layer + DINO loss on several ranks: the loss is rank-local (DDP averages gradients), the centre
+    moves by the EMA of the GLOBAL teacher mean (all-reduce of the [K] column sums, lafs_train.py:675) and ends with
+    identical bits on every rank -- through NCCL and through the peer-memory all-reduce."""
+    import lafs_cvpr2024_b200 as P
+    in_dim, K, B, nc = 64, 2048, 8, 4
+    torch.manual_seed(0)                                     # same heads on every rank
+    hs = P.DINOHead(in_dim, K, nlayers=2, hidden_dim=96, bottleneck_dim=64, fused_loss=True).cuda()
+    ht = P.DINOHead(in_dim, K, nlayers=2, hidden_dim=96, bottleneck_dim=64, fused_loss=True).cuda()
+    with torch.no_grad():
+        for h in (hs, ht):
+            h.last_layer.weight_v.normal_(0, 0.5)
+    g = torch.Generator().manual_seed(20 + rank)             # different samples per rank
+    fs, ft = torch.randn(nc * B, in_dim, generator=g).cuda(), torch.randn(2 * B, in_dim, generator=g).cuda()
+    c0 = torch.randn(1, K, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3)) * 0.05
+    centres = []
+    for peer in (False, True):
+        crit = P.DINOLoss(K, nc, 0.04, 0.07, 30, 41).cuda()
+        if peer:
+            crit.enable_peer_exchange()
+        crit.center = c0.clone()
+        with torch.no_grad():
+            to = ht(ft)
+        loss = crit(hs(fs), to, 3)
+        loss.backward()
+        # reference: the unfused modules on this rank's samples + the global teacher mean
+        with torch.no_grad():
+            t_log = to.logits()
+        allt = [torch.empty_like(t_log) for _ in range(world)]
+        dist.all_gather(allt, t_log.contiguous())
+        ref_c = c0 * 0.9 + torch.cat(allt).float().sum(0, keepdim=True) / (2 * B * world) * (1 - 0.9)
+        torch.testing.assert_close(crit.center, ref_c, rtol=0, atol=2e-3 * float(ref_c.abs().max()) + 1e-4)
+        cu = P.DINOLoss(K, nc, 0.04, 0.07, 30, 41).cuda()
+        cu.center = c0.clone()
+        hs.fused_loss = False
+        lu = cu(hs(fs), t_log, 3)
+        hs.fused_loss = True
+        assert abs(float(loss) - float(lu)) <= 1e-3 * abs(float(lu)), (peer, float(loss), float(lu))
+        cs = [torch.empty_like(crit.center) for _ in range(world)]
+        dist.all_gather(cs, crit.center.contiguous())
+        assert all(torch.equal(cs[0], c) for c in cs)        # identical bits on every rank
+        centres.append(crit.center.clone())
+    torch.testing.assert_close(centres[0], centres[1], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_fused_dino_head_two_gpus():
+    world = 2
+    port = 29700 + (os.getpid() % 100)
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        _spawn_and_wait("_body_fused_dino_head", world, port, ret)
+        assert dict(ret) == {0: "ok", 1: "ok"}, dict(ret)
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
 def test_sharded_head_and_center_two_gpus():
     world = 2
