@@ -38,16 +38,24 @@ def label_to_shard(label, num_classes, world):
 
 def two_hot_from_dense(target):
     """Recovers (label_a, label_b, lam) from a dense mixup target [B, C] (util/mixup_my.py:18-24:
-    lam at label[i], 1-lam at label[B-1-i], exactly <= 2 non-zeros per row)."""
+    lam at label[i], 1-lam at label[B-1-i], at most two non-zeros per row, ONE lam for the whole batch).
+    One device->host read (the reference builds the dense target on the host in the first place, ViT_face.py:64-71)."""
     vals, idx = target.topk(2, dim=1)
-    if bool(((target != 0).sum(1) > 2).any()):
-        raise ValueError("dense soft targets with more than two non-zeros per row are not supported "
-                         "by the fused head (the reference's Mixup produces at most two)")
     la, lb = idx[:, 0], idx[:, 1]
     lb = torch.where(vals[:, 1] == 0, la, lb)
     # rows whose two classes coincide (or hard rows) have val0 == 1; lam is a batch scalar otherwise
     mixed = vals[:, 1] != 0
-    lam = float(vals[mixed, 0].max()) if bool(mixed.any()) else 1.0
+    big = torch.where(mixed, vals[:, 0], torch.full_like(vals[:, 0], -1.0))
+    small = torch.where(mixed, vals[:, 0], torch.full_like(vals[:, 0], 2.0))
+    too_many, any_mixed, lam_hi, lam_lo = torch.stack([
+        ((target != 0).sum(1) > 2).any().to(vals.dtype), mixed.any().to(vals.dtype), big.max(), small.min()]).tolist()
+    if too_many:
+        raise ValueError("dense soft targets with more than two non-zeros per row are not supported "
+                         "by the fused head (the reference's Mixup produces at most two)")
+    if any_mixed and lam_hi - lam_lo > 1e-6:
+        raise ValueError("dense soft targets with a different mixing weight per row (Mixup modes 'elem' / 'pair') are "
+                         f"not supported by the fused head: weights span [{lam_lo}, {lam_hi}]; pass label_a, label_b, lam")
+    lam = float(lam_hi) if any_mixed else 1.0
     return la, lb, lam
 
 
@@ -214,17 +222,16 @@ class _HeadLogitsFn(torch.autograd.Function):
         ldg = _round8(C)
         G = torch.zeros(B, ldg, dtype=torch.bfloat16, device=e_hat.device)
         gz = grad_logits.detach().float() * s                      # d z / d cos = s (margin is a shift)
-        if kind == KIND_ARCFACE:                                   # target column: s * d phi / d cos
+        if kind == KIND_ARCFACE:                                   # target column: s * d phi / d cos (no host sync)
             loc = la - class_lo
             own = (loc >= 0) & (loc < C)
-            rows = torch.nonzero(own).flatten()
-            if rows.numel():
-                cols = loc[rows]
-                cos_t = (e_hat[rows].float() * w_hat[cols].float()).sum(1)
-                th = math.cos(math.pi - m)
-                sine = torch.sqrt((1 - cos_t * cos_t).clamp(1e-12, 1))
-                dphi = torch.where(cos_t > th, math.cos(m) + cos_t * math.sin(m) / sine, torch.ones_like(cos_t))
-                gz[rows, cols] = gz[rows, cols] * dphi
+            cols = loc.clamp(0, C - 1)
+            rows = torch.arange(B, device=e_hat.device)
+            cos_t = (e_hat.float() * w_hat[cols].float()).sum(1)
+            th = math.cos(math.pi - m)
+            sine = torch.sqrt((1 - cos_t * cos_t).clamp(1e-12, 1))
+            dphi = torch.where(own & (cos_t > th), math.cos(m) + cos_t * math.sin(m) / sine, torch.ones_like(cos_t))
+            gz[rows, cols] = gz[rows, cols] * dphi
         G[:, :C] = gz.to(torch.bfloat16)
         de, dw = _head_backward(G, ldg, e_hat, w_hat, inv_e, inv_w, B, C, D, False)
         return de.to(in_dtype), dw, None, None, None, None
@@ -297,6 +304,11 @@ class _MarginHead(nn.Module):
         return torch.cat(parts)[: self.out_features].contiguous()
 
     # ---- helpers -----------------------------------------------------------------------------
+    # The reference's one_hot.scatter_ (ViT_face.py:66-68) raises on a label outside [0, out_features); a label the
+    # kernels never meet only drops its target term (loss = lse).  Checking costs a device->host read per call, so it
+    # is opt-in: head.check_labels = True.
+    check_labels = False
+
     def _labels(self, label, label_b, lam):
         if label.dim() > 1:                                # dense [B, C] soft targets (reference API)
             if self.kind == KIND_ARCFACE:
@@ -305,6 +317,11 @@ class _MarginHead(nn.Module):
             return la.to(torch.int64).contiguous(), lb.to(torch.int64).contiguous(), lam
         la = label.to(torch.int64).contiguous()
         lb = None if label_b is None else label_b.to(torch.int64).contiguous()
+        if self.check_labels:
+            both = la if lb is None else torch.cat([la, lb])
+            lo, hi = torch.stack([both.min(), both.max()]).tolist()
+            if lo < 0 or hi >= self.out_features:
+                raise IndexError(f"label out of range: [{lo}, {hi}] outside [0, {self.out_features})")
         return la, lb, float(lam)
 
     def _operands(self, input):

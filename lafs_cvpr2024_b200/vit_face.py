@@ -147,12 +147,13 @@ class Transformer(nn.Module):
         return x
 
 
-def _tokens_and_embedding(imgs, theta, linear, training_path):
+def _tokens_and_embedding(imgs, theta, linear, training_path, allow_tc=True):
     """patch tokens -> patch_to_embedding on the fused tcgen05 gather->embed kernel (no token tensor in
     HBM).  With gradients its backward runs on the tcgen05 GEMMs of patches.gather_embed_train; shapes
     the fused kernel does not cover (dim % 128 != 0, more than 208 landmarks) take the differentiable
-    fp32 gather kernel + nn.Linear."""
-    fused_ok = (linear.weight.shape[0] % 128 == 0 and theta.shape[1] <= 208 and imgs.shape[1] == 3
+    fp32 gather kernel + nn.Linear -- and so does a model that asked for full precision (allow_tc=False: fp16=False
+    in the constructor and no autocast region): the tensor-core path rounds tokens and weights to bf16."""
+    fused_ok = (allow_tc and linear.weight.shape[0] % 128 == 0 and theta.shape[1] <= 208 and imgs.shape[1] == 3
                 and tuple(imgs.shape[-2:]) == (112, 112))
     if training_path:
         if fused_ok:
@@ -278,7 +279,10 @@ class ViT_face_landmark_patch8(nn.Module):
             need_grad = torch.is_grad_enabled() and (theta.requires_grad or x.requires_grad
                                                      or self.patch_to_embedding.weight.requires_grad)
             lin = self.patch_to_embedding
-            if (not need_grad and lin.weight.shape[0] % 128 == 0 and num_land <= 208 and x.shape[1] == 3
+            # half-precision contract of the reference: its models are built with fp16=True and trained under autocast
+            # (ViT_face.py:561, train_largescale.py:803-804); only then does patch_to_embedding run on bf16 operands
+            use_tc = bool(self.fp16) or torch.is_autocast_enabled()
+            if (use_tc and not need_grad and lin.weight.shape[0] % 128 == 0 and num_land <= 208 and x.shape[1] == 3
                     and tuple(x.shape[-2:]) == (112, 112) and self.pos_embedding.shape[1] >= num_land + 1):
                 # inference / frozen path: cls row, pos_embedding and dropout are part of the fused kernel's epilogue
                 # (SURVEY 8f row 2): the transformer input leaves ONE kernel
@@ -287,7 +291,7 @@ class ViT_face_landmark_patch8(nn.Module):
                 (x,) = gather_embed(x.float(), theta[:, :num_land], PatchEmbedWeights([(lin.weight, lin.bias)]),
                                     seq=[(self.pos_embedding, self.cls_token)], drop_p=p_drop, seed=seed)
                 return self._after_embedding(x.to(lin.weight.dtype), label, mask, visualize, save_token, opt, theta)
-            x = _tokens_and_embedding(x.float(), theta[:, :num_land], self.patch_to_embedding, need_grad)
+            x = _tokens_and_embedding(x.float(), theta[:, :num_land], self.patch_to_embedding, need_grad, use_tc)
         else:
             x = self.patch_to_embedding(x)                       # SSL path: tokens prepared by the landmark CNN
         b, n, _ = x.shape

@@ -184,6 +184,49 @@ def test_cosface_forward_logits_backward_golden(P, golden):
     assert (h.weight.grad.cpu() - ref_gw).abs().max() <= 2e-2 * ref_gw.abs().max()
 
 
+@pytest.mark.parametrize("shard", [None, (1, 3)])
+def test_arcface_forward_logits_backward_vs_oracle(P, shard):
+    """logits = ArcFace(x, label); CrossEntropyLoss(logits, label).backward(): the target column's d phi / d cos factor
+    of the full-logits path (computed on the device without a host sync), unsharded and on a class shard (some
+    labels owned by other ranks), against autograd through the oracle on the same bf16 operands."""
+    torch.manual_seed(77)
+    B, C, D = 96, 1501, 128
+    x, w = torch.randn(B, D), torch.randn(C, D) * 0.05
+    lab = torch.randint(0, C, (B,))
+    lab[0], lab[1] = 0, C - 1
+    lo, hi = (0, C) if shard is None else P.shard_bounds(C, shard[1])[shard[0]]
+    h = P.ArcFace(D, C, None, shard=shard).cuda()
+    with torch.no_grad():
+        h.weight.copy_(w[lo:hi])
+    xg = x.cuda().requires_grad_(True)
+    logits = h(xg, lab.cuda())
+    up = torch.randn(B, hi - lo, generator=torch.Generator().manual_seed(5))
+    (logits * up.cuda()).sum().backward()
+    xh = bf16_round(torch.nn.functional.normalize(x)).requires_grad_(True)
+    wh = bf16_round(torch.nn.functional.normalize(w)).requires_grad_(True)
+    ref = O.arcface_logits(xh, wh, lab, pre_normalized=True)[:, lo:hi]
+    assert (logits.detach().cpu() - ref.detach()).abs().max() <= 1e-3 * ref.detach().abs().max()
+    (ref * up).sum().backward()
+    # chain through F.normalize on both sides (the oracle differentiated w.r.t. the unit operands)
+    xn, wn = x.norm(dim=1, keepdim=True), w.norm(dim=1, keepdim=True)
+    xu, wu = x / xn, w / wn
+    ref_gx = (xh.grad - xu * (xu * xh.grad).sum(1, keepdim=True)) / xn
+    ref_gw = ((wh.grad - wu * (wu * wh.grad).sum(1, keepdim=True)) / wn)[lo:hi]
+    assert (xg.grad.cpu() - ref_gx).abs().max() <= 1e-2 * ref_gx.abs().max()
+    assert (h.weight.grad.cpu() - ref_gw).abs().max() <= 1e-2 * ref_gw.abs().max()
+
+
+def test_label_range_check_is_opt_in(P):
+    h = P.CosFace(64, 100, None).cuda()
+    x = torch.randn(4, 64, device="cuda")
+    bad = torch.tensor([1, 2, 100, 3], device="cuda")
+    assert torch.isfinite(h.forward_loss(x, bad))            # default: the out-of-range row contributes its lse only
+    h.check_labels = True
+    with pytest.raises(IndexError):
+        h.forward_loss(x, bad)
+    assert torch.isfinite(h.forward_loss(x, torch.tensor([1, 2, 99, 0], device="cuda")))
+
+
 def _step_outputs(P, B, C, D, kind, env):
     """loss, row lse, dE, dW of one fused-loss step under the given kernel-variant switches."""
     import os

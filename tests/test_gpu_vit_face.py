@@ -89,6 +89,31 @@ def test_inference_uses_fused_path(P):
     assert (emb.cpu() - emb_ref).abs().max() <= 2e-2 * emb_ref.abs().max()     # bf16 patch embedding inside
 
 
+def test_full_precision_model_keeps_fp32_patch_embedding(P):
+    """fp16=False and no autocast region: patch_to_embedding stays an fp32 nn.Linear on the (bit-exact) gathered tokens,
+    with and without gradients; inside an autocast region the same model takes the tensor-core path again."""
+    torch.backends.cudnn.allow_tf32 = False          # the stand-in trunk must match its CPU twin closely
+    torch.backends.cuda.matmul.allow_tf32 = False
+    m = make(P, loss_type="None", fp16=False)
+    ref = copy.deepcopy(m)
+    x = torch.rand(3, 3, 112, 112) * 2 - 1
+    with torch.no_grad():
+        emb_ref, _ = oracle_forward(ref, x)
+        emb = m.cuda()(x.cuda())
+    # fp32 everywhere: 10x tighter than the bf16 path's 2e-2 (what is left is the cuDNN / CPU difference of the trunk)
+    assert (emb.cpu() - emb_ref).abs().max() <= 2e-3 * emb_ref.abs().max()
+    e = m(x.cuda())                                   # eval mode (the landmark head has a Dropout), gradients on
+    e.square().mean().backward()
+    er, _ = oracle_forward(ref, x)
+    er.square().mean().backward()
+    assert (e.detach().cpu() - er.detach()).abs().max() <= 2e-3 * er.detach().abs().max()
+    gw, gr = m.patch_to_embedding.weight.grad.cpu(), ref.patch_to_embedding.weight.grad
+    assert (gw - gr).abs().max() <= 5e-3 * gr.abs().max()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        emb_ac = m(x.cuda())
+    assert (emb_ac.float().cpu() - emb_ref).abs().max() <= 5e-2 * emb_ref.abs().max()
+
+
 def test_landmark_cnn_wrapper_ssl_calls(P):
     torch.manual_seed(1)
     cnn = P.face_landmark_4simmin_glo_loc(loss_type="CosFace", GPU_ID=None, num_class=10, num_patches=196, image_size=112,
