@@ -650,7 +650,7 @@ def bench_head(P, world, rank, dev, dist, args):
     return out
 
 
-def bench_dino_head(dev, iters=20, B=None, ncrops=None, K=None, D=256):
+def bench_dino_head(dev, iters=20, B=None, ncrops=None, K=None, D=256, fused_only=False):
     """DINOHead.last_layer (weight-normed 256 -> 65536) fused with the DINO loss
     (lafs_cvpr2024_b200/dino_head.py) against the unfused form of the same work on the same GPU: cuBLAS bf16
     last-layer GEMMs that write the [(ncrops+2)B, K] logits + this repo's DINO loss kernels on those logits + autograd
@@ -738,6 +738,8 @@ def bench_dino_head(dev, iters=20, B=None, ncrops=None, K=None, D=256):
                     "logit_bytes_in_hbm": 0, "probability_bytes_written": probs,
                     "note": "no [rows, K] logits or fp32 gradient in HBM; bf16 probabilities written once by the "
                             "recomputing GEMM (teacher rows in the forward, student rows in the backward)"}
+    if fused_only:
+        return out
     try:
         ms_u, mode_u = graph_time(unfused_step)
         loss_u = float(unfused_step())

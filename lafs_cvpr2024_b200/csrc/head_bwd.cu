@@ -619,9 +619,10 @@ extern "C" int lafs_head_bwd_embed(const void* grad_bf16, long long ldg, const v
   p.m_tiles = (B + 127) / 128; p.n_tiles = (D + 255) / 256;
   p.kblocks_total = (C_local + 63) / 64;
   p.out = (float*)workspace; p.ldo = D; p.split_stride = (long long)B * D;
-  // W_hat multicast width (LAFS_DE_CLUSTER: 1, 2 or 4): the widest cluster shape that still fills
-  // most of the machine with one wave of (M group, N tile, K split) work items
-  int want = 4;
+  // W_hat multicast width (LAFS_DE_CLUSTER: 1, 2 or 4).  Measured on B200 (round 2): pairs are never slower than
+  // quads -- B=1024, C=205990, D=512: 206 us (2) / 222 us (4) / 228 us (1); B=512, C=93431: 64.5 us for all three;
+  // the fused DINO head's two calls (1536 / 512 rows, K=65536, D=256): 0.4157 ms (2) / 0.421 ms (4) per step
+  int want = 2;
   if (const char* e = getenv("LAFS_DE_CLUSTER")) want = atoi(e);
   int cl = 1, nclusters = kNumSMs;
   if (want >= 4 && p.m_tiles % 4 == 0) {

@@ -48,6 +48,20 @@ def _one(dev):
     return t
 
 
+def _overlap_enabled():
+    """LAFS_DH_OVERLAP=0: everything on the calling stream (measurement / debugging)."""
+    import os
+    return os.environ.get("LAFS_DH_OVERLAP", "1") not in ("", "0")
+
+
+def _side_stream(dev):
+    key = ("side", dev)
+    t = _const_cache.get(key)
+    if t is None:
+        t = _const_cache[key] = torch.cuda.Stream(device=dev)
+    return t
+
+
 def _ld_probs(K):
     """row pitch of the bf16 probability matrix: a multiple of 16 elements (32-byte rows: 256-bit stores)."""
     return (K + 15) // 16 * 16
@@ -116,23 +130,40 @@ def dino_head_forward(xs, xt, vs, gs, vt, gt, center, ncrops, inv_ts, inv_tt, ke
     gt_c = None if gt is None else gt.detach().float().contiguous().view(-1)
     c = center.detach().float().contiguous().view(-1)
 
-    # teacher operands: [x_hat | 1 1 1 | 0], column sums of x_hat, [w | -centre split | 0] (+ logit column sums)
+    # every buffer is allocated on the calling stream; the teacher's operand preparation (HBM-bound, ~60 us at the
+    # reference size) then runs on a side stream under the student's preparation and statistics GEMM
     xt_hat = torch.empty(rt, Dt, dtype=torch.bfloat16, device=dev)
-    _lib.call("lafs_dh_prep_rows", xt_c.data_ptr(), _lib.dtype_code(xt_c), rt, D, Dt, xt_hat.data_ptr(), None, st)
     xsum = torch.empty(D, dtype=torch.float32, device=dev)
-    _lib.call("lafs_dh_xsum", xt_hat.data_ptr(), rt, D, Dt, xsum.data_ptr(), st)
     wt = torch.empty(K, Dt, dtype=torch.bfloat16, device=dev)
     colsum = torch.empty(K, dtype=torch.float32, device=dev)
-    _lib.call("lafs_dh_prep_weight", vt_c.data_ptr(), _lib.ptr(gt_c), c.data_ptr(), xsum.data_ptr(), K, D, Dt,
-              wt.data_ptr(), None, colsum.data_ptr(), st)
-    # student operands
     xs_hat = torch.empty(rs, D, dtype=torch.bfloat16, device=dev)
     inv_xs = torch.empty(rs, dtype=torch.float32, device=dev)
-    _lib.call("lafs_dh_prep_rows", xs_c.data_ptr(), _lib.dtype_code(xs_c), rs, D, D, xs_hat.data_ptr(), inv_xs.data_ptr(), st)
     ws = torch.empty(K, D, dtype=torch.bfloat16, device=dev)
     inv_w = torch.empty(K, dtype=torch.float32, device=dev)
+    main = torch.cuda.current_stream()
+    side = _side_stream(dev) if _overlap_enabled() else None
+
+    def teacher_operands():
+        # [x_hat | 1 1 1 | 0], column sums of x_hat, [w | -centre split | 0] (+ logit column sums for the centre update)
+        q = _lib.stream()
+        _lib.call("lafs_dh_prep_rows", xt_c.data_ptr(), _lib.dtype_code(xt_c), rt, D, Dt, xt_hat.data_ptr(), None, q)
+        _lib.call("lafs_dh_xsum", xt_hat.data_ptr(), rt, D, Dt, xsum.data_ptr(), q)
+        _lib.call("lafs_dh_prep_weight", vt_c.data_ptr(), _lib.ptr(gt_c), c.data_ptr(), xsum.data_ptr(), K, D, Dt,
+                  wt.data_ptr(), None, colsum.data_ptr(), q)
+
+    if side is not None:
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            teacher_operands()
+    else:
+        teacher_operands()
+    # student operands, row lse of s/ts
+    _lib.call("lafs_dh_prep_rows", xs_c.data_ptr(), _lib.dtype_code(xs_c), rs, D, D, xs_hat.data_ptr(), inv_xs.data_ptr(), st)
     _lib.call("lafs_dh_prep_weight", vs_c.data_ptr(), _lib.ptr(gs_c), None, None, K, D, D, ws.data_ptr(),
               inv_w.data_ptr(), None, st)
+    lse2_s = _row_lse2(xs_hat, ws, rs, K, D, inv_ts)
+    if side is not None:
+        main.wait_stream(side)
 
     # teacher: row lse of (t - c)/tt, Q = softmax (bf16, the last 2B rows of the probability matrix), U = Q . W_s
     ldp = _ld_probs(K)
@@ -141,8 +172,6 @@ def dino_head_forward(xs, xt, vs, gs, vt, gt, center, ncrops, inv_ts, inv_tt, ke
     lse2_t = _row_lse2(xt_hat, wt, rt, K, Dt, inv_tt)
     _probs(xt_hat, wt, rt, K, Dt, inv_tt, lse2_t, Q, ldp)
     U = _probs_times(Q, ldp, ws, rt, K, D)
-    # student: row lse of s/ts; loss
-    lse2_s = _row_lse2(xs_hat, ws, rs, K, D, inv_ts)
     loss = torch.empty((), dtype=torch.float32, device=dev)
     sample_loss = torch.empty(B, dtype=torch.float32, device=dev)
     _lib.call("lafs_dh_loss", lse2_s.data_ptr(), U.data_ptr(), xs_hat.data_ptr(), B, ncrops, D, float(inv_ts),

@@ -102,13 +102,14 @@ def test_full_precision_model_keeps_fp32_patch_embedding(P):
         emb = m.cuda()(x.cuda())
     # fp32 everywhere: 10x tighter than the bf16 path's 2e-2 (what is left is the cuDNN / CPU difference of the trunk)
     assert (emb.cpu() - emb_ref).abs().max() <= 2e-3 * emb_ref.abs().max()
+    proj = torch.randn(emb_ref.shape[1], generator=torch.Generator().manual_seed(2))   # the output is LayerNorm'ed:
     e = m(x.cuda())                                   # eval mode (the landmark head has a Dropout), gradients on
-    e.square().mean().backward()
+    (e @ proj.cuda()).sum().backward()                # a random projection has a real gradient, e.square().mean() has none
     er, _ = oracle_forward(ref, x)
-    er.square().mean().backward()
+    (er @ proj).sum().backward()
     assert (e.detach().cpu() - er.detach()).abs().max() <= 2e-3 * er.detach().abs().max()
     gw, gr = m.patch_to_embedding.weight.grad.cpu(), ref.patch_to_embedding.weight.grad
-    assert (gw - gr).abs().max() <= 5e-3 * gr.abs().max()
+    assert (gw - gr).abs().max() <= 1e-2 * gr.abs().max()
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
         emb_ac = m(x.cuda())
     assert (emb_ac.float().cpu() - emb_ref).abs().max() <= 5e-2 * emb_ref.abs().max()

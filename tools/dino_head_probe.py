@@ -14,4 +14,5 @@ if __name__ == "__main__":
     torch.backends.cuda.matmul.allow_tf32 = False
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
-    print(json.dumps(bench.bench_dino_head(dev, 20, *a)))
+    fused_only = os.environ.get("LAFS_PROBE_FUSED_ONLY", "0") not in ("", "0")
+    print(json.dumps(bench.bench_dino_head(dev, 20, *a, fused_only=fused_only)))
