@@ -46,3 +46,18 @@ def test_committed_profiles_of_our_arm_follow_the_contract():
         assert not ({"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(d["clocks"]["reasons"]))
         if d["n_gpus"] == 1:
             assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
+
+
+def test_round2_profiles_carry_the_parity_and_fused_head_evidence():
+    """what DESIGN.md quotes from profiles/: sharded-vs-unsharded head parity at every N > 1, and the fused
+    DINOHead-tail + loss leg next to its unfused form at N = 1."""
+    for n in (2, 4, 8):
+        d = json.loads(open(os.path.join(ROOT, "profiles", f"r02_bench_n{n}.json")).read().strip().splitlines()[-1])
+        assert d["n_gpus"] == n
+        for name, h in d["head"].items():
+            assert h["shards"] == n and 0 <= h["parity_max_rel"] <= 2e-3, (n, name, h.get("parity_max_rel"))
+    d = json.loads(open(os.path.join(ROOT, "profiles", "r02_bench_n1.json")).read().strip().splitlines()[-1])
+    leg = d["extras"]["dino_head_fused(last_layer+loss)"]
+    assert leg["out_dim"] == 65536 and leg["B"] == 256 and leg["fused"]["logit_bytes_in_hbm"] == 0
+    assert leg["fused"]["ms_fwd_bwd"] < leg["unfused_same_gpu"]["ms_fwd_bwd"]
+    assert leg["loss_rel_diff_fused_vs_unfused"] <= 1e-3
