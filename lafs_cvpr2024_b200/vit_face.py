@@ -372,13 +372,22 @@ class face_landmark_4simmin_glo_loc(nn.Module):
         else:
             theta = self.landmarks(x, Random_prob, return_prob, ran_sample)
             self.theta = theta
+            num_land = self._keep_num(x.shape[-2], theta.shape[1], Random_prob and not return_prob)
         if return_land:
             return theta, x
         src = x if x_Aug is None else x_Aug
-        n = theta.shape[1]
-        r = int(math.isqrt(n))
         from .patches import extract_patches_pytorch_gridsample
-        return theta, extract_patches_pytorch_gridsample(src, theta, self.patch_shape, r * r)
+        return theta, extract_patches_pytorch_gridsample(src, theta[:, :num_land], self.patch_shape, num_land)
+
+    def _keep_num(self, imgshape, n_theta, resampled):
+        """How many of theta's landmarks the reference hands to the extractor (ViT_face.py:1319-1325,1363-1385):
+        all of a re-sampled set (36 or row_num^2); otherwise num_patches for the 144 / 196-patch models on 112-pixel
+        faces and (H / p)^2 -- the FIRST that many -- for any other input size."""
+        if resampled:
+            return n_theta
+        if self.num_patches in (144, 196) and imgshape == 112:
+            return self.num_patches
+        return (imgshape // self.patch_size) ** 2
 
     def forward_tokens(self, x, x_Aug=None, Random_prob=False, return_prob=False, ran_sample=False):
         """theta and the '(p1 p2 c)' token tensor [B,n,192] directly (fuses lafs_train.py:535-538)."""

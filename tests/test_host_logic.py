@@ -75,3 +75,15 @@ def test_deferred_logits_hand_over():
     ht.fused_loss = True
     with pytest.raises(RuntimeError, match="no CPU fallback"):  # the fused path is CUDA-only, like every kernel path
         crit(d, ht(torch.randn(4, 24)), 0)
+
+
+def test_landmark_cnn_keep_num_rule():
+    """ViT_face.py:1319-1325,1363-1385: which landmarks reach the patch extractor."""
+    import lafs_cvpr2024_b200 as P
+    kw = dict(loss_type="None", GPU_ID=None, num_class=2, image_size=112, patch_size=8, dim=64, depth=1, heads=2,
+              mlp_dim=32, stn=torch.nn.Identity())
+    m196 = P.face_landmark_4simmin_glo_loc(num_patches=196, **kw)
+    m144 = P.face_landmark_4simmin_glo_loc(num_patches=144, **kw)
+    assert m196._keep_num(112, 196, False) == 196 and m144._keep_num(112, 144, False) == 144
+    assert m196._keep_num(96, 196, False) == 144            # other input sizes: the first (H/p)^2 landmarks
+    assert m196._keep_num(112, 36, True) == 36 and m196._keep_num(112, 196, True) == 196   # re-sampled sets are kept whole
