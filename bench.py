@@ -422,7 +422,8 @@ def run_ours(args):
     # beyond the centre all-reduce already measured above: reported at N = 1) -------------------------------------
     if world == 1:
         try:
-            extras["dino_head_fused(last_layer+loss)"] = bench_dino_head(dev, iters=max(5, min(args.steps, 20)))
+            extras["dino_head_fused(last_layer+loss)"] = bench_dino_head(dev, iters=max(5, min(args.steps, 20)),
+                                                                         cpu_ref=not args.no_cpu)
         except Exception as e:
             extras["dino_head_fused_error"] = str(e).splitlines()[0][:160]
             torch.cuda.synchronize()
@@ -650,7 +651,7 @@ def bench_head(P, world, rank, dev, dist, args):
     return out
 
 
-def bench_dino_head(dev, iters=20, B=None, ncrops=None, K=None, D=256, fused_only=False):
+def bench_dino_head(dev, iters=20, B=None, ncrops=None, K=None, D=256, fused_only=False, cpu_ref=False):
     """DINOHead.last_layer (weight-normed 256 -> 65536) fused with the DINO loss
     (lafs_cvpr2024_b200/dino_head.py) against the unfused form of the same work on the same GPU: cuBLAS bf16
     last-layer GEMMs that write the [(ncrops+2)B, K] logits + this repo's DINO loss kernels on those logits + autograd
@@ -755,7 +756,26 @@ def bench_dino_head(dev, iters=20, B=None, ncrops=None, K=None, D=256, fused_onl
         torch.cuda.synchronize()
     del dl
     torch.cuda.empty_cache()
+    if cpu_ref:
+        out.update(dino_head_cpu_reference(B, ncrops, K, D))
     return out
+
+
+def dino_head_cpu_reference(B, ncrops, K, D):
+    """The reference's own modules for the fused-head leg's work on the host cores (a reported baseline, bounded:
+    3 steps of ~1.5 s).  Never raises: the measured line must not be lost to a baseline leg."""
+    if not _reference_available():
+        return {}
+    try:
+        from oracle import ref_step
+        torch.set_num_threads(os.cpu_count() or 1)
+        sec, loss_c = ref_step.dino_head_reference_step("cpu", B, ncrops, K, D, iters=2)
+        return {"cpu_reference": {"ms_fwd_bwd": round(sec * 1e3, 1), "cores": torch.get_num_threads(), "kind": "reference",
+                                  "loss": loss_c, "sample": "vision_transformer.DINOHead.last_layer on F.normalize'd "
+                                  "features (student + teacher) + lafs_train.DINOLoss forward/backward, fp32, "
+                                  "median of 2 steps after one warm-up, full size"}}
+    except Exception as e:
+        return {"cpu_reference_error": str(e).splitlines()[0][:160]}
 
 
 HEAD_PARITY_TOL = 2e-3     # max-norm relative; the two runs share operands and lse up to fp32 summation order

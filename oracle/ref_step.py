@@ -202,3 +202,38 @@ def student_update_reference_step(device, param_shapes, iters=3, seed=3):
         if i > 0:
             ts.append(time.perf_counter() - t0)
     return float(np.median(ts))
+
+
+def dino_head_reference_step(device, B, ncrops, K, D, iters=2, seed=11):
+    """The reference's DINOHead tail + DINOLoss from the bottleneck features, forward + backward, on `device`:
+    x = F.normalize(x); x = last_layer(x) (vision_transformer.py:298-300, weight-normed Linear built by the reference's
+    own DINOHead constructor) for the student (all crops) and the teacher (2 global crops), L.DINOLoss.forward
+    (+ update_center) and loss.backward() (lafs_train.py:583,600,643-679).  Returns (seconds per step, loss)."""
+    import warnings
+    ns = ref_harness.load()
+    dev = torch.device(device)
+    torch.manual_seed(seed)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        hs = ns.vt.DINOHead(D, K, nlayers=1, bottleneck_dim=D).to(dev)      # mlp = one Linear (not timed), last_layer D -> K
+        ht = ns.vt.DINOHead(D, K, nlayers=1, bottleneck_dim=D).to(dev)
+    crit = ns.L.DINOLoss(K, ncrops, 0.04, 0.04, 0, 1).to(dev)
+    xs = torch.randn(ncrops * B, D, device=dev, requires_grad=True)
+    xt = torch.randn(2 * B, D, device=dev)
+    ts = []
+    for i in range(iters + 1):
+        xs.grad = None
+        hs.zero_grad(set_to_none=True)
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            t_out = ht.last_layer(nn.functional.normalize(xt, dim=-1, p=2))
+        s_out = hs.last_layer(nn.functional.normalize(xs, dim=-1, p=2))
+        loss = crit(s_out, t_out, 0)
+        loss.backward()
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+        if i > 0:
+            ts.append(time.perf_counter() - t0)
+    return float(np.median(ts)), float(loss.detach())

@@ -61,3 +61,16 @@ def test_round2_profiles_carry_the_parity_and_fused_head_evidence():
     assert leg["out_dim"] == 65536 and leg["B"] == 256 and leg["fused"]["logit_bytes_in_hbm"] == 0
     assert leg["fused"]["ms_fwd_bwd"] < leg["unfused_same_gpu"]["ms_fwd_bwd"]
     assert leg["loss_rel_diff_fused_vs_unfused"] <= 1e-3
+
+
+def test_fused_head_cpu_reference_leg_runs_the_reference():
+    """bench.py's host-core baseline for the fused DINO-head leg: the reference's DINOHead tail + DINOLoss (small size
+    here); it must report instead of raising."""
+    sys.path.insert(0, ROOT)
+    import bench
+    out = bench.dino_head_cpu_reference(4, 4, 1024, 64)
+    if os.path.isfile("/root/reference/lafs_train.py") or os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "lafs_train.py")):
+        cb = out["cpu_reference"]
+        assert cb["kind"] == "reference" and cb["ms_fwd_bwd"] > 0 and cb["cores"] >= 1 and 0 < cb["loss"] < 20
+    else:
+        assert out == {}
