@@ -8,7 +8,7 @@ last_layer -> DINOLoss path: the [(ncrops+2)B, out_dim] logit
       state-dict keys mlp.*, last_layer.weight_g, last_layer.weight_v   (as the reference's checkpoints)
 
     DINOLoss.forward(student_output, teacher_output, epoch) accepts DeferredLogits for both arguments and then
-    runs `dino_head_loss` below: loss, centre update and the gradients w.r.t. the student's bottleneck features
+    runs `fused_dino_loss` below: loss, centre update and the gradients w.r.t. the student's bottleneck features
     and last_layer.weight_v / weight_g, identical (to bf16-operand rounding) to
         dino_loss(student_head.last_layer(F.normalize(xs)), teacher_head.last_layer(F.normalize(xt)), epoch)
     so lafs_train.py:581-583 runs unchanged:  teacher(images[:2]) / student(images) return what their head returns
